@@ -1,0 +1,229 @@
+"""ctypes bindings for the TEST-ONLY CPU oracle (oracle/liboracle.so, oracle/_ref/libnep_cpu_ref.so).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+import this module.  The product path (gpumd_b200/) never does.
+"""
+import ctypes as C
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+_LIB = None
+_REF = None
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int)
+
+
+def build():
+    """(Re)build liboracle.so and, when /root/reference is present, _ref/libnep_cpu_ref.so."""
+    subprocess.run(["make", "-C", str(HERE), "all"], check=True, capture_output=True)
+
+
+def _d(a):
+    return None if a is None else a.ctypes.data_as(_dp)
+
+
+def _i(a):
+    return None if a is None else a.ctypes.data_as(_ip)
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        path = HERE / "liboracle.so"
+        if not path.exists():
+            build()
+        L = C.CDLL(str(path))
+        L.oracle_nep_load.restype = C.c_void_p
+        L.oracle_nep_load.argtypes = [C.c_char_p]
+        L.oracle_nep_free.argtypes = [C.c_void_p]
+        L.oracle_nep_info.argtypes = [C.c_void_p, C.c_int]
+        L.oracle_nep_rc_radial_max.restype = C.c_double
+        L.oracle_nep_rc_radial_max.argtypes = [C.c_void_p]
+        L.oracle_nep_rc_angular_max.restype = C.c_double
+        L.oracle_nep_rc_angular_max.argtypes = [C.c_void_p]
+        L.oracle_nep_compute.argtypes = [
+            C.c_void_p, C.c_int, C.c_int, _ip, _dp, _ip, _dp, _dp, _dp, _dp, _dp,
+            _ip, _ip, C.c_int, _ip, _ip, C.c_int]
+        L.oracle_neighbor_list.argtypes = [C.c_int, _dp, _ip, _dp, C.c_double, _ip, _ip, C.c_int]
+        L.oracle_lj_compute.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, _ip, _dp, _dp, _dp, _dp]
+        L.oracle_apply_pbc.argtypes = [C.c_int, _dp, _ip, _dp]
+        L.oracle_velocity_verlet.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp]
+        L.oracle_find_thermo.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp]
+        _LIB = L
+    return _LIB
+
+
+def _box(h, pbc):
+    h = np.ascontiguousarray(np.asarray(h, dtype=np.float64).reshape(9))
+    pbc = np.ascontiguousarray(np.asarray(pbc, dtype=np.int32).reshape(3))
+    return h, pbc
+
+
+class NepOracle:
+    """oracle_nep_* (plain-C restatement of src/force/nep.cu)."""
+
+    INFO = dict(num_types=0, dim=1, num_neurons=2, n_max_radial=3, n_max_angular=4,
+                basis_size_radial=5, basis_size_angular=6, L_max=7, num_L=8, MN_radial=9,
+                MN_angular=10, zbl=11, version=12)
+
+    def __init__(self, path):
+        self.L = lib()
+        self.h = self.L.oracle_nep_load(str(path).encode())
+        if not self.h:
+            raise RuntimeError(f"oracle: cannot load {path}")
+        self.info = {k: self.L.oracle_nep_info(self.h, v) for k, v in self.INFO.items()}
+        self.rc_radial = self.L.oracle_nep_rc_radial_max(self.h)
+        self.rc_angular = self.L.oracle_nep_rc_angular_max(self.h)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.L.oracle_nep_free(self.h)
+            self.h = None
+
+    def compute(self, type_, h, pbc, pos, precision=32, lists=False, descriptors=False):
+        """pos: (3,N) float64 SoA. Returns dict(pe[N], force[3,N], virial[9,N], ...)."""
+        n = int(np.asarray(type_).shape[0])
+        type_ = np.ascontiguousarray(type_, dtype=np.int32)
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(3 * n)
+        h, pbc = _box(h, pbc)
+        pe = np.zeros(n)
+        f = np.zeros(3 * n)
+        v = np.zeros(9 * n)
+        q = np.zeros(self.info["dim"] * n) if descriptors else None
+        mn_r = mn_a = 0
+        NNr = NLr = NNa = NLa = None
+        if lists:
+            mn_r, mn_a = max(self.info["MN_radial"], 1) * 4, max(self.info["MN_angular"], 1) * 4
+            NNr = np.zeros(n, np.int32)
+            NLr = np.full(n * mn_r, -1, np.int32)
+            NNa = np.zeros(n, np.int32)
+            NLa = np.full(n * mn_a, -1, np.int32)
+        rc = self.L.oracle_nep_compute(
+            self.h, precision, n, _i(type_), _d(h), _i(pbc), _d(pos), _d(pe), _d(f), _d(v), _d(q),
+            _i(NNr), _i(NLr), mn_r, _i(NNa), _i(NLa), mn_a)
+        if rc != 0:
+            raise RuntimeError(f"oracle_nep_compute failed: {rc}")
+        out = dict(pe=pe, force=f.reshape(3, n), virial=v.reshape(9, n))
+        if descriptors:
+            out["q"] = q.reshape(self.info["dim"], n)
+        if lists:
+            out.update(NN_radial=NNr, NL_radial=NLr.reshape(n, mn_r), NN_angular=NNa,
+                       NL_angular=NLa.reshape(n, mn_a))
+        return out
+
+
+def neighbor_list(h, pbc, pos, rc, mn=512):
+    L = lib()
+    n = pos.shape[1]
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(3 * n)
+    h, pbc = _box(h, pbc)
+    NN = np.zeros(n, np.int32)
+    NL = np.full(n * mn, -1, np.int32)
+    r = L.oracle_neighbor_list(n, _d(h), _i(pbc), _d(pos), float(rc), _i(NN), _i(NL), mn)
+    if r != 0:
+        raise RuntimeError(f"oracle_neighbor_list failed: {r}")
+    return NN, NL.reshape(n, mn)
+
+
+def lj_compute(para, type_, h, pbc, pos):
+    """para: (nt,nt,3) eps, sigma, cutoff."""
+    L = lib()
+    para = np.ascontiguousarray(para, dtype=np.float64)
+    nt = para.shape[0]
+    n = pos.shape[1]
+    type_ = np.ascontiguousarray(type_, dtype=np.int32)
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(3 * n)
+    h, pbc = _box(h, pbc)
+    pe, f, v = np.zeros(n), np.zeros(3 * n), np.zeros(9 * n)
+    r = L.oracle_lj_compute(nt, _d(para.reshape(-1)), n, _i(type_), _d(h), _i(pbc), _d(pos),
+                            _d(pe), _d(f), _d(v))
+    if r != 0:
+        raise RuntimeError(f"oracle_lj_compute failed: {r}")
+    return dict(pe=pe, force=f.reshape(3, n), virial=v.reshape(9, n))
+
+
+def apply_pbc(h, pbc, pos):
+    L = lib()
+    n = pos.shape[1]
+    out = np.ascontiguousarray(pos, dtype=np.float64).reshape(3 * n).copy()
+    h, pbc = _box(h, pbc)
+    L.oracle_apply_pbc(n, _d(h), _i(pbc), _d(out))
+    return out.reshape(3, n)
+
+
+def velocity_verlet(step1, dt, mass, pos, vel, force):
+    L = lib()
+    n = mass.shape[0]
+    p = np.ascontiguousarray(pos, dtype=np.float64).reshape(3 * n).copy()
+    v = np.ascontiguousarray(vel, dtype=np.float64).reshape(3 * n).copy()
+    f = np.ascontiguousarray(force, dtype=np.float64).reshape(3 * n)
+    m = np.ascontiguousarray(mass, dtype=np.float64)
+    L.oracle_velocity_verlet(int(step1), n, float(dt), _d(m), _d(p), _d(v), _d(f))
+    return p.reshape(3, n), v.reshape(3, n)
+
+
+def find_thermo(n_temp, volume, mass, pe, vel, virial):
+    L = lib()
+    n = mass.shape[0]
+    t = np.zeros(8)
+    L.oracle_find_thermo(
+        n, int(n_temp), float(volume), _d(np.ascontiguousarray(mass, dtype=np.float64)),
+        _d(np.ascontiguousarray(pe, dtype=np.float64)),
+        _d(np.ascontiguousarray(vel, dtype=np.float64).reshape(3 * n)),
+        _d(np.ascontiguousarray(virial, dtype=np.float64).reshape(9 * n)), _d(t))
+    return t
+
+
+# ---------------------------------------------------------------- the reference's own NEP_CPU
+
+def ref_available():
+    return (HERE / "_ref" / "libnep_cpu_ref.so").exists()
+
+
+def ref():
+    global _REF
+    if _REF is None:
+        R = C.CDLL(str(HERE / "_ref" / "libnep_cpu_ref.so"))
+        R.refnep_load.restype = C.c_void_p
+        R.refnep_load.argtypes = [C.c_char_p]
+        R.refnep_free.argtypes = [C.c_void_p]
+        R.refnep_compute.argtypes = [C.c_void_p, C.c_int, _ip, _dp, _dp, _dp, _dp, _dp]
+        _REF = R
+    return _REF
+
+
+class RefNepCpu:
+    """The reference's vendored NEP_CPU (tools/.../nep.cpp NEP3::compute), FP64, PBC in all
+    three directions (it has no pbc argument)."""
+
+    def __init__(self, path):
+        self.R = ref()
+        # NEP_CPU prints the model summary to stdout in its constructor; silence it
+        fd = os.dup(1)
+        devnull = os.open(os.devnull, os.O_WRONLY)
+        os.dup2(devnull, 1)
+        try:
+            self.h = self.R.refnep_load(str(path).encode())
+        finally:
+            os.dup2(fd, 1)
+            os.close(fd)
+            os.close(devnull)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.R.refnep_free(self.h)
+            self.h = None
+
+    def compute(self, type_, h, pos):
+        n = int(np.asarray(type_).shape[0])
+        type_ = np.ascontiguousarray(type_, dtype=np.int32)
+        pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(3 * n)
+        h = np.ascontiguousarray(np.asarray(h, dtype=np.float64).reshape(9))
+        pe, f, v = np.zeros(n), np.zeros(3 * n), np.zeros(9 * n)
+        self.R.refnep_compute(self.h, n, _i(type_), _d(h), _d(pos), _d(pe), _d(f), _d(v))
+        return dict(pe=pe, force=f.reshape(3, n), virial=v.reshape(9, n))
