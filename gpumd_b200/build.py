@@ -1,0 +1,71 @@
+"""Build libb200md.so (hand-written CUDA for sm_100a) in-tree with nvcc.
+
+    python -m gpumd_b200.build          # or gpumd_b200.build.build_lib()
+
+The shared library lands at gpumd_b200/libb200md.so (git-ignored, travels to the GPU box with the
+gpurun snapshot).  nvcc cross-compiles without a GPU.
+"""
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+PKG = Path(__file__).resolve().parent
+CSRC = PKG / "csrc"
+LIB = PKG / "libb200md.so"
+OBJ = PKG / "build"
+
+CU_SOURCES = ["b2_host.cu", "b2_neighbor.cu", "b2_nep.cu", "b2_md.cu"]
+CPP_SOURCES = ["b2_nep_model.cpp"]
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-Xcompiler", "-fPIC",
+]
+
+
+def _nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found: libb200md cannot be built (there is no CPU fallback)")
+    return exe
+
+
+def _stale(target, deps):
+    if not target.exists():
+        return True
+    t = target.stat().st_mtime
+    return any(d.stat().st_mtime > t for d in deps)
+
+
+def build_lib(force=False, verbose=False):
+    nvcc = _nvcc()
+    OBJ.mkdir(exist_ok=True)
+    headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "b200md.h"]
+    jobs = []
+    objs = []
+    for src in CU_SOURCES + CPP_SOURCES:
+        s = CSRC / src
+        o = OBJ / (s.stem + ".o")
+        objs.append(o)
+        if force or _stale(o, [s] + headers):
+            jobs.append([nvcc] + NVCC_FLAGS + ["-c", str(s), "-o", str(o)])
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + r.stdout + r.stderr)
+        if verbose and (r.stdout or r.stderr):
+            print(r.stdout + r.stderr)
+
+    with ThreadPoolExecutor(max_workers=4) as ex:
+        list(ex.map(run, jobs))
+    if force or jobs or not LIB.exists():
+        run([nvcc, "-shared", "-Xcompiler", "-fPIC", "-gencode", "arch=compute_100a,code=sm_100a",
+             "-o", str(LIB)] + [str(o) for o in objs] + ["-lcudart"])
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build_lib(force="--force" in sys.argv, verbose=True))

@@ -1,0 +1,151 @@
+// b2_common.cuh -- shared definitions for libb200md (sm_100a).
+//
+// Kernel BODIES in this library are written as `B2_HD` functions of (thread index, params) so
+// that tests/emu can compile the very same arithmetic for the host and check it against the
+// oracle without a GPU.  The emulation build is test infrastructure only: the shipped library
+// contains no host execution path (b2_api.cu returns an error if CUDA is unavailable).
+#pragma once
+#include <math.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define B2_HD __device__ __forceinline__
+#define B2_LDG(p) __ldg(p)
+#else
+#define B2_HD static inline
+#define B2_LDG(p) (*(p))
+#endif
+
+#if defined(__CUDA_ARCH__)
+#define B2_ATOMIC_OR(p, v) atomicOr((p), (v))
+#else
+#define B2_ATOMIC_OR(p, v) (*(p) |= (v))
+#endif
+
+// Box passed by value to kernels: GPUMD's Box::cpu_h / float_h (src/model/box.cuh:18-35).
+struct B2Box {
+  double h[18]; // h[0..8] row-major (lattice vectors are columns), h[9..17] inverse
+  float hf[18];
+  int pbc[3];
+  int ortho;
+  double thickness[3];
+  double volume;
+};
+
+// sorted-atom record: one 32-byte sector per neighbour gather
+struct __attribute__((aligned(32))) B2Atom {
+  double x, y, z;
+  int type;
+  int pad;
+};
+
+// FP32 minimum image with the reference's semantics (src/model/box.cuh:84-129): orthogonal boxes
+// shift once by +-L when |x| > L/2; triclinic boxes go through fractional coordinates.  The fma
+// nesting of the triclinic branch is the one nvcc's default contraction produces for the
+// reference expression a*x + b*y + c*z = fma(c,z, fma(a,x, b*y)).
+B2_HD void b2_mic(const B2Box& b, float& x, float& y, float& z)
+{
+  if (b.ortho) {
+    if (b.pbc[0]) {
+      const float L = b.hf[0], hl = L * 0.5f;
+      if (x < -hl)
+        x += L;
+      else if (x > hl)
+        x -= L;
+    }
+    if (b.pbc[1]) {
+      const float L = b.hf[4], hl = L * 0.5f;
+      if (y < -hl)
+        y += L;
+      else if (y > hl)
+        y -= L;
+    }
+    if (b.pbc[2]) {
+      const float L = b.hf[8], hl = L * 0.5f;
+      if (z < -hl)
+        z += L;
+      else if (z > hl)
+        z -= L;
+    }
+  } else {
+    float sx = fmaf(b.hf[11], z, fmaf(b.hf[9], x, b.hf[10] * y));
+    float sy = fmaf(b.hf[14], z, fmaf(b.hf[12], x, b.hf[13] * y));
+    float sz = fmaf(b.hf[17], z, fmaf(b.hf[15], x, b.hf[16] * y));
+    if (b.pbc[0])
+      sx -= nearbyintf(sx);
+    if (b.pbc[1])
+      sy -= nearbyintf(sy);
+    if (b.pbc[2])
+      sz -= nearbyintf(sz);
+    x = fmaf(b.hf[2], sz, fmaf(b.hf[0], sx, b.hf[1] * sy));
+    y = fmaf(b.hf[5], sz, fmaf(b.hf[3], sx, b.hf[4] * sy));
+    z = fmaf(b.hf[8], sz, fmaf(b.hf[6], sx, b.hf[7] * sy));
+  }
+}
+
+// FP64 minimum image (src/model/box.cuh:37-82), used where the reference uses it
+// (gpu_find_force_many_body, src/force/potential.cu:211-217).
+B2_HD void b2_mic(const B2Box& b, double& x, double& y, double& z)
+{
+  if (b.ortho) {
+    if (b.pbc[0]) {
+      const double L = b.h[0];
+      if (x < -L * 0.5)
+        x += L;
+      else if (x > L * 0.5)
+        x -= L;
+    }
+    if (b.pbc[1]) {
+      const double L = b.h[4];
+      if (y < -L * 0.5)
+        y += L;
+      else if (y > L * 0.5)
+        y -= L;
+    }
+    if (b.pbc[2]) {
+      const double L = b.h[8];
+      if (z < -L * 0.5)
+        z += L;
+      else if (z > L * 0.5)
+        z -= L;
+    }
+  } else {
+    double sx = b.h[9] * x + b.h[10] * y + b.h[11] * z;
+    double sy = b.h[12] * x + b.h[13] * y + b.h[14] * z;
+    double sz = b.h[15] * x + b.h[16] * y + b.h[17] * z;
+    if (b.pbc[0])
+      sx -= nearbyint(sx);
+    if (b.pbc[1])
+      sy -= nearbyint(sy);
+    if (b.pbc[2])
+      sz -= nearbyint(sz);
+    x = b.h[0] * sx + b.h[1] * sy + b.h[2] * sz;
+    y = b.h[3] * sx + b.h[4] * sy + b.h[5] * sz;
+    z = b.h[6] * sx + b.h[7] * sy + b.h[8] * sz;
+  }
+}
+
+// Pair displacement exactly as every reference kernel forms it (e.g. src/force/nep.cu:467-470):
+// FP64 subtract, narrow to FP32, FP32 minimum image.
+B2_HD void b2_r12(
+  const B2Box& b, const B2Atom& a1, const B2Atom& a2, float& x12, float& y12, float& z12)
+{
+  x12 = (float)(a2.x - a1.x);
+  y12 = (float)(a2.y - a1.y);
+  z12 = (float)(a2.z - a1.z);
+  b2_mic(b, x12, y12, z12);
+}
+
+// d^2 with the fma nesting nvcc emits for `x*x + y*y + z*z` (checked on the PTX of the reference
+// expression, DESIGN.md "FP32 membership"): fma(z,z, fma(x,x, y*y)).  Membership tests against a
+// cutoff use this so neighbour sets are bit-identical to the reference's.
+B2_HD float b2_d2(float x, float y, float z) { return fmaf(z, z, fmaf(x, x, y * y)); }
+
+// error bits latched on the device
+enum {
+  B2_ERR_SKIN_OVERFLOW = 1,
+  B2_ERR_RADIAL_OVERFLOW = 2,
+  B2_ERR_ANGULAR_OVERFLOW = 4,
+  B2_ERR_CELL_RANGE = 8,
+};

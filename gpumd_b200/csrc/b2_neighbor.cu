@@ -1,0 +1,303 @@
+// b2_neighbor.cu -- kernels and host driver for the cell-sorted skin list (see b2_neighbor.cuh).
+#include "../../include/b200md.h"
+#include "b2_host.h"
+#include "b2_neighbor.cuh"
+#include "b2_neighbor_host.h"
+
+namespace b2 {
+
+namespace {
+
+constexpr int BLK = 256;
+
+__global__ void k_init_perm(int n, int* perm, int* flags)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    perm[i] = i;
+  if (i == 0) {
+    flags[0] = 1; // first call always builds
+    flags[1] = 0;
+    flags[2] = 0;
+  }
+}
+
+__global__ void k_force_rebuild(int* flags) { flags[0] = 1; }
+
+__global__ void __launch_bounds__(BLK) k_pack_check(
+  B2NeighborView v, B2Box box, const int* __restrict__ type, const double* __restrict__ x,
+  const double* __restrict__ y, const double* __restrict__ z, float trigger_d2)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < v.n)
+    b2_body_pack_check(i, v, box, type, x, y, z, trigger_d2);
+}
+
+// ---- everything below runs only when flags[0] != 0 -----------------------------------------
+
+__global__ void __launch_bounds__(BLK) k_zero_cells(B2NeighborView v, int ncell)
+{
+  if (!v.flags[0])
+    return;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncell) {
+    v.cell_count[c] = 0;
+    v.cell_fill[c] = 0;
+  }
+}
+
+__global__ void __launch_bounds__(BLK) k_cell_count(B2NeighborView v, B2Box box, B2Grid g)
+{
+  if (!v.flags[0])
+    return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < v.n) {
+    int cx, cy, cz;
+    const int c = b2_cell_of(box, g, v.atoms[i], &cx, &cy, &cz);
+    v.cell_of[i] = c;
+    atomicAdd(&v.cell_count[c], 1);
+  }
+}
+
+// single-block exclusive scan over the cell counts: tiles of 1024*4 with a running carry
+__global__ void __launch_bounds__(1024) k_scan_cells(B2NeighborView v, int ncell)
+{
+  if (!v.flags[0])
+    return;
+  __shared__ int warp_sums[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  if (tid == 0)
+    carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < ncell; base += 4096) {
+    const int idx = base + tid * 4;
+    int a[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      a[k] = (idx + k < ncell) ? v.cell_count[idx + k] : 0;
+    const int mine = a[0] + a[1] + a[2] + a[3];
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o)
+        incl += t;
+    }
+    if (lane == 31)
+      warp_sums[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+      int w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, w, o);
+        if (lane >= o)
+          w += t;
+      }
+      warp_sums[lane] = w; // inclusive over warps
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    int excl = carry + (wid ? warp_sums[wid - 1] : 0) + incl - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      if (idx + k < ncell)
+        v.cell_start[idx + k] = excl;
+      excl += a[k];
+    }
+    __syncthreads();
+    if (tid == 1023)
+      carry_s = carry + warp_sums[31];
+    __syncthreads();
+  }
+  if (tid == 0)
+    v.cell_start[ncell] = carry_s;
+}
+
+__global__ void __launch_bounds__(BLK) k_cell_fill(B2NeighborView v)
+{
+  if (!v.flags[0])
+    return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < v.n) {
+    const int c = v.cell_of[i];
+    const int slot = v.cell_start[c] + atomicAdd(&v.cell_fill[c], 1);
+    v.order_tmp[slot] = i;
+  }
+}
+
+__global__ void __launch_bounds__(BLK) k_sort_cells(B2NeighborView v, int ncell)
+{
+  if (!v.flags[0])
+    return;
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c < ncell)
+    b2_body_sort_cell(c, v);
+}
+
+__global__ void __launch_bounds__(BLK) k_commit(B2NeighborView v)
+{
+  if (!v.flags[0])
+    return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < v.n)
+    b2_body_commit(i, v);
+}
+
+__global__ void __launch_bounds__(128)
+  k_skin_list(B2NeighborView v, B2Box box, B2Grid g, float cutoff2)
+{
+  if (!v.flags[0])
+    return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < v.n)
+    b2_body_skin_list(i, v, box, g, cutoff2);
+}
+
+__global__ void k_rebuild_done(int* flags)
+{
+  if (flags[0]) {
+    flags[0] = 0;
+    flags[2] += 1;
+  }
+}
+
+} // namespace
+
+B2Grid make_grid(const B2Box& box, double cell_size)
+{
+  B2Grid g;
+  for (int d = 0; d < 3; ++d) {
+    int nb = (int)floor(box.thickness[d] / cell_size);
+    if (nb < 1)
+      nb = 1;
+    g.nb[d] = nb;
+    g.scale[d] = (double)nb;
+  }
+  g.ncell = g.nb[0] * g.nb[1] * g.nb[2];
+  return g;
+}
+
+int Neighbor::init(int num_atoms, double rc_, int mn_skin_)
+{
+  n = num_atoms;
+  rc = rc_;
+  mn_skin = mn_skin_;
+  B2_CUDA(atoms.reserve(n));
+  B2_CUDA(atoms_tmp.reserve(n));
+  B2_CUDA(snap.reserve((size_t)3 * n));
+  B2_CUDA(perm.reserve(n));
+  B2_CUDA(perm_tmp.reserve(n));
+  B2_CUDA(cell_of.reserve(n));
+  B2_CUDA(order_tmp.reserve(n));
+  B2_CUDA(nn_skin.reserve(n));
+  B2_CUDA(nl_skin.reserve((size_t)mn_skin * n));
+  B2_CUDA(flags.reserve(4));
+  B2_CUDA(cudaMemset(snap.p, 0, sizeof(double) * 3 * (size_t)n));
+  k_init_perm<<<grid_for(n, BLK), BLK>>>(n, perm.p, flags.p);
+  B2_LAUNCHED();
+  have_grid = false;
+  return B200MD_OK;
+}
+
+B2NeighborView Neighbor::view() const
+{
+  B2NeighborView v;
+  v.n = n;
+  v.mn_skin = mn_skin;
+  v.atoms = atoms.p;
+  v.atoms_tmp = atoms_tmp.p;
+  v.snap = snap.p;
+  v.perm = perm.p;
+  v.perm_tmp = perm_tmp.p;
+  v.cell_of = cell_of.p;
+  v.order_tmp = order_tmp.p;
+  v.cell_count = cell_count.p;
+  v.cell_fill = cell_fill.p;
+  v.cell_start = cell_start.p;
+  v.nn_skin = nn_skin.p;
+  v.nl_skin = nl_skin.p;
+  v.flags = flags.p;
+  return v;
+}
+
+int Neighbor::update(
+  const B2Box& box, const int* d_type, const double* d_pos, int n_in, cudaStream_t st)
+{
+  if (n_in != n) {
+    set_error("number of atoms differs from the value given at construction");
+    return B200MD_ERR_ARG;
+  }
+  // large-box requirement of the reference: nep.cu:1304-1312 (small boxes use explicit images)
+  for (int d = 0; d < 3; ++d) {
+    if (box.pbc[d] && box.thickness[d] <= 2.5 * (rc + skin)) {
+      set_error(
+        "periodic box thickness <= 2.5*(rc+1): this is the reference's small-box path "
+        "(nep_small_box.cuh), which libb200md does not implement");
+      return B200MD_ERR_SMALL_BOX;
+    }
+  }
+  const B2Grid g = make_grid(box, 0.5 * (rc + skin));
+  for (int d = 0; d < 3; ++d) {
+    if (box.pbc[d] && g.nb[d] < 5) {
+      set_error("internal: fewer than 5 cells in a periodic direction");
+      return B200MD_ERR_SMALL_BOX;
+    }
+  }
+  if ((size_t)g.ncell + 1 > cell_start.n) {
+    const size_t cap = (size_t)(g.ncell * 1.2) + 64;
+    B2_CUDA(cudaStreamSynchronize(st));
+    B2_CUDA(cell_count.reserve(cap));
+    B2_CUDA(cell_fill.reserve(cap));
+    B2_CUDA(cell_start.reserve(cap + 1));
+  }
+  if (have_grid && (g.nb[0] != grid.nb[0] || g.nb[1] != grid.nb[1] || g.nb[2] != grid.nb[2])) {
+    k_force_rebuild<<<1, 1, 0, st>>>(flags.p);
+    B2_LAUNCHED();
+  }
+  grid = g;
+  have_grid = true;
+
+  const B2NeighborView v = view();
+  const double* x = d_pos;
+  const double* y = d_pos + n;
+  const double* z = d_pos + 2 * (size_t)n;
+  const float trigger = (float)(skin * skin * 0.25);
+  const float cutoff = (float)((rc + skin) * (rc + skin));
+  const int gn = grid_for(n, BLK), gc = grid_for(g.ncell, BLK);
+
+  k_pack_check<<<gn, BLK, 0, st>>>(v, box, d_type, x, y, z, trigger);
+  B2_LAUNCHED();
+  k_zero_cells<<<gc, BLK, 0, st>>>(v, g.ncell);
+  B2_LAUNCHED();
+  k_cell_count<<<gn, BLK, 0, st>>>(v, box, g);
+  B2_LAUNCHED();
+  k_scan_cells<<<1, 1024, 0, st>>>(v, g.ncell);
+  B2_LAUNCHED();
+  k_cell_fill<<<gn, BLK, 0, st>>>(v);
+  B2_LAUNCHED();
+  k_sort_cells<<<gc, BLK, 0, st>>>(v, g.ncell);
+  B2_LAUNCHED();
+  k_commit<<<gn, BLK, 0, st>>>(v);
+  B2_LAUNCHED();
+  k_skin_list<<<grid_for(n, 128), 128, 0, st>>>(v, box, g, cutoff);
+  B2_LAUNCHED();
+  k_rebuild_done<<<1, 1, 0, st>>>(flags.p);
+  B2_LAUNCHED();
+  return B200MD_OK;
+}
+
+int Neighbor::check(cudaStream_t st, int* err_bits, int* rebuilds)
+{
+  int host[4] = {0, 0, 0, 0};
+  B2_CUDA(cudaMemcpyAsync(host, flags.p, sizeof(int) * 3, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  if (err_bits)
+    *err_bits = host[1];
+  if (rebuilds)
+    *rebuilds = host[2];
+  return B200MD_OK;
+}
+
+} // namespace b2

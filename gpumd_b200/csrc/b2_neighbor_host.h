@@ -1,0 +1,33 @@
+// b2_neighbor_host.h -- host-side owner of the cell-sorted skin list (see b2_neighbor.cuh).
+#pragma once
+#include "b2_host.h"
+#include "b2_neighbor.cuh"
+
+namespace b2 {
+
+B2Grid make_grid(const B2Box& box, double cell_size);
+
+class Neighbor
+{
+public:
+  int n = 0;
+  int mn_skin = 0;
+  double rc = 0.0;
+  double skin = 1.0; // src/force/neighbor.cuh:212
+  B2Grid grid;
+  bool have_grid = false;
+
+  DevBuf<B2Atom> atoms, atoms_tmp;
+  DevBuf<double> snap;
+  DevBuf<int> perm, perm_tmp, cell_of, order_tmp, cell_count, cell_fill, cell_start, nn_skin,
+    nl_skin, flags;
+
+  // Neighbor::initialize, src/force/neighbor.cu:824-833
+  int init(int num_atoms, double rc, int mn_skin);
+  // Neighbor::find_neighbor_global, src/force/neighbor.cu:756-800 (fully asynchronous here)
+  int update(const B2Box& box, const int* d_type, const double* d_pos, int n, cudaStream_t st);
+  int check(cudaStream_t st, int* err_bits, int* rebuilds);
+  B2NeighborView view() const;
+};
+
+} // namespace b2

@@ -1,0 +1,569 @@
+// b2_nep.cu -- NEP potential of libb200md: kernels (thin wrappers over the bodies in b2_nep.cuh),
+// template dispatch, device tables, and the C-ABI entry points b200md_nep_*.
+#include "../../include/b200md.h"
+#include "b2_host.h"
+#include "b2_neighbor_host.h"
+#include "b2_nep.cuh"
+#include "b2_nep_model.h"
+#include <cstring>
+#include <new>
+#include <vector>
+
+namespace b2 {
+
+namespace {
+
+constexpr int BLK = 128;
+constexpr int MLP_BLK = 256;
+
+__global__ void __launch_bounds__(BLK) k_split(B2NepView P, B2Box box)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.n)
+    b2_body_split(i, P, box);
+}
+
+template <int NT, int K1>
+__global__ void __launch_bounds__(BLK) k_desc_radial(B2NepView P, B2Box box)
+{
+  extern __shared__ float dyn_smem[];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.n)
+    b2_body_desc_radial<NT, K1>(i, P, box, dyn_smem, blockDim.x, threadIdx.x);
+}
+
+template <int K1, int NCH>
+__global__ void __launch_bounds__(BLK) k_desc_angular(B2NepView P, B2Box box)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.n)
+    b2_body_desc_angular<K1, NCH>(i, P, box);
+}
+
+// One tile of MLP_BLK consecutive (cell-sorted) atoms per block.  The tile is counting-sorted by
+// type in shared memory so that the lanes of a warp read the same weight rows (uniform loads).
+template <int DIMP>
+__global__ void __launch_bounds__(MLP_BLK) k_mlp(B2NepView P)
+{
+  __shared__ int order[MLP_BLK];
+  __shared__ int cnt[B2_MAX_TYPES + 1];
+  const int tid = threadIdx.x;
+  const int base = blockIdx.x * MLP_BLK;
+  const int i = base + tid;
+  int mine = i;
+  if (P.nt > 1) {
+    if (tid <= B2_MAX_TYPES)
+      cnt[tid] = 0;
+    __syncthreads();
+    int t = 0, rank = 0;
+    if (i < P.n) {
+      t = P.atoms[i].type;
+      rank = atomicAdd(&cnt[t], 1);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int run = 0;
+      for (int k = 0; k < P.nt; ++k) {
+        const int c = cnt[k];
+        cnt[k] = run;
+        run += c;
+      }
+    }
+    __syncthreads();
+    if (i < P.n)
+      order[cnt[t] + rank] = i;
+    __syncthreads();
+    if (i < P.n)
+      mine = order[tid];
+  }
+  if (i < P.n)
+    b2_body_mlp<DIMP>(mine, P);
+}
+
+template <int NT, int K1>
+__global__ void __launch_bounds__(BLK) k_force_radial(B2NepView P, B2Box box)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.n)
+    b2_body_force_radial<NT, K1>(i, P, box);
+}
+
+template <int K1>
+__global__ void __launch_bounds__(BLK) k_force_angular(B2NepView P, B2Box box)
+{
+  extern __shared__ float dyn_smem[];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.n)
+    b2_body_force_angular<K1>(i, P, box, dyn_smem, blockDim.x, threadIdx.x);
+}
+
+__global__ void __launch_bounds__(BLK) k_reduce_angular(B2NepView P, B2Box box)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.n)
+    b2_body_reduce_angular(i, P, box);
+}
+
+__global__ void __launch_bounds__(BLK) k_zbl(B2NepView P, B2Box box)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.n)
+    b2_body_zbl(i, P, box);
+}
+
+__global__ void __launch_bounds__(256) k_unpack(
+  int n, const int* __restrict__ perm, const double* __restrict__ acc, double* pe, double* force,
+  double* virial)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    b2_body_unpack(i, n, perm, acc, pe, force, virial);
+}
+
+// parity hooks ---------------------------------------------------------------------------------
+__global__ void k_export_list(
+  int n, const int* perm, const int* nn, const int* nl, int mn_out, int* NN_out, int* NL_out,
+  int* flags)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  const int a = perm[i];
+  int cnt = nn[i];
+  if (cnt > mn_out) {
+    atomicOr(&flags[1], (int)B2_ERR_RADIAL_OVERFLOW);
+    cnt = mn_out;
+  }
+  int* row = NL_out + (size_t)a * mn_out;
+  for (int k = 0; k < cnt; ++k) { // insertion sort into ascending caller index
+    const int v = perm[nl[(size_t)k * n + i]];
+    int q = k - 1;
+    while (q >= 0 && row[q] > v) {
+      row[q + 1] = row[q];
+      --q;
+    }
+    row[q + 1] = v;
+  }
+  NN_out[a] = cnt;
+}
+
+__global__ void k_export_q(B2NepView P, float* out)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.n)
+    return;
+  const int a = P.perm[i];
+  for (int d = 0; d < P.dim; ++d)
+    out[(size_t)d * P.n + a] = P.q[(size_t)d * P.n + i] * P.q_scaler[d];
+}
+
+template <typename T>
+int upload(DevBuf<T>& buf, const std::vector<T>& host)
+{
+  const size_t count = host.empty() ? 1 : host.size();
+  B2_CUDA(buf.reserve(count));
+  if (!host.empty())
+    B2_CUDA(cudaMemcpy(buf.p, host.data(), sizeof(T) * host.size(), cudaMemcpyHostToDevice));
+  return B200MD_OK;
+}
+
+} // namespace
+
+} // namespace b2
+
+using namespace b2;
+
+struct b200md_nep {
+  NepModel model;
+  Neighbor nb;
+  int n = 0;
+  DevBuf<float> rc_r, rcinv_r, rc2_r, rc_a, rcinv_a, rc2_a, c_r, c_a, w0p, b0, w1, bias, q_scaler,
+    zbl_para, cov_radius;
+  DevBuf<int> zbl_z;
+  DevBuf<int> nn_r, nl_r, nn_a, nl_a;
+  DevBuf<float> q, sfx, FpA, U, f12;
+  DevBuf<double> acc;
+  // staging for the host-buffer entry point
+  DevBuf<int> h_type;
+  DevBuf<double> h_pos, h_out;
+  B2NepView view;
+  int ang_block = BLK;
+  size_t ang_smem = 0, rad_smem = 0;
+};
+
+namespace {
+
+template <int NT, int K1>
+int launch_desc_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
+{
+  auto kern = k_desc_radial<NT, K1>;
+  if (NT == 0 && p->rad_smem > 48 * 1024)
+    B2_CUDA(cudaFuncSetAttribute(
+      kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->rad_smem));
+  kern<<<grid_for(p->n, BLK), BLK, NT == 0 ? p->rad_smem : 0, st>>>(p->view, box);
+  B2_LAUNCHED();
+  return B200MD_OK;
+}
+
+template <int K1>
+int dispatch_desc_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
+{
+  switch (p->model.nt) {
+    case 1: return launch_desc_radial<1, K1>(p, box, st);
+    case 2: return launch_desc_radial<2, K1>(p, box, st);
+    default: return launch_desc_radial<0, K1>(p, box, st);
+  }
+}
+
+template <int NT, int K1>
+int launch_force_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
+{
+  k_force_radial<NT, K1><<<grid_for(p->n, BLK), BLK, 0, st>>>(p->view, box);
+  B2_LAUNCHED();
+  return B200MD_OK;
+}
+
+template <int K1>
+int dispatch_force_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
+{
+  switch (p->model.nt) {
+    case 1: return launch_force_radial<1, K1>(p, box, st);
+    case 2: return launch_force_radial<2, K1>(p, box, st);
+    default: return launch_force_radial<0, K1>(p, box, st);
+  }
+}
+
+template <int K1>
+int launch_angular(const b200md_nep* p, const B2Box& box, cudaStream_t st, bool force)
+{
+  if (!force) {
+    k_desc_angular<K1, 5><<<grid_for(p->n, BLK), BLK, 0, st>>>(p->view, box);
+    B2_LAUNCHED();
+    return B200MD_OK;
+  }
+  auto kern = k_force_angular<K1>;
+  if (p->ang_smem > 48 * 1024)
+    B2_CUDA(cudaFuncSetAttribute(
+      kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ang_smem));
+  kern<<<grid_for(p->n, p->ang_block), p->ang_block, p->ang_smem, st>>>(p->view, box);
+  B2_LAUNCHED();
+  return B200MD_OK;
+}
+
+template <int DIMP>
+int launch_mlp(const b200md_nep* p, cudaStream_t st)
+{
+  k_mlp<DIMP><<<grid_for(p->n, MLP_BLK), MLP_BLK, 0, st>>>(p->view);
+  B2_LAUNCHED();
+  return B200MD_OK;
+}
+
+#define B2_TRY(expr)          \
+  do {                        \
+    const int rc_ = (expr);   \
+    if (rc_ != B200MD_OK)     \
+      return rc_;             \
+  } while (0)
+
+int nep_pipeline(b200md_nep* p, const B2Box& box, cudaStream_t st)
+{
+  const int n = p->n;
+  k_split<<<grid_for(n, BLK), BLK, 0, st>>>(p->view, box);
+  B2_LAUNCHED();
+  switch (p->model.K1R) {
+    case 9: B2_TRY(dispatch_desc_radial<9>(p, box, st)); break;
+    case 13: B2_TRY(dispatch_desc_radial<13>(p, box, st)); break;
+    default: B2_TRY(dispatch_desc_radial<17>(p, box, st)); break;
+  }
+  switch (p->model.K1A) {
+    case 9: B2_TRY(launch_angular<9>(p, box, st, false)); break;
+    case 13: B2_TRY(launch_angular<13>(p, box, st, false)); break;
+    default: B2_TRY(launch_angular<17>(p, box, st, false)); break;
+  }
+  switch (p->model.DIMP) {
+    case 16: B2_TRY(launch_mlp<16>(p, st)); break;
+    case 32: B2_TRY(launch_mlp<32>(p, st)); break;
+    case 48: B2_TRY(launch_mlp<48>(p, st)); break;
+    case 64: B2_TRY(launch_mlp<64>(p, st)); break;
+    case 80: B2_TRY(launch_mlp<80>(p, st)); break;
+    case 96: B2_TRY(launch_mlp<96>(p, st)); break;
+    case 112: B2_TRY(launch_mlp<112>(p, st)); break;
+    default: B2_TRY(launch_mlp<128>(p, st)); break;
+  }
+  switch (p->model.K1R) {
+    case 9: B2_TRY(dispatch_force_radial<9>(p, box, st)); break;
+    case 13: B2_TRY(dispatch_force_radial<13>(p, box, st)); break;
+    default: B2_TRY(dispatch_force_radial<17>(p, box, st)); break;
+  }
+  switch (p->model.K1A) {
+    case 9: B2_TRY(launch_angular<9>(p, box, st, true)); break;
+    case 13: B2_TRY(launch_angular<13>(p, box, st, true)); break;
+    default: B2_TRY(launch_angular<17>(p, box, st, true)); break;
+  }
+  k_reduce_angular<<<grid_for(n, BLK), BLK, 0, st>>>(p->view, box);
+  B2_LAUNCHED();
+  if (p->model.zbl_enabled) {
+    k_zbl<<<grid_for(n, BLK), BLK, 0, st>>>(p->view, box);
+    B2_LAUNCHED();
+  }
+  return B200MD_OK;
+}
+
+int nep_setup(b200md_nep* p, int num_atoms)
+{
+  NepModel& m = p->model;
+  p->n = num_atoms;
+  const size_t N = (size_t)num_atoms;
+  B2_TRY(upload(p->rc_r, m.rc_r));
+  B2_TRY(upload(p->rcinv_r, m.rcinv_r));
+  B2_TRY(upload(p->rc2_r, m.rc2_r));
+  B2_TRY(upload(p->rc_a, m.rc_a));
+  B2_TRY(upload(p->rcinv_a, m.rcinv_a));
+  B2_TRY(upload(p->rc2_a, m.rc2_a));
+  B2_TRY(upload(p->c_r, m.c_r));
+  B2_TRY(upload(p->c_a, m.c_a));
+  B2_TRY(upload(p->w0p, m.w0p));
+  B2_TRY(upload(p->b0, m.b0));
+  B2_TRY(upload(p->w1, m.w1));
+  B2_TRY(upload(p->bias, m.bias));
+  B2_TRY(upload(p->q_scaler, m.q_scaler));
+  B2_TRY(upload(p->zbl_para, m.zbl_para));
+  B2_TRY(upload(p->zbl_z, m.atomic_numbers));
+  std::vector<float> cov(COVALENT_RADIUS, COVALENT_RADIUS + 94);
+  B2_TRY(upload(p->cov_radius, cov));
+
+  // Neighbor::initialize: skin-list capacity MN*((rc+skin)/rc)^3, neighbor.cu:824-829
+  const double rc = m.rc_radial_max;
+  const double rs = rc + 1.0;
+  const int mn_skin = (int)(m.MN_radial * rs * rs * rs / (rc * rc * rc));
+  B2_TRY(p->nb.init(num_atoms, rc, mn_skin));
+
+  B2_CUDA(p->nn_r.reserve(N));
+  B2_CUDA(p->nl_r.reserve(N * m.MN_radial));
+  B2_CUDA(p->nn_a.reserve(N));
+  B2_CUDA(p->nl_a.reserve(N * m.MN_angular));
+  B2_CUDA(p->q.reserve(N * m.dim));
+  B2_CUDA(p->sfx.reserve(N * m.na1 * B2_NABC));
+  B2_CUDA(p->FpA.reserve(N * m.dim_angular));
+  B2_CUDA(p->U.reserve(N * m.UST));
+  B2_CUDA(p->f12.reserve(N * 3 * m.MN_angular));
+  B2_CUDA(p->acc.reserve(N * 13));
+
+  B2NepView& P = p->view;
+  std::memset(&P, 0, sizeof P);
+  P.nt = m.nt;
+  P.nr1 = m.nr1;
+  P.na1 = m.na1;
+  P.kr1 = m.kr1;
+  P.ka1 = m.ka1;
+  P.K1R = m.K1R;
+  P.K1A = m.K1A;
+  P.KP = m.KP;
+  P.UST = m.UST;
+  P.has222 = m.has222;
+  P.has1111 = m.has1111;
+  P.num_L = m.num_L;
+  P.dim = m.dim;
+  P.dim_ang = m.dim_angular;
+  P.nneu = m.nneu;
+  P.DIMP = m.DIMP;
+  P.zbl_enabled = m.zbl_enabled;
+  P.zbl_flexible = m.zbl_flexible;
+  P.zbl_typewise = m.zbl_typewise;
+  P.zbl_rc_inner = m.zbl_rc_inner;
+  P.zbl_rc_outer = m.zbl_rc_outer;
+  P.zbl_typewise_factor = m.zbl_typewise_factor;
+  P.rc_r = p->rc_r.p;
+  P.rcinv_r = p->rcinv_r.p;
+  P.rc2_r = p->rc2_r.p;
+  P.rc_a = p->rc_a.p;
+  P.rcinv_a = p->rcinv_a.p;
+  P.rc2_a = p->rc2_a.p;
+  P.c_r = p->c_r.p;
+  P.c_a = p->c_a.p;
+  P.w0p = p->w0p.p;
+  P.b0 = p->b0.p;
+  P.w1 = p->w1.p;
+  P.bias = p->bias.p;
+  P.q_scaler = p->q_scaler.p;
+  P.zbl_z = p->zbl_z.p;
+  P.zbl_para = p->zbl_para.p;
+  P.cov_radius = p->cov_radius.p;
+  P.n = num_atoms;
+  P.mn_r = m.MN_radial;
+  P.mn_a = m.MN_angular;
+  P.atoms = p->nb.atoms.p;
+  P.perm = p->nb.perm.p;
+  P.nn_skin = p->nb.nn_skin.p;
+  P.nl_skin = p->nb.nl_skin.p;
+  P.nn_r = p->nn_r.p;
+  P.nl_r = p->nl_r.p;
+  P.nn_a = p->nn_a.p;
+  P.nl_a = p->nl_a.p;
+  P.q = p->q.p;
+  P.sfx = p->sfx.p;
+  P.FpA = p->FpA.p;
+  P.U = p->U.p;
+  P.f12 = p->f12.p;
+  P.acc = p->acc.p;
+  P.flags = p->nb.flags.p;
+
+  // shared-memory budgets
+  p->ang_block = BLK;
+  p->ang_smem = (size_t)m.na1 * B2_NABC * p->ang_block * sizeof(float);
+  while (p->ang_smem > 200 * 1024 && p->ang_block > 32) {
+    p->ang_block /= 2;
+    p->ang_smem = (size_t)m.na1 * B2_NABC * p->ang_block * sizeof(float);
+  }
+  p->rad_smem = (size_t)m.nt * m.K1R * BLK * sizeof(float);
+  if (m.nt > 2 && p->rad_smem > 200 * 1024) {
+    set_error("too many atom types for the shared-memory radial accumulators");
+    return B200MD_ERR_ARG;
+  }
+  B2_CUDA(cudaDeviceSynchronize());
+  return B200MD_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int b200md_nep_create(const char* path, int num_atoms, b200md_nep** out)
+{
+  if (!path || !out || num_atoms <= 0) {
+    set_error("b200md_nep_create: bad argument");
+    return B200MD_ERR_ARG;
+  }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("b200md_nep_create: no CUDA device (libb200md has no CPU fallback)");
+    return B200MD_ERR_CUDA;
+  }
+  b200md_nep* p = new (std::nothrow) b200md_nep;
+  if (!p) {
+    set_error("out of host memory");
+    return B200MD_ERR_ARG;
+  }
+  const std::string err = p->model.load(path);
+  if (!err.empty()) {
+    set_error(err);
+    const bool io = err.rfind("Failed to open", 0) == 0;
+    delete p;
+    return io ? B200MD_ERR_IO : B200MD_ERR_ARG;
+  }
+  const int rc = nep_setup(p, num_atoms);
+  if (rc != B200MD_OK) {
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return B200MD_OK;
+}
+
+void b200md_nep_destroy(b200md_nep* p) { delete p; }
+
+int b200md_nep_info(const b200md_nep* p, int what)
+{
+  switch (what) {
+    case 0: return p->model.nt;
+    case 1: return p->model.dim;
+    case 2: return p->model.nneu;
+    case 3: return p->model.MN_radial;
+    case 4: return p->model.MN_angular;
+    case 5: return p->model.zbl_enabled ? 1 : 0;
+    case 6: {
+      int bits = 0, rebuilds = 0;
+      const_cast<b200md_nep*>(p)->nb.check(0, &bits, &rebuilds);
+      return rebuilds;
+    }
+    default: return -1;
+  }
+}
+
+double b200md_nep_rc(const b200md_nep* p) { return p->model.rc_radial_max; }
+
+const char* b200md_nep_symbol(const b200md_nep* p, int t)
+{
+  return (t >= 0 && t < p->model.nt) ? p->model.symbols[t].c_str() : "";
+}
+
+int b200md_nep_compute(
+  b200md_nep* p, int n, const double h[9], const int pbc[3], const int* d_type,
+  const double* d_position, double* d_potential, double* d_force, double* d_virial, void* stream)
+{
+  cudaStream_t st = (cudaStream_t)stream;
+  const B2Box box = make_box(h, pbc);
+  B2_TRY(p->nb.update(box, d_type, d_position, n, st));
+  B2_TRY(nep_pipeline(p, box, st));
+  k_unpack<<<grid_for(n, 256), 256, 0, st>>>(
+    n, p->nb.perm.p, p->acc.p, d_potential, d_force, d_virial);
+  B2_LAUNCHED();
+  return B200MD_OK;
+}
+
+int b200md_nep_compute_host(
+  b200md_nep* p, int n, const double h[9], const int pbc[3], const int* type,
+  const double* position, double* potential, double* force, double* virial)
+{
+  const size_t N = (size_t)n;
+  B2_CUDA(p->h_type.reserve(N));
+  B2_CUDA(p->h_pos.reserve(3 * N));
+  B2_CUDA(p->h_out.reserve(13 * N));
+  cudaStream_t st = 0;
+  B2_CUDA(cudaMemcpyAsync(p->h_type.p, type, sizeof(int) * N, cudaMemcpyHostToDevice, st));
+  B2_CUDA(cudaMemcpyAsync(p->h_pos.p, position, sizeof(double) * 3 * N, cudaMemcpyHostToDevice, st));
+  B2_CUDA(cudaMemsetAsync(p->h_out.p, 0, sizeof(double) * 13 * N, st));
+  double* d_pe = p->h_out.p;
+  double* d_f = p->h_out.p + N;
+  double* d_v = p->h_out.p + 4 * N;
+  B2_TRY(b200md_nep_compute(p, n, h, pbc, p->h_type.p, p->h_pos.p, d_pe, d_f, d_v, st));
+  B2_CUDA(cudaMemcpyAsync(potential, d_pe, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaMemcpyAsync(force, d_f, sizeof(double) * 3 * N, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaMemcpyAsync(virial, d_v, sizeof(double) * 9 * N, cudaMemcpyDeviceToHost, st));
+  B2_CUDA(cudaStreamSynchronize(st));
+  return b200md_nep_check(p, st);
+}
+
+int b200md_nep_export_neighbors(
+  b200md_nep* p, int mn_r, int* d_NN_r, int* d_NL_r, int mn_a, int* d_NN_a, int* d_NL_a,
+  void* stream)
+{
+  cudaStream_t st = (cudaStream_t)stream;
+  const int n = p->n;
+  if (d_NN_r && d_NL_r) {
+    k_export_list<<<grid_for(n, 128), 128, 0, st>>>(
+      n, p->nb.perm.p, p->nn_r.p, p->nl_r.p, mn_r, d_NN_r, d_NL_r, p->nb.flags.p);
+    B2_LAUNCHED();
+  }
+  if (d_NN_a && d_NL_a) {
+    k_export_list<<<grid_for(n, 128), 128, 0, st>>>(
+      n, p->nb.perm.p, p->nn_a.p, p->nl_a.p, mn_a, d_NN_a, d_NL_a, p->nb.flags.p);
+    B2_LAUNCHED();
+  }
+  return B200MD_OK;
+}
+
+int b200md_nep_export_descriptors(b200md_nep* p, float* d_q, void* stream)
+{
+  k_export_q<<<grid_for(p->n, 128), 128, 0, (cudaStream_t)stream>>>(p->view, d_q);
+  B2_LAUNCHED();
+  return B200MD_OK;
+}
+
+int b200md_nep_check(b200md_nep* p, void* stream)
+{
+  int bits = 0, rebuilds = 0;
+  B2_TRY(p->nb.check((cudaStream_t)stream, &bits, &rebuilds));
+  if (bits) {
+    char buf[256];
+    snprintf(
+      buf, sizeof buf,
+      "neighbour capacity exceeded on the device (bits=%d: 1 skin list, 2 radial MN, 4 angular MN)",
+      bits);
+    set_error(buf);
+    return B200MD_ERR_OVERFLOW;
+  }
+  return B200MD_OK;
+}
+
+} // extern "C"

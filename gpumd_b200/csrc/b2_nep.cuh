@@ -1,0 +1,896 @@
+// b2_nep.cuh -- device math and kernel bodies of the NEP path of libb200md (sm_100a).
+//
+// What it computes is what the reference computes (src/force/nep.cu:436-975 with
+// src/utilities/nep_utilities.cuh); HOW is re-derived for a cell-sorted, gather-only,
+// register-resident formulation:
+//
+//  * radial descriptor: q_n = sum_j sum_k c[t1,t2,n,k] fn_k(r_ij) is accumulated as
+//    S[t2][k] = sum_{j of type t2} fn_k(r_ij) (K+1 adds per pair instead of (n_max+1)(K+1) FMAs and
+//    coefficient loads, nep.cu:536-545) and contracted with c once per atom;
+//  * radial force: the per-pair sums over n (nep.cu:718-733) are pre-contracted per atom into
+//    U_i[t][k] = sum_n Fp_i[n] c[t_i,t,n,k]; a pair then costs two (K+1)-term dot products
+//    A = fn'.U_i[t_j], B = fn'.U_j[t_i] and one 48-byte gather of U_j (the reference gathers
+//    n_max+1 strided Fp values and re-reads 2(n_max+1)(K+1) coefficients per pair);
+//  * angular part: dU/ds[n][abc] (3-body + the chain-rule terms of the 4-/5-body invariants) is
+//    formed ONCE per atom; a pair then contracts it with g_n, g_n' and uses the closed-form
+//    gradients of the real solid harmonics up to L = 4.  The reference re-derives the 4-/5-body
+//    prefactors for every pair (nep_utilities.cuh:625-718) and walks generic coefficient tables
+//    (nep_utilities.cuh:1342-1434);
+//  * the per-atom MLP is a separate pass over type-sorted tiles of atoms with zero-padded weight
+//    rows (apply_ann_one_layer, nep_utilities.cuh:169-194).
+// Summation orders therefore differ from the reference at the FP32 rounding level; the membership
+// of the radial/angular neighbour sets does not (b2_r12 / b2_d2 in b2_common.cuh).
+#pragma once
+#include "b2_common.cuh"
+
+// normalisation of the real harmonics (C3B, nep_utilities.cuh:18-27; L <= 4 part)
+#define B2_C3B_LIST                                                                             \
+  0.238732414637843f, 0.119366207318922f, 0.119366207318922f, 0.099471839432435f,              \
+    0.596831036594608f, 0.596831036594608f, 0.149207759148652f, 0.149207759148652f,            \
+    0.139260575205408f, 0.104445431404056f, 0.104445431404056f, 1.044454314040563f,            \
+    1.044454314040563f, 0.174075719006761f, 0.174075719006761f, 0.011190581936149f,            \
+    0.223811638722978f, 0.223811638722978f, 0.111905819361489f, 0.111905819361489f,            \
+    1.566681471060845f, 1.566681471060845f, 0.195835183882606f, 0.195835183882606f
+// C4B, C5B (nep_utilities.cuh:40-46)
+#define B2_C4B0 (-0.007499480826664f)
+#define B2_C4B1 (-0.134990654879954f)
+#define B2_C4B2 (0.067495327439977f)
+#define B2_C4B3 (0.404971964639861f)
+#define B2_C4B4 (-0.809943929279723f)
+#define B2_C5B0 (0.026596810706114f)
+#define B2_C5B1 (0.053193621412227f)
+#define B2_C5B2 (0.026596810706114f)
+
+constexpr int B2_NABC = 24;      // (L_max+1)^2 - 1 for L_max = 4
+constexpr int B2_MAX_TYPES = 94; // NUM_ELEMENTS, src/utilities/common.cuh:18
+
+struct B2NepView {
+  // ---- model (device tables) ----
+  int nt;       // number of types
+  int nr1, na1; // n_max_radial+1, n_max_angular+1
+  int kr1, ka1; // basis_size_radial+1, basis_size_angular+1 (true sizes)
+  int K1R, K1A; // padded basis counts the kernels are instantiated for (9, 13 or 17)
+  int KP;       // U-table row stride per type: K1R rounded up to a multiple of 4
+  int UST;      // U-table stride per atom = nt * KP
+  int has222, has1111, num_L; // L_max is 4
+  int dim, dim_ang, nneu, DIMP;
+  int zbl_enabled, zbl_flexible, zbl_typewise;
+  float zbl_rc_inner, zbl_rc_outer, zbl_typewise_factor;
+  const float* rc_r;    // [nt*nt] pair cutoff (rc[t1]+rc[t2])*0.5f
+  const float* rcinv_r; // [nt*nt] 1.0f / rc_r
+  const float* rc2_r;   // [nt*nt] rc_r*rc_r
+  const float* rc_a;
+  const float* rcinv_a;
+  const float* rc2_a;
+  const float* c_r;      // [nt*nt][nr1][K1R] zero-padded in k
+  const float* c_a;      // [nt*nt][na1][K1A]
+  const float* w0p;      // [nt][nneu][DIMP] zero-padded rows
+  const float* b0;       // [nt][nneu]
+  const float* w1;       // [nt][nneu]
+  const float* bias;     // [nt]  b1 (+ typewise bias for NEP5)
+  const float* q_scaler; // [DIMP] zero-padded
+  const int* zbl_z;      // [nt] atomic numbers
+  const float* zbl_para; // flexible ZBL table
+  const float* cov_radius; // [94]
+  // ---- per-step state ----
+  int n;
+  int mn_r, mn_a;
+  const B2Atom* atoms; // sorted records
+  const int* perm;
+  const int* nn_skin;
+  const int* nl_skin;
+  int* nn_r;
+  int* nl_r; // [mn_r * n]
+  int* nn_a;
+  int* nl_a; // [mn_a * n]
+  float* q;   // [dim * n]   unscaled descriptors
+  float* sfx; // [na1*24 * n] angular sums s[n][abc]
+  float* FpA; // [dim_ang * n] dU/dq (already multiplied by q_scaler), angular part
+  float* U;   // [n * UST]   pre-contracted radial table
+  float* f12; // [3 * mn_a * n]
+  double* acc; // [13 * n]: pe, fx,fy,fz, virial xx,yy,zz,xy,xz,yz,yx,zx,zy (sorted order)
+  int* flags;
+};
+
+// ---------------------------------------------------------------------------------------------
+// neighbour-set split: find_neighbor_list_large_box, nep.cu:436-486
+// ---------------------------------------------------------------------------------------------
+B2_HD void b2_body_split(int i, const B2NepView& P, const B2Box& box)
+{
+  const B2Atom a1 = P.atoms[i];
+  const int nn = P.nn_skin[i];
+  const int row = a1.type * P.nt;
+  int cr = 0, ca = 0;
+  for (int k = 0; k < nn; ++k) {
+    const int j = P.nl_skin[(size_t)k * P.n + i];
+    const B2Atom a2 = P.atoms[j];
+    float x12, y12, z12;
+    b2_r12(box, a1, a2, x12, y12, z12);
+    const float d2 = b2_d2(x12, y12, z12);
+    const int pair = row + a2.type;
+    if (d2 >= B2_LDG(&P.rc2_r[pair]))
+      continue;
+    if (cr < P.mn_r)
+      P.nl_r[(size_t)cr * P.n + i] = j;
+    ++cr;
+    if (d2 < B2_LDG(&P.rc2_a[pair])) {
+      if (ca < P.mn_a)
+        P.nl_a[(size_t)ca * P.n + i] = j;
+      ++ca;
+    }
+  }
+  if (cr > P.mn_r) {
+    B2_ATOMIC_OR(&P.flags[1], (int)B2_ERR_RADIAL_OVERFLOW);
+    cr = P.mn_r;
+  }
+  if (ca > P.mn_a) {
+    B2_ATOMIC_OR(&P.flags[1], (int)B2_ERR_ANGULAR_OVERFLOW);
+    ca = P.mn_a;
+  }
+  P.nn_r[i] = cr;
+  P.nn_a[i] = ca;
+}
+
+// ---------------------------------------------------------------------------------------------
+// radial basis.  fc, fc' : nep_utilities.cuh:409-431;  fn, fn' : nep_utilities.cuh:572-623
+// ---------------------------------------------------------------------------------------------
+template <int K1>
+B2_HD void b2_basis(float d, float rc, float rcinv, float* fn)
+{
+  float fc = 0.0f;
+  if (d < rc)
+    fc = 0.5f * cosf(3.1415927f * (d * rcinv)) + 0.5f;
+  const float y = d * rcinv - 1.0f;
+  const float x = 2.0f * y * y - 1.0f;
+  const float hfc = 0.5f * fc;
+  fn[0] = fc;
+  fn[1] = (x + 1.0f) * hfc;
+  float t0 = 1.0f, t1 = x;
+#pragma unroll
+  for (int k = 2; k < K1; ++k) {
+    const float t2 = 2.0f * x * t1 - t0;
+    t0 = t1;
+    t1 = t2;
+    fn[k] = (t2 + 1.0f) * hfc;
+  }
+}
+
+// WITH_FN = false skips fn (the radial force only needs the derivatives)
+template <int K1, bool WITH_FN>
+B2_HD void b2_basis_d(float d, float rc, float rcinv, float* fn, float* fnp)
+{
+  float fc = 0.0f, fcp = 0.0f;
+  if (d < rc) {
+    float s, c;
+#if defined(__CUDA_ARCH__)
+    sincosf(3.1415927f * (d * rcinv), &s, &c);
+#else
+    s = sinf(3.1415927f * (d * rcinv));
+    c = cosf(3.1415927f * (d * rcinv));
+#endif
+    fc = 0.5f * c + 0.5f;
+    fcp = -1.5707963f * s * rcinv;
+  }
+  const float y = d * rcinv - 1.0f;
+  const float x = 2.0f * y * y - 1.0f;
+  const float g = 2.0f * y * rcinv * fc; // d/dr of (x+1)/2, times fc
+  const float hfc = 0.5f * fc, hfcp = 0.5f * fcp;
+  if (WITH_FN) {
+    fn[0] = fc;
+    fn[1] = (x + 1.0f) * hfc;
+  }
+  fnp[0] = fcp;
+  fnp[1] = g + (x + 1.0f) * hfcp;
+  float t0 = 1.0f, t1 = x;        // T_{k-2}, T_{k-1}
+  float u0 = 1.0f, u1 = 2.0f * x; // U_{k-2}, U_{k-1}
+#pragma unroll
+  for (int k = 2; k < K1; ++k) {
+    const float t2 = 2.0f * x * t1 - t0;
+    t0 = t1;
+    t1 = t2;
+    // d T_k / dx = k U_{k-1}
+    fnp[k] = ((float)k * u1) * g + (t2 + 1.0f) * hfcp;
+    if (WITH_FN)
+      fn[k] = (t2 + 1.0f) * hfc;
+    const float u2 = 2.0f * x * u1 - u0;
+    u0 = u1;
+    u1 = u2;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// radial descriptor (radial half of find_descriptor, nep.cu:521-546)
+// NT > 0: per-type accumulators in registers (models with <= NT types); NT == 0: accumulators in
+// the caller-provided scratch `acc` laid out [(t2*K1+k)*stride + lane].
+// ---------------------------------------------------------------------------------------------
+template <int NT, int K1>
+B2_HD void b2_body_desc_radial(
+  int i, const B2NepView& P, const B2Box& box, float* acc, int stride, int lane)
+{
+  const B2Atom a1 = P.atoms[i];
+  const int t1 = a1.type;
+  const int nn = P.nn_r[i];
+  float S[NT > 0 ? NT : 1][K1];
+  if (NT > 0) {
+#pragma unroll
+    for (int t = 0; t < (NT > 0 ? NT : 1); ++t)
+#pragma unroll
+      for (int k = 0; k < K1; ++k)
+        S[t][k] = 0.0f;
+  } else {
+    for (int m = 0; m < P.nt * K1; ++m)
+      acc[(size_t)m * stride + lane] = 0.0f;
+  }
+  for (int s = 0; s < nn; ++s) {
+    const int j = P.nl_r[(size_t)s * P.n + i];
+    const B2Atom a2 = P.atoms[j];
+    float x12, y12, z12;
+    b2_r12(box, a1, a2, x12, y12, z12);
+    const float d = sqrtf(b2_d2(x12, y12, z12));
+    const int t2 = a2.type;
+    const int pair = t1 * P.nt + t2;
+    float fn[K1];
+    b2_basis<K1>(d, B2_LDG(&P.rc_r[pair]), B2_LDG(&P.rcinv_r[pair]), fn);
+    if (NT == 1) {
+#pragma unroll
+      for (int k = 0; k < K1; ++k)
+        S[0][k] += fn[k];
+    } else if (NT > 1) {
+#pragma unroll
+      for (int t = 0; t < (NT > 0 ? NT : 1); ++t) {
+        const float m = (t2 == t) ? 1.0f : 0.0f;
+#pragma unroll
+        for (int k = 0; k < K1; ++k)
+          S[t][k] = fmaf(m, fn[k], S[t][k]);
+      }
+    } else {
+      float* a = acc + (size_t)(t2 * K1) * stride + lane;
+#pragma unroll
+      for (int k = 0; k < K1; ++k)
+        a[(size_t)k * stride] += fn[k];
+    }
+  }
+  // contraction with the expansion coefficients
+  for (int n = 0; n < P.nr1; ++n) {
+    float q = 0.0f;
+    if (NT > 0) {
+#pragma unroll
+      for (int t = 0; t < (NT > 0 ? NT : 1); ++t) {
+        if (t < P.nt) {
+          const float* c = P.c_r + ((size_t)(t1 * P.nt + t) * P.nr1 + n) * K1;
+#pragma unroll
+          for (int k = 0; k < K1; ++k)
+            q = fmaf(B2_LDG(&c[k]), S[t][k], q);
+        }
+      }
+    } else {
+      for (int t = 0; t < P.nt; ++t) {
+        const float* c = P.c_r + ((size_t)(t1 * P.nt + t) * P.nr1 + n) * K1;
+        const float* a = acc + (size_t)(t * K1) * stride + lane;
+#pragma unroll
+        for (int k = 0; k < K1; ++k)
+          q = fmaf(B2_LDG(&c[k]), a[(size_t)k * stride], q);
+      }
+    }
+    P.q[(size_t)n * P.n + i] = q;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// real solid harmonics on the unit sphere, L = 1..4, in the reference's ordering
+// (accumulate_s_one, nep_utilities.cuh:1674-1723 with Z_COEFFICIENT_1..4, :87-103):
+// for each L: m = 0, then Re/Im (x+iy)^m times the z-polynomial, m = 1..L.
+// ---------------------------------------------------------------------------------------------
+B2_HD void b2_harmonics(float x, float y, float z, float* B)
+{
+  const float x2 = x * x, y2 = y * y, z2 = z * z;
+  const float c2 = x2 - y2, s2 = 2.0f * x * y;                       // Re, Im (x+iy)^2
+  const float c3 = x * (x2 - 3.0f * y2), s3 = y * (3.0f * x2 - y2); // (x+iy)^3
+  const float c4 = c2 * c2 - s2 * s2, s4 = 2.0f * c2 * s2;           // (x+iy)^4
+  B[0] = z;
+  B[1] = x;
+  B[2] = y;
+  B[3] = 3.0f * z2 - 1.0f;
+  B[4] = x * z;
+  B[5] = y * z;
+  B[6] = c2;
+  B[7] = s2;
+  const float p31 = 5.0f * z2 - 1.0f;
+  B[8] = (5.0f * z2 - 3.0f) * z;
+  B[9] = p31 * x;
+  B[10] = p31 * y;
+  B[11] = z * c2;
+  B[12] = z * s2;
+  B[13] = c3;
+  B[14] = s3;
+  const float p41 = (7.0f * z2 - 3.0f) * z, p42 = 7.0f * z2 - 1.0f;
+  B[15] = (35.0f * z2 - 30.0f) * z2 + 3.0f;
+  B[16] = p41 * x;
+  B[17] = p41 * y;
+  B[18] = p42 * c2;
+  B[19] = p42 * s2;
+  B[20] = z * c3;
+  B[21] = z * s3;
+  B[22] = c4;
+  B[23] = s4;
+}
+
+// G = sum_abc W[abc] * grad B_abc evaluated at the unit vector (x,y,z), where B_abc are the
+// homogeneous (degree L) forms of the harmonics above (r^2 = 1 substituted after differentiating).
+B2_HD void b2_harmonics_grad_dot(
+  float x, float y, float z, const float* W, float& gx, float& gy, float& gz)
+{
+  const float x2 = x * x, y2 = y * y, z2 = z * z;
+  const float xy = x * y, xz = x * z, yz = y * z;
+  const float c2 = x2 - y2, s2 = 2.0f * xy;
+  const float c3 = x * (x2 - 3.0f * y2), s3 = y * (3.0f * x2 - y2);
+  // L = 1
+  gx = W[1];
+  gy = W[2];
+  gz = W[0];
+  // L = 2: 3z^2-r^2, xz, yz, x^2-y^2, 2xy
+  gx += W[3] * (-2.0f * x) + W[4] * z + W[6] * (2.0f * x) + W[7] * (2.0f * y);
+  gy += W[3] * (-2.0f * y) + W[5] * z - W[6] * (2.0f * y) + W[7] * (2.0f * x);
+  gz += W[3] * (4.0f * z) + W[4] * x + W[5] * y;
+  // L = 3: 5z^3-3zr^2, (5z^2-r^2)x, (5z^2-r^2)y, z(x^2-y^2), 2xyz, x^3-3xy^2, 3x^2y-y^3
+  {
+    const float p = 5.0f * z2 - 1.0f;
+    gx += W[8] * (-6.0f * xz) + W[9] * (p - 2.0f * x2) + W[10] * (-2.0f * xy) +
+          W[11] * (2.0f * xz) + W[12] * (2.0f * yz) + W[13] * (3.0f * c2) + W[14] * (6.0f * xy);
+    gy += W[8] * (-6.0f * yz) + W[9] * (-2.0f * xy) + W[10] * (p - 2.0f * y2) -
+          W[11] * (2.0f * yz) + W[12] * (2.0f * xz) - W[13] * (6.0f * xy) + W[14] * (3.0f * c2);
+    gz += W[8] * (9.0f * z2 - 3.0f) + W[9] * (8.0f * xz) + W[10] * (8.0f * yz) + W[11] * c2 +
+          W[12] * s2;
+  }
+  // L = 4: 35z^4-30z^2r^2+3r^4, (7z^3-3zr^2)x, (7z^3-3zr^2)y, (7z^2-r^2)(x^2-y^2),
+  //        (7z^2-r^2)2xy, z(x^3-3xy^2), z(3x^2y-y^3), x^4-6x^2y^2+y^4, 4xy(x^2-y^2)
+  {
+    const float a0 = 12.0f - 60.0f * z2;         // d/dx, d/dy prefactor of the m=0 term
+    const float p1 = (7.0f * z2 - 3.0f) * z;     // 7z^3 - 3z
+    const float p1z = 15.0f * z2 - 3.0f;         // d/dz of (7z^3-3zr^2) at r=1
+    const float p2 = 7.0f * z2 - 1.0f;
+    gx += W[15] * (a0 * x) + W[16] * (p1 - 6.0f * z * x2) + W[17] * (-6.0f * z * xy) +
+          W[18] * (2.0f * x * (p2 - c2)) + W[19] * (2.0f * y * p2 - 4.0f * x2 * y) +
+          W[20] * (3.0f * z * c2) + W[21] * (6.0f * z * xy) +
+          W[22] * (4.0f * c3) + W[23] * (4.0f * s3);
+    gy += W[15] * (a0 * y) + W[16] * (-6.0f * z * xy) + W[17] * (p1 - 6.0f * z * y2) +
+          W[18] * (-2.0f * y * (p2 + c2)) + W[19] * (2.0f * x * p2 - 4.0f * x * y2) -
+          W[20] * (6.0f * z * xy) + W[21] * (3.0f * z * c2) -
+          W[22] * (4.0f * s3) + W[23] * (4.0f * c3);
+    gz += W[15] * (z * (80.0f * z2 - 48.0f)) + W[16] * (x * p1z) + W[17] * (y * p1z) +
+          W[18] * (12.0f * z * c2) + W[19] * (12.0f * z * s2) + W[20] * c3 + W[21] * s3;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// angular descriptor (angular half of find_descriptor, nep.cu:549-581, find_q
+// nep_utilities.cuh:1819-1872).  Processes the radial index n in chunks of NCH so that the
+// NCH*24 accumulators stay in registers; each chunk walks the (short) angular list once.
+// ---------------------------------------------------------------------------------------------
+template <int K1, int NCH>
+B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
+{
+  const float C3B[B2_NABC] = {B2_C3B_LIST};
+  const B2Atom a1 = P.atoms[i];
+  const int t1 = a1.type;
+  const int nn = P.nn_a[i];
+  for (int n0 = 0; n0 < P.na1; n0 += NCH) {
+    float s[NCH][B2_NABC];
+#pragma unroll
+    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+      for (int abc = 0; abc < B2_NABC; ++abc)
+        s[c][abc] = 0.0f;
+    for (int m = 0; m < nn; ++m) {
+      const int j = P.nl_a[(size_t)m * P.n + i];
+      const B2Atom a2 = P.atoms[j];
+      float x12, y12, z12;
+      b2_r12(box, a1, a2, x12, y12, z12);
+      const float d = sqrtf(b2_d2(x12, y12, z12));
+      const int pair = t1 * P.nt + a2.type;
+      float fn[K1];
+      b2_basis<K1>(d, B2_LDG(&P.rc_a[pair]), B2_LDG(&P.rcinv_a[pair]), fn);
+      const float dinv = 1.0f / d;
+      float B[B2_NABC];
+      b2_harmonics(x12 * dinv, y12 * dinv, z12 * dinv, B);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        if (n0 + c < P.na1) {
+          const float* cc = P.c_a + ((size_t)pair * P.na1 + (n0 + c)) * K1;
+          float g = 0.0f;
+#pragma unroll
+          for (int k = 0; k < K1; ++k)
+            g = fmaf(fn[k], B2_LDG(&cc[k]), g);
+#pragma unroll
+          for (int abc = 0; abc < B2_NABC; ++abc)
+            s[c][abc] = fmaf(g, B[abc], s[c][abc]);
+        }
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int n = n0 + c;
+      if (n < P.na1) {
+        float* qa = P.q + (size_t)P.nr1 * P.n + i; // q[(nr1 + L*na1 + n) * N + i]
+        // 3-body invariants, L = 1..4
+        int st = 0;
+#pragma unroll
+        for (int L = 1; L <= 4; ++L) {
+          float v = 0.0f;
+#pragma unroll
+          for (int k = 1; k < 2 * L + 1; ++k)
+            v = fmaf(C3B[st + k] * s[c][st + k], s[c][st + k], v);
+          v = 2.0f * v + C3B[st] * s[c][st] * s[c][st];
+          qa[(size_t)((L - 1) * P.na1 + n) * P.n] = v;
+          st += 2 * L + 1;
+        }
+        int Lidx = 4;
+        if (P.has222) {
+          const float* t = &s[c][3];
+          const float v = B2_C4B0 * t[0] * t[0] * t[0] + B2_C4B1 * t[0] * (t[1] * t[1] + t[2] * t[2]) +
+                          B2_C4B2 * t[0] * (t[3] * t[3] + t[4] * t[4]) +
+                          B2_C4B3 * t[3] * (t[2] * t[2] - t[1] * t[1]) + B2_C4B4 * t[1] * t[2] * t[4];
+          qa[(size_t)(Lidx * P.na1 + n) * P.n] = v;
+          ++Lidx;
+        }
+        if (P.has1111) {
+          const float s0 = s[c][0] * s[c][0], tt = s[c][1] * s[c][1] + s[c][2] * s[c][2];
+          qa[(size_t)(Lidx * P.na1 + n) * P.n] = B2_C5B0 * s0 * s0 + B2_C5B1 * s0 * tt + B2_C5B2 * tt * tt;
+          ++Lidx;
+        }
+#pragma unroll
+        for (int abc = 0; abc < B2_NABC; ++abc)
+          P.sfx[(size_t)(n * B2_NABC + abc) * P.n + i] = s[c][abc];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-atom MLP (apply_ann_one_layer[_nep5], nep_utilities.cuh:169-194, 285-310; nep.cu:583-657)
+// plus the radial pre-contraction U_i[t][k] = sum_n Fp_i[n] c[t_i,t,n,k].
+// ---------------------------------------------------------------------------------------------
+template <int DIMP>
+B2_HD void b2_body_mlp(int i, const B2NepView& P)
+{
+  const int t = P.atoms[i].type;
+  float q[DIMP], Fp[DIMP];
+#pragma unroll
+  for (int d = 0; d < DIMP; ++d) {
+    q[d] = (d < P.dim) ? P.q[(size_t)d * P.n + i] * B2_LDG(&P.q_scaler[d]) : 0.0f;
+    Fp[d] = 0.0f;
+  }
+  const float* w0 = P.w0p + (size_t)t * P.nneu * DIMP;
+  const float* b0 = P.b0 + (size_t)t * P.nneu;
+  const float* w1 = P.w1 + (size_t)t * P.nneu;
+  float F = 0.0f;
+  for (int n = 0; n < P.nneu; ++n) {
+    const float* row = w0 + (size_t)n * DIMP;
+    float dot = 0.0f;
+#pragma unroll
+    for (int d = 0; d < DIMP; ++d)
+      dot = fmaf(B2_LDG(&row[d]), q[d], dot);
+    const float x1 = tanhf(dot - B2_LDG(&b0[n]));
+    const float w1n = B2_LDG(&w1[n]);
+    F = fmaf(w1n, x1, F);
+    const float coef = w1n * (1.0f - x1 * x1);
+#pragma unroll
+    for (int d = 0; d < DIMP; ++d)
+      Fp[d] = fmaf(coef, B2_LDG(&row[d]), Fp[d]);
+  }
+  F -= B2_LDG(&P.bias[t]);
+  P.acc[i] = (double)F;
+#pragma unroll
+  for (int d = 0; d < DIMP; ++d)
+    Fp[d] *= B2_LDG(&P.q_scaler[d]);
+  // angular part of dU/dq
+#pragma unroll
+  for (int d = 0; d < DIMP; ++d) {
+    if (d >= P.nr1 && d < P.dim)
+      P.FpA[(size_t)(d - P.nr1) * P.n + i] = Fp[d];
+  }
+  // radial pre-contraction
+  float* U = P.U + (size_t)i * P.UST;
+  for (int t2 = 0; t2 < P.nt; ++t2) {
+    const float* c = P.c_r + (size_t)(t * P.nt + t2) * P.nr1 * P.K1R;
+    for (int k = 0; k < P.KP; ++k) {
+      float u = 0.0f;
+      if (k < P.K1R) {
+#pragma unroll
+        for (int n = 0; n < DIMP; ++n) {
+          if (n < P.nr1)
+            u = fmaf(Fp[n], B2_LDG(&c[n * P.K1R + k]), u);
+        }
+      }
+      U[t2 * P.KP + k] = u;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// radial force (find_force_radial, nep.cu:661-772) in the pre-contracted form:
+//   F_i   += (A + B) * r12 / d,   A = fn'(d) . U_i[t_j],  B = fn'(d) . U_j[t_i]
+//   W_i^ab += r12^a * f21^b,      f21 = -B * r12 / d
+// ---------------------------------------------------------------------------------------------
+template <int NT, int K1>
+B2_HD void b2_body_force_radial(int i, const B2NepView& P, const B2Box& box)
+{
+  const B2Atom a1 = P.atoms[i];
+  const int t1 = a1.type;
+  const int nn = P.nn_r[i];
+  const float* Ui = P.U + (size_t)i * P.UST;
+  float Ur[NT > 0 ? NT : 1][K1];
+  if (NT > 0) {
+#pragma unroll
+    for (int t = 0; t < (NT > 0 ? NT : 1); ++t)
+#pragma unroll
+      for (int k = 0; k < K1; ++k)
+        Ur[t][k] = (t < P.nt) ? Ui[t * P.KP + k] : 0.0f;
+  }
+  float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+  float vxx = 0.0f, vyy = 0.0f, vzz = 0.0f, vxy = 0.0f, vxz = 0.0f, vyz = 0.0f;
+  for (int s = 0; s < nn; ++s) {
+    const int j = P.nl_r[(size_t)s * P.n + i];
+    const B2Atom a2 = P.atoms[j];
+    float x12, y12, z12;
+    b2_r12(box, a1, a2, x12, y12, z12);
+    const float d = sqrtf(b2_d2(x12, y12, z12));
+    const float dinv = 1.0f / d;
+    const int t2 = a2.type;
+    const int pair = t1 * P.nt + t2;
+    float fnp[K1];
+    b2_basis_d<K1, false>(d, B2_LDG(&P.rc_r[pair]), B2_LDG(&P.rcinv_r[pair]), nullptr, fnp);
+    const float* Uj = P.U + (size_t)j * P.UST + t1 * P.KP;
+    float A = 0.0f, Bv = 0.0f;
+    if (NT == 1) {
+#pragma unroll
+      for (int k = 0; k < K1; ++k)
+        A = fmaf(fnp[k], Ur[0][k], A);
+    } else if (NT > 1) {
+#pragma unroll
+      for (int k = 0; k < K1; ++k) {
+        float u = Ur[0][k];
+#pragma unroll
+        for (int t = 1; t < (NT > 0 ? NT : 1); ++t)
+          u = (t2 == t) ? Ur[t][k] : u;
+        A = fmaf(fnp[k], u, A);
+      }
+    } else {
+      const float* Uit = Ui + t2 * P.KP;
+#pragma unroll
+      for (int k = 0; k < K1; ++k)
+        A = fmaf(fnp[k], Uit[k], A);
+    }
+#pragma unroll
+    for (int k = 0; k < K1; ++k)
+      Bv = fmaf(fnp[k], Uj[k], Bv);
+    const float sA = (A + Bv) * dinv;
+    const float sB = -Bv * dinv; // f21 = sB * r12
+    fx = fmaf(sA, x12, fx);
+    fy = fmaf(sA, y12, fy);
+    fz = fmaf(sA, z12, fz);
+    vxx = fmaf(x12 * x12, sB, vxx);
+    vyy = fmaf(y12 * y12, sB, vyy);
+    vzz = fmaf(z12 * z12, sB, vzz);
+    vxy = fmaf(x12 * y12, sB, vxy);
+    vxz = fmaf(x12 * z12, sB, vxz);
+    vyz = fmaf(y12 * z12, sB, vyz);
+  }
+  double* a = P.acc + i;
+  const size_t N = (size_t)P.n;
+  a[1 * N] = fx;
+  a[2 * N] = fy;
+  a[3 * N] = fz;
+  a[4 * N] = vxx;
+  a[5 * N] = vyy;
+  a[6 * N] = vzz;
+  a[7 * N] = vxy;
+  a[8 * N] = vxz;
+  a[9 * N] = vyz;
+  a[10 * N] = vxy; // yx: the radial pair virial r12 (x) f21 is symmetric
+  a[11 * N] = vxz; // zx
+  a[12 * N] = vyz; // zy
+}
+
+// ---------------------------------------------------------------------------------------------
+// angular partial forces (find_partial_force_angular, nep.cu:774-861, accumulate_f12
+// nep_utilities.cuh:1523-1672).  `w` is scratch for the per-atom weights dU/ds[n][abc], laid out
+// w[(n*24+abc)*stride + lane] (shared memory on the device).
+// ---------------------------------------------------------------------------------------------
+template <int K1>
+B2_HD void b2_body_force_angular(
+  int i, const B2NepView& P, const B2Box& box, float* w, int stride, int lane)
+{
+  const float C3B[B2_NABC] = {B2_C3B_LIST};
+  const size_t N = (size_t)P.n;
+  // ---- weights: 3-body (calculate_s_one, nep_utilities.cuh:1327-1340) + chain rule of the
+  //      4-body (:625-679) and 5-body (:681-718) invariants ----
+  for (int n = 0; n < P.na1; ++n) {
+    float s[B2_NABC];
+#pragma unroll
+    for (int abc = 0; abc < B2_NABC; ++abc)
+      s[abc] = P.sfx[(size_t)(n * B2_NABC + abc) * N + i];
+    float wv[B2_NABC];
+    int st = 0;
+#pragma unroll
+    for (int L = 1; L <= 4; ++L) {
+      const float F = P.FpA[(size_t)((L - 1) * P.na1 + n) * N + i];
+      wv[st] = 2.0f * F * C3B[st] * s[st];
+#pragma unroll
+      for (int k = 1; k < 2 * L + 1; ++k)
+        wv[st + k] = 4.0f * F * C3B[st + k] * s[st + k];
+      st += 2 * L + 1;
+    }
+    int Lidx = 4;
+    if (P.has222) {
+      const float F = P.FpA[(size_t)(Lidx * P.na1 + n) * N + i];
+      const float* t = &s[3];
+      wv[3] += F * (3.0f * B2_C4B0 * t[0] * t[0] + B2_C4B1 * (t[1] * t[1] + t[2] * t[2]) +
+                    B2_C4B2 * (t[3] * t[3] + t[4] * t[4]));
+      wv[4] += F * (2.0f * B2_C4B1 * t[0] * t[1] - 2.0f * B2_C4B3 * t[3] * t[1] + B2_C4B4 * t[2] * t[4]);
+      wv[5] += F * (2.0f * B2_C4B1 * t[0] * t[2] + 2.0f * B2_C4B3 * t[3] * t[2] + B2_C4B4 * t[1] * t[4]);
+      wv[6] += F * (2.0f * B2_C4B2 * t[0] * t[3] + B2_C4B3 * (t[2] * t[2] - t[1] * t[1]));
+      wv[7] += F * (2.0f * B2_C4B2 * t[0] * t[4] + B2_C4B4 * t[1] * t[2]);
+      ++Lidx;
+    }
+    if (P.has1111) {
+      const float F = P.FpA[(size_t)(Lidx * P.na1 + n) * N + i];
+      const float tt = s[1] * s[1] + s[2] * s[2];
+      wv[0] += F * (4.0f * B2_C5B0 * s[0] * s[0] * s[0] + 2.0f * B2_C5B1 * tt * s[0]);
+      wv[1] += F * (2.0f * B2_C5B1 * s[0] * s[0] * s[1] + 4.0f * B2_C5B2 * tt * s[1]);
+      wv[2] += F * (2.0f * B2_C5B1 * s[0] * s[0] * s[2] + 4.0f * B2_C5B2 * tt * s[2]);
+      ++Lidx;
+    }
+#pragma unroll
+    for (int abc = 0; abc < B2_NABC; ++abc)
+      w[(size_t)(n * B2_NABC + abc) * stride + lane] = wv[abc];
+  }
+  // ---- pairs ----
+  const B2Atom a1 = P.atoms[i];
+  const int t1 = a1.type;
+  const int nn = P.nn_a[i];
+  const size_t plane = (size_t)P.mn_a * N;
+  for (int m = 0; m < nn; ++m) {
+    const int j = P.nl_a[(size_t)m * N + i];
+    const B2Atom a2 = P.atoms[j];
+    float x12, y12, z12;
+    b2_r12(box, a1, a2, x12, y12, z12);
+    const float d = sqrtf(b2_d2(x12, y12, z12));
+    const float dinv = 1.0f / d;
+    const int pair = t1 * P.nt + a2.type;
+    float fn[K1], fnp[K1];
+    b2_basis_d<K1, true>(d, B2_LDG(&P.rc_a[pair]), B2_LDG(&P.rcinv_a[pair]), fn, fnp);
+    float W[B2_NABC], Wp[B2_NABC];
+#pragma unroll
+    for (int abc = 0; abc < B2_NABC; ++abc) {
+      W[abc] = 0.0f;
+      Wp[abc] = 0.0f;
+    }
+    for (int n = 0; n < P.na1; ++n) {
+      const float* cc = P.c_a + ((size_t)pair * P.na1 + n) * K1;
+      float g = 0.0f, gp = 0.0f;
+#pragma unroll
+      for (int k = 0; k < K1; ++k) {
+        const float ck = B2_LDG(&cc[k]);
+        g = fmaf(fn[k], ck, g);
+        gp = fmaf(fnp[k], ck, gp);
+      }
+      const float* wn = w + (size_t)(n * B2_NABC) * stride + lane;
+#pragma unroll
+      for (int abc = 0; abc < B2_NABC; ++abc) {
+        const float wv = wn[(size_t)abc * stride];
+        W[abc] = fmaf(g, wv, W[abc]);
+        Wp[abc] = fmaf(gp, wv, Wp[abc]);
+      }
+    }
+    const float xh = x12 * dinv, yh = y12 * dinv, zh = z12 * dinv;
+    float B[B2_NABC];
+    b2_harmonics(xh, yh, zh, B);
+    // radial part: sum_abc (g' - L g / r) w b(rhat)
+    float ar = 0.0f, al = 0.0f;
+    {
+      int st = 0;
+#pragma unroll
+      for (int L = 1; L <= 4; ++L) {
+        float tl = 0.0f;
+#pragma unroll
+        for (int k = 0; k < 2 * L + 1; ++k) {
+          ar = fmaf(Wp[st + k], B[st + k], ar);
+          tl = fmaf(W[st + k], B[st + k], tl);
+        }
+        al = fmaf((float)L, tl, al);
+        st += 2 * L + 1;
+      }
+    }
+    float gx, gy, gz;
+    b2_harmonics_grad_dot(xh, yh, zh, W, gx, gy, gz);
+    const float rad = ar - al * dinv;
+    const size_t slot = (size_t)m * N + i;
+    P.f12[slot] = fmaf(rad, xh, gx * dinv);
+    P.f12[plane + slot] = fmaf(rad, yh, gy * dinv);
+    P.f12[2 * plane + slot] = fmaf(rad, zh, gz * dinv);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// F_i = sum_j (f12_ij - f12_ji), W_i = sum_j r_ij (x) f12_ji
+// (gpu_find_force_many_body, src/force/potential.cu:170-297; the reverse slot is found by binary
+// search in j's ascending list, potential.cu:226-247)
+// ---------------------------------------------------------------------------------------------
+B2_HD void b2_body_reduce_angular(int i, const B2NepView& P, const B2Box& box)
+{
+  const size_t N = (size_t)P.n;
+  const size_t plane = (size_t)P.mn_a * N;
+  const B2Atom a1 = P.atoms[i];
+  const int nn = P.nn_a[i];
+  float f[3] = {0.0f, 0.0f, 0.0f};
+  float v[9] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f}; // row-major r (x) f21
+  for (int m = 0; m < nn; ++m) {
+    const size_t slot = (size_t)m * N + i;
+    const int j = P.nl_a[slot];
+    const B2Atom a2 = P.atoms[j];
+    double xd = a2.x - a1.x, yd = a2.y - a1.y, zd = a2.z - a1.z;
+    b2_mic(box, xd, yd, zd); // potential.cu:211-217: FP64 minimum image, then narrowed
+    const float r[3] = {(float)xd, (float)yd, (float)zd};
+    int lo = 0, hi = P.nn_a[j] - 1, rev = 0;
+    while (lo <= hi) {
+      const int mid = (lo + hi) >> 1;
+      const int v2 = P.nl_a[(size_t)mid * N + j];
+      if (v2 < i)
+        lo = mid + 1;
+      else if (v2 > i)
+        hi = mid - 1;
+      else {
+        rev = mid;
+        break;
+      }
+    }
+    const size_t rslot = (size_t)rev * N + j;
+    const float f12[3] = {P.f12[slot], P.f12[plane + slot], P.f12[2 * plane + slot]};
+    const float f21[3] = {P.f12[rslot], P.f12[plane + rslot], P.f12[2 * plane + rslot]};
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+      f[a] += f12[a] - f21[a];
+#pragma unroll
+      for (int b = 0; b < 3; ++b)
+        v[a * 3 + b] = fmaf(r[a], f21[b], v[a * 3 + b]);
+    }
+  }
+  double* a = P.acc + i;
+  a[1 * N] += f[0];
+  a[2 * N] += f[1];
+  a[3 * N] += f[2];
+  a[4 * N] += v[0];  // xx
+  a[5 * N] += v[4];  // yy
+  a[6 * N] += v[8];  // zz
+  a[7 * N] += v[1];  // xy
+  a[8 * N] += v[2];  // xz
+  a[9 * N] += v[5];  // yz
+  a[10 * N] += v[3]; // yx
+  a[11 * N] += v[6]; // zx
+  a[12 * N] += v[7]; // zy
+}
+
+// ---------------------------------------------------------------------------------------------
+// ZBL pair repulsion over the angular list (find_force_ZBL, nep.cu:863-975;
+// find_f_and_fp_zbl nep_utilities.cuh:433-508)
+// ---------------------------------------------------------------------------------------------
+B2_HD void b2_zbl_pair(
+  const float* para8 /* a0,b0,...,a3,b3 */, float r1, float r2, float zizj, float a_inv, float d,
+  float dinv, float& f, float& fp)
+{
+  const float x = d * a_inv;
+  float phi = 0.0f, phip = 0.0f;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float t = para8[2 * k] * expf(-para8[2 * k + 1] * x);
+    phi += t;
+    phip -= para8[2 * k + 1] * t;
+  }
+  phi *= zizj;
+  phip *= zizj * a_inv;
+  phip = phip * dinv - phi * dinv * dinv;
+  phi *= dinv;
+  float fc, fcp;
+  if (d < r1) {
+    fc = 1.0f;
+    fcp = 0.0f;
+  } else if (d < r2) {
+    const float pf = 3.1415927f / (r2 - r1);
+    fc = cosf(pf * (d - r1)) * 0.5f + 0.5f;
+    fcp = -sinf(pf * (d - r1)) * pf * 0.5f;
+  } else {
+    fc = 0.0f;
+    fcp = 0.0f;
+  }
+  fp = phip * fc + phi * fcp;
+  f = phi * fc;
+}
+
+B2_HD void b2_body_zbl(int i, const B2NepView& P, const B2Box& box)
+{
+  const size_t N = (size_t)P.n;
+  const B2Atom a1 = P.atoms[i];
+  const int ty1 = a1.type;
+  const int zi = B2_LDG(&P.zbl_z[ty1]);
+  const float pzi = powf((float)zi, 0.23f);
+  const int nn = P.nn_a[i];
+  float pe = 0.0f, f[3] = {0.0f, 0.0f, 0.0f};
+  float vxx = 0.0f, vyy = 0.0f, vzz = 0.0f, vxy = 0.0f, vxz = 0.0f, vyz = 0.0f;
+  for (int m = 0; m < nn; ++m) {
+    const int j = P.nl_a[(size_t)m * N + i];
+    const B2Atom a2 = P.atoms[j];
+    float x12, y12, z12;
+    b2_r12(box, a1, a2, x12, y12, z12);
+    const float d = sqrtf(b2_d2(x12, y12, z12));
+    const float dinv = 1.0f / d;
+    const int ty2 = a2.type;
+    const int zj = B2_LDG(&P.zbl_z[ty2]);
+    const float a_inv = (pzi + powf((float)zj, 0.23f)) * 2.134563f;
+    const float zizj = 14.399645f * (float)zi * (float)zj; // K_C_SP, common.cuh:23
+    float fv, fpv;
+    if (P.zbl_flexible) {
+      const int ta = ty1 < ty2 ? ty1 : ty2, tb = ty1 < ty2 ? ty2 : ty1;
+      const int zidx = ta * P.nt - (ta * (ta - 1)) / 2 + (tb - ta);
+      float para[10];
+#pragma unroll
+      for (int k = 0; k < 10; ++k)
+        para[k] = B2_LDG(&P.zbl_para[10 * zidx + k]);
+      b2_zbl_pair(para + 2, para[0], para[1], zizj, a_inv, d, dinv, fv, fpv);
+    } else {
+      const float uni[8] = {0.18175f, 3.1998f, 0.50986f, 0.94229f,
+                            0.28022f, 0.4029f, 0.02817f, 0.20162f};
+      float rin = P.zbl_rc_inner, rout = P.zbl_rc_outer;
+      if (P.zbl_typewise) {
+        const float tw =
+          (B2_LDG(&P.cov_radius[zi - 1]) + B2_LDG(&P.cov_radius[zj - 1])) * P.zbl_typewise_factor;
+        rout = fminf(tw, rout);
+        rin = 0.0f;
+      }
+      b2_zbl_pair(uni, rin, rout, zizj, a_inv, d, dinv, fv, fpv);
+    }
+    const float f2 = fpv * dinv * 0.5f; // f12 = r12 * f2, f21 = -f12
+    f[0] += 2.0f * (x12 * f2);
+    f[1] += 2.0f * (y12 * f2);
+    f[2] += 2.0f * (z12 * f2);
+    vxx -= x12 * (x12 * f2);
+    vyy -= y12 * (y12 * f2);
+    vzz -= z12 * (z12 * f2);
+    vxy -= x12 * (y12 * f2);
+    vxz -= x12 * (z12 * f2);
+    vyz -= y12 * (z12 * f2);
+    pe += fv * 0.5f;
+  }
+  double* a = P.acc + i;
+  a[0] += pe;
+  a[1 * N] += f[0];
+  a[2 * N] += f[1];
+  a[3 * N] += f[2];
+  a[4 * N] += vxx;
+  a[5 * N] += vyy;
+  a[6 * N] += vzz;
+  a[7 * N] += vxy;
+  a[8 * N] += vxz;
+  a[9 * N] += vyz;
+  a[10 * N] += vxy;
+  a[11 * N] += vxz;
+  a[12 * N] += vyz;
+}
+
+// ---------------------------------------------------------------------------------------------
+// scatter the sorted-order results back to the caller's arrays with += (the accumulate
+// convention of Potential::compute, nep.cu:653, 755-770)
+// ---------------------------------------------------------------------------------------------
+B2_HD void b2_body_unpack(
+  int i, int n, const int* perm, const double* acc, double* pe, double* force, double* virial)
+{
+  const int dst = perm[i];
+  const size_t N = (size_t)n;
+  pe[dst] += acc[i];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    force[k * N + dst] += acc[(1 + k) * N + i];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+    virial[k * N + dst] += acc[(4 + k) * N + i];
+}

@@ -1,0 +1,38 @@
+// b2_nep_model.h -- host-side NEP model: nep.txt parser and the flattened tables the kernels use.
+// File format and parameter order follow the reference's NEP::NEP / update_potential
+// (src/force/nep.cu:100-434); the table layouts are this library's own (see B2NepView).
+#pragma once
+#include <string>
+#include <vector>
+
+namespace b2 {
+
+struct NepModel {
+  int version = 4;
+  int nt = 0;
+  std::vector<std::string> symbols;
+  std::vector<int> atomic_numbers;
+  bool zbl_enabled = false, zbl_flexible = false, zbl_typewise = false;
+  float zbl_rc_inner = 0.0f, zbl_rc_outer = 0.0f, zbl_typewise_factor = 0.65f;
+  std::vector<float> zbl_para;
+  std::vector<float> rc_radial, rc_angular; // per type
+  float rc_radial_max = 0.0f, rc_angular_max = 0.0f;
+  int MN_radial = 0, MN_angular = 0; // enlarged by 1.25 (nep.cu:234-235)
+  int n_max_radial = 0, n_max_angular = 0, basis_size_radial = 0, basis_size_angular = 0;
+  int L_max = 0, has222 = 0, has1111 = 0, num_L = 0, dim_angular = 0, dim = 0, nneu = 0;
+
+  // derived sizes
+  int nr1 = 0, na1 = 0, kr1 = 0, ka1 = 0, K1R = 0, K1A = 0, KP = 0, UST = 0, DIMP = 0;
+
+  // flattened tables (see B2NepView for layouts)
+  std::vector<float> rc_r, rcinv_r, rc2_r, rc_a, rcinv_a, rc2_a; // [nt*nt]
+  std::vector<float> c_r, c_a, w0p, b0, w1, bias, q_scaler;
+
+  // returns empty string on success, else the error message
+  std::string load(const char* path);
+};
+
+extern const float COVALENT_RADIUS[94];
+int atomic_number_of(const std::string& symbol); // 0 if unknown
+
+} // namespace b2

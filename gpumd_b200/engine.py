@@ -1,0 +1,249 @@
+"""Python mirror of GPUMD's plugin surface for the hot path, over the libb200md C-ABI.
+
+Class and method names follow the reference (paths relative to the GPUMD tree):
+  Box            src/model/box.cuh:18-35
+  Atom           src/model/atom.cuh:21-52        (SoA float64 device arrays)
+  Potential      src/force/potential.cuh:20-113  (compute(box, type, position, potential, force, virial))
+  NEP, LJ        src/force/nep.cuh:27-184, src/force/lj.cuh:31-49
+  Force          src/force/force.cuh:27-85       (parse_potential, compute)
+  Ensemble_NVE   src/integrate/ensemble_nve.cuh  (compute1, compute2)
+The C++ adapters a GPUMD maintainer would compile into the reference live in gpumd_b200/host/.
+
+Device arrays are torch CUDA tensors (torch = allocator + stream provider only); all arithmetic
+happens in libb200md.so.  Without the library or without a GPU these classes raise.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import lib as _lib
+
+K_B = 8.617343e-5                    # src/utilities/common.cuh:21
+TIME_UNIT_CONVERSION = 1.018051e+1   # src/utilities/common.cuh:26
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise _lib.B200mdError("no CUDA device: gpumd_b200 has no CPU fallback")
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+class Box:
+    """cpu_h[0..8] (row-major, lattice vectors as columns) + pbc flags."""
+
+    def __init__(self, h, pbc=(1, 1, 1)):
+        self.cpu_h = np.ascontiguousarray(np.asarray(h, dtype=np.float64).reshape(9))
+        self.pbc = np.ascontiguousarray(np.asarray(pbc, dtype=np.int32).reshape(3))
+
+    def get_volume(self):
+        return abs(float(np.linalg.det(self.cpu_h.reshape(3, 3))))
+
+    @property
+    def _h(self):
+        return self.cpu_h.ctypes.data_as(C.POINTER(C.c_double))
+
+    @property
+    def _p(self):
+        return self.pbc.ctypes.data_as(C.POINTER(C.c_int))
+
+
+class Atom:
+    """Per-atom device state, same arrays and layouts as GPUMD's Atom."""
+
+    def __init__(self, type_, position, mass, velocity=None, device="cuda"):
+        _require_cuda()
+        n = int(np.asarray(type_).shape[0])
+        self.number_of_atoms = n
+        dev = torch.device(device)
+        self.type = torch.as_tensor(np.ascontiguousarray(type_, dtype=np.int32), device=dev)
+        self.position_per_atom = torch.as_tensor(
+            np.ascontiguousarray(position, dtype=np.float64).reshape(3 * n), device=dev)
+        self.mass = torch.as_tensor(np.ascontiguousarray(mass, dtype=np.float64), device=dev)
+        v = np.zeros(3 * n) if velocity is None else np.ascontiguousarray(
+            velocity, dtype=np.float64).reshape(3 * n)
+        self.velocity_per_atom = torch.as_tensor(v, device=dev)
+        self.force_per_atom = torch.zeros(3 * n, dtype=torch.float64, device=dev)
+        self.virial_per_atom = torch.zeros(9 * n, dtype=torch.float64, device=dev)
+        self.potential_per_atom = torch.zeros(n, dtype=torch.float64, device=dev)
+
+
+class Potential:
+    """Abstract base, src/force/potential.cuh:20-113."""
+
+    N1 = 0
+    N2 = 0
+    rc = 0.0
+
+    def compute(self, box, type_, position, potential, force, virial):
+        raise NotImplementedError
+
+
+class NEP(Potential):
+    """NEP(file_potential, num_atoms), src/force/nep.cu:100-395; compute = nep.cu:1356-1389."""
+
+    def __init__(self, file_potential, num_atoms):
+        _require_cuda()
+        self._L = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._L.b200md_nep_create(str(file_potential).encode(), int(num_atoms), C.byref(h)))
+        self._h = h
+        self.N1, self.N2 = 0, int(num_atoms)
+        self.rc = self._L.b200md_nep_rc(h)
+        self.num_types = self._L.b200md_nep_info(h, 0)
+        self.dim = self._L.b200md_nep_info(h, 1)
+        self.MN_radial = self._L.b200md_nep_info(h, 3)
+        self.MN_angular = self._L.b200md_nep_info(h, 4)
+        self.symbols = [self._L.b200md_nep_symbol(h, t).decode() for t in range(self.num_types)]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.b200md_nep_destroy(self._h)
+            self._h = None
+
+    def compute(self, box, type_, position, potential, force, virial):
+        n = type_.shape[0]
+        _lib.check(self._L.b200md_nep_compute(
+            self._h, n, box._h, box._p, _ptr(type_), _ptr(position), _ptr(potential), _ptr(force),
+            _ptr(virial), _stream()))
+
+    def compute_host(self, box, type_, position, potential, force, virial):
+        """Host (numpy or pinned torch CPU) buffers in and out; outputs are overwritten."""
+        n = int(type_.shape[0])
+
+        def p(a):
+            return C.c_void_p(a.data_ptr() if isinstance(a, torch.Tensor) else a.ctypes.data)
+
+        _lib.check(self._L.b200md_nep_compute_host(
+            self._h, n, box._h, box._p, p(type_), p(position), p(potential), p(force), p(virial)))
+
+    def check(self):
+        _lib.check(self._L.b200md_nep_check(self._h, _stream()))
+
+    @property
+    def num_rebuilds(self):
+        return self._L.b200md_nep_info(self._h, 6)
+
+    def export_neighbors(self, mn_r=None, mn_a=None):
+        """(NN_radial, NL_radial[n,mn_r], NN_angular, NL_angular[n,mn_a]) of the last compute, in the
+        caller's atom indices, ascending; -1 padded."""
+        n = self.N2
+        mn_r = mn_r or self.MN_radial
+        mn_a = mn_a or self.MN_angular
+        dev = torch.device("cuda")
+        NNr = torch.zeros(n, dtype=torch.int32, device=dev)
+        NLr = torch.full((n, mn_r), -1, dtype=torch.int32, device=dev)
+        NNa = torch.zeros(n, dtype=torch.int32, device=dev)
+        NLa = torch.full((n, mn_a), -1, dtype=torch.int32, device=dev)
+        _lib.check(self._L.b200md_nep_export_neighbors(
+            self._h, mn_r, _ptr(NNr), _ptr(NLr), mn_a, _ptr(NNa), _ptr(NLa), _stream()))
+        self.check()
+        return NNr.cpu().numpy(), NLr.cpu().numpy(), NNa.cpu().numpy(), NLa.cpu().numpy()
+
+    def export_descriptors(self):
+        q = torch.zeros(self.dim, self.N2, dtype=torch.float32, device="cuda")
+        _lib.check(self._L.b200md_nep_export_descriptors(self._h, _ptr(q), _stream()))
+        return q.cpu().numpy()
+
+
+class LJ(Potential):
+    """LJ potential; the file is the whole potential file ("lj Nt sym..." + Nt^2 lines),
+    src/force/lj.cu:28-59; compute = lj.cu:184-219."""
+
+    def __init__(self, file_potential, num_atoms):
+        _require_cuda()
+        self._L = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._L.b200md_lj_create(str(file_potential).encode(), int(num_atoms), C.byref(h)))
+        self._h = h
+        self.N1, self.N2 = 0, int(num_atoms)
+        self.rc = self._L.b200md_lj_rc(h)
+        self.num_types = self._L.b200md_lj_info(h, 0)
+        self.symbols = [self._L.b200md_lj_symbol(h, t).decode() for t in range(self.num_types)]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.b200md_lj_destroy(self._h)
+            self._h = None
+
+    def compute(self, box, type_, position, potential, force, virial):
+        n = type_.shape[0]
+        _lib.check(self._L.b200md_lj_compute(
+            self._h, n, box._h, box._p, _ptr(type_), _ptr(position), _ptr(potential), _ptr(force),
+            _ptr(virial), _stream()))
+
+    def check(self):
+        _lib.check(self._L.b200md_lj_check(self._h, _stream()))
+
+    @property
+    def num_rebuilds(self):
+        return self._L.b200md_lj_info(self._h, 6)
+
+
+class Force:
+    """Force driver, src/force/force.cu: parse_potential (75-218) and compute (771-985)."""
+
+    def __init__(self):
+        self.potentials = []
+        self._L = _lib.load()
+
+    def parse_potential(self, file_potential, num_atoms):
+        with open(file_potential) as f:
+            first = f.readline().split()[0]
+        if first.startswith("nep"):
+            pot = NEP(file_potential, num_atoms)
+        elif first == "lj":
+            pot = LJ(file_potential, num_atoms)
+        else:
+            raise _lib.B200mdError(f"illegal potential model '{first}' for gpumd_b200")
+        self.potentials = [pot]
+        return pot
+
+    def compute(self, box, position, type_, potential, force, virial):
+        n = type_.shape[0]
+        st = _stream()
+        _lib.check(self._L.b200md_apply_pbc(n, box._h, box._p, _ptr(position), st))
+        _lib.check(self._L.b200md_zero_properties(n, _ptr(potential), _ptr(force), _ptr(virial), st))
+        self.potentials[0].compute(box, type_, position, potential, force, virial)
+
+
+class Ensemble_NVE:
+    """NVE integrator, src/integrate/ensemble_nve.cu:31-95 (velocity-Verlet + thermo)."""
+
+    def __init__(self, num_atoms):
+        _require_cuda()
+        self._L = _lib.load()
+        nbytes = self._L.b200md_thermo_scratch_bytes(int(num_atoms))
+        self._scratch = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+
+    def compute1(self, time_step, box, atom, thermo=None):
+        _lib.check(self._L.b200md_velocity_verlet(
+            1, atom.number_of_atoms, float(time_step), _ptr(atom.mass),
+            _ptr(atom.position_per_atom), _ptr(atom.velocity_per_atom), _ptr(atom.force_per_atom),
+            _stream()))
+
+    def compute2(self, time_step, box, atom, thermo):
+        n = atom.number_of_atoms
+        st = _stream()
+        _lib.check(self._L.b200md_velocity_verlet(
+            0, n, float(time_step), _ptr(atom.mass), _ptr(atom.position_per_atom),
+            _ptr(atom.velocity_per_atom), _ptr(atom.force_per_atom), st))
+        self.find_thermo(box.get_volume(), atom, thermo)
+
+    def find_thermo(self, volume, atom, thermo):
+        n = atom.number_of_atoms
+        _lib.check(self._L.b200md_find_thermo(
+            n, n, float(volume), _ptr(atom.mass), _ptr(atom.potential_per_atom),
+            _ptr(atom.velocity_per_atom), _ptr(atom.virial_per_atom), _ptr(thermo),
+            _ptr(self._scratch), _stream()))
+
+
+def launch_count():
+    return _lib.load().b200md_launch_count()

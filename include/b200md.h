@@ -1,0 +1,130 @@
+/*
+ * b200md.h -- C-ABI of libb200md.so: the Blackwell-native (sm_100a) MD hot path that drops in
+ * behind GPUMD's Potential / Ensemble plugin surface.
+ *
+ * Every entry point states the reference interface it replaces (paths relative to the GPUMD
+ * tree, commit d98135d).  Conventions on this boundary are GPUMD's own:
+ *   - all `d_*` pointers are DEVICE pointers owned by the caller (GPUMD's GPU_Vector<T>);
+ *     the library owns only its scratch (cell lists, neighbour lists, descriptor buffers);
+ *   - per-atom arrays are SoA: position[3N] = x[N],y[N],z[N] (src/model/atom.cuh:21-52),
+ *     virial[9N] = xx,yy,zz,xy,xz,yz,yx,zx,zy blocks of N (src/force/force.cu:859-861);
+ *   - h[9] is Box::cpu_h[0..8] (src/model/box.cuh:18-35): row-major, lattice vectors as columns;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, which is what
+ *     every reference kernel uses);
+ *   - functions return 0 on success, non-zero on error; b200md_last_error() describes it.
+ *     (The reference prints and exit(1)s, src/utilities/error.cuh:22-62; the C++ adapter in
+ *     gpumd_b200/host does exactly that with these codes.)
+ *   - work is enqueued asynchronously; capacity overflows detected on the device are latched
+ *     and reported by b200md_*_check(), which synchronises the stream.
+ * There is no CPU fallback anywhere behind this interface.
+ */
+#ifndef B200MD_H
+#define B200MD_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200MD_OK 0
+#define B200MD_ERR_ARG 1       /* bad argument / unsupported model */
+#define B200MD_ERR_IO 2        /* cannot read potential file */
+#define B200MD_ERR_CUDA 3      /* CUDA runtime error */
+#define B200MD_ERR_SMALL_BOX 4 /* periodic thickness <= 2.5*(rc+1): reference's small-box path */
+#define B200MD_ERR_OVERFLOW 5  /* neighbour / cell capacity exceeded on the device */
+
+const char* b200md_last_error(void);
+/* number of kernels this library has launched since load (bench.py's gpu_launches) */
+long long b200md_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * NEP potential.  Replaces class NEP : Potential (src/force/nep.cuh:27-184):
+ *   b200md_nep_create  <- NEP::NEP(const char* file_potential, const int num_atoms), nep.cu:100-395
+ *   b200md_nep_compute <- NEP::compute(Box&, type, position, potential, force, virial),
+ *                         nep.cu:1356-1389 -> compute_large_box nep.cu:978-1138
+ *                         (outputs are ACCUMULATED with += exactly like nep.cu:653,755-770)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b200md_nep b200md_nep;
+
+int b200md_nep_create(const char* nep_txt_path, int num_atoms, b200md_nep** out);
+void b200md_nep_destroy(b200md_nep* p);
+
+/* what: 0 num_types, 1 descriptor dim, 2 neurons, 3 MN_radial (enlarged), 4 MN_angular
+ * (enlarged), 5 zbl enabled, 6 number of neighbour-list rebuilds so far */
+int b200md_nep_info(const b200md_nep* p, int what);
+double b200md_nep_rc(const b200md_nep* p); /* Potential::rc, src/force/potential.cuh:32 */
+/* atomic symbol of type t (species -> type index mapping, src/model/read_xyz.cu:349-361) */
+const char* b200md_nep_symbol(const b200md_nep* p, int t);
+
+int b200md_nep_compute(
+  b200md_nep* p, int n, const double h[9], const int pbc[3], const int* d_type,
+  const double* d_position, double* d_potential, double* d_force, double* d_virial, void* stream);
+
+/* Same call with HOST buffers (pageable or pinned): copies type/position in, runs the path,
+ * ACCUMULATES into the host outputs after copying them... no: OVERWRITES potential[n],
+ * force[3n], virial[9n] with the result.  This is the end-to-end entry bench.py times. */
+int b200md_nep_compute_host(
+  b200md_nep* p, int n, const double h[9], const int pbc[3], const int* type,
+  const double* position, double* potential, double* force, double* virial);
+
+/* Parity hook: the radial / angular neighbour sets of the LAST compute call, mapped back to the
+ * caller's atom indices, ascending, row-major NL[i*mn + k] -- the quantity the reference builds
+ * in find_neighbor_list_large_box (nep.cu:436-486).  Device pointers. */
+int b200md_nep_export_neighbors(
+  b200md_nep* p, int mn_r, int* d_NN_r, int* d_NL_r, int mn_a, int* d_NN_a, int* d_NL_a,
+  void* stream);
+/* Parity hook: scaled descriptors q[d*N + i] (caller order) of the last compute call. */
+int b200md_nep_export_descriptors(b200md_nep* p, float* d_q, void* stream);
+
+/* synchronise and report latched device-side errors (B200MD_ERR_OVERFLOW) */
+int b200md_nep_check(b200md_nep* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * LJ potential.  Replaces class LJ : Potential (src/force/lj.cuh:31-49):
+ *   b200md_lj_create  <- LJ::LJ(FILE*, int num_types, int num_atoms), lj.cu:28-59
+ *                        (the file is the whole potential file, first line "lj Nt sym...")
+ *   b200md_lj_compute <- LJ::compute, lj.cu:184-219
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b200md_lj b200md_lj;
+int b200md_lj_create(const char* lj_txt_path, int num_atoms, b200md_lj** out);
+void b200md_lj_destroy(b200md_lj* p);
+double b200md_lj_rc(const b200md_lj* p);
+int b200md_lj_info(const b200md_lj* p, int what); /* 0 num_types, 6 rebuild count */
+const char* b200md_lj_symbol(const b200md_lj* p, int t);
+int b200md_lj_compute(
+  b200md_lj* p, int n, const double h[9], const int pbc[3], const int* d_type,
+  const double* d_position, double* d_potential, double* d_force, double* d_virial, void* stream);
+int b200md_lj_check(b200md_lj* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Force::compute pre-steps (src/force/force.cu:771-801):
+ *   b200md_apply_pbc        <- gpu_apply_pbc, force.cu:424-459
+ *   b200md_zero_properties  <- initialize_properties, force.cu:314-333
+ * ------------------------------------------------------------------------------------------ */
+int b200md_apply_pbc(int n, const double h[9], const int pbc[3], double* d_position, void* stream);
+int b200md_zero_properties(
+  int n, double* d_potential, double* d_force, double* d_virial, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Integrator kernels behind Ensemble::compute1 / compute2 (src/integrate/ensemble.cuh:26-157):
+ *   b200md_velocity_verlet <- Ensemble::velocity_verlet / gpu_velocity_verlet,
+ *                             ensemble.cu:176-214,348-397 (no fixed/move groups)
+ *   b200md_find_thermo     <- Ensemble::find_thermo / gpu_find_thermo_instant_temperature,
+ *                             ensemble.cu:434-673: d_thermo[0..7] = T,U,sxx,syy,szz,sxy,sxz,syz
+ *   b200md_scale_velocity  <- Ensemble::scale_velocity_global, ensemble.cu:676-698
+ * time_step is in GPUMD natural units (fs / 10.18051, src/utilities/common.cuh:26).
+ * d_scratch for find_thermo: at least b200md_thermo_scratch_bytes(n) bytes of device memory.
+ * ------------------------------------------------------------------------------------------ */
+int b200md_velocity_verlet(
+  int is_step1, int n, double time_step, const double* d_mass, double* d_position,
+  double* d_velocity, const double* d_force, void* stream);
+long long b200md_thermo_scratch_bytes(int n);
+int b200md_find_thermo(
+  int n, int n_temperature, double volume, const double* d_mass, const double* d_potential,
+  const double* d_velocity, const double* d_virial, double* d_thermo8, void* d_scratch,
+  void* stream);
+int b200md_scale_velocity(int n, double factor, double* d_velocity, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

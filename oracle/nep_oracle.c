@@ -346,20 +346,20 @@ void oracle_mic_f32(const oracle_box* b, float* x, float* y, float* z)
         *z -= h[8];
     }
   } else {
-    /* device code is compiled with FMA contraction; the exact contraction pattern is
-       irrelevant at the tolerance level triclinic parity is checked at */
-    float sx = h[9] * *x + h[10] * *y + h[11] * *z;
-    float sy = h[12] * *x + h[13] * *y + h[14] * *z;
-    float sz = h[15] * *x + h[16] * *y + h[17] * *z;
+    /* fma nesting nvcc's default contraction gives `a*x + b*y + c*z`: fma(c,z, fma(a,x, b*y))
+       (same DAG shape as oracle_d2_f32; checked on PTX) */
+    float sx = fmaf(h[11], *z, fmaf(h[9], *x, h[10] * *y));
+    float sy = fmaf(h[14], *z, fmaf(h[12], *x, h[13] * *y));
+    float sz = fmaf(h[17], *z, fmaf(h[15], *x, h[16] * *y));
     if (b->pbc[0])
       sx -= nearbyintf(sx);
     if (b->pbc[1])
       sy -= nearbyintf(sy);
     if (b->pbc[2])
       sz -= nearbyintf(sz);
-    *x = h[0] * sx + h[1] * sy + h[2] * sz;
-    *y = h[3] * sx + h[4] * sy + h[5] * sz;
-    *z = h[6] * sx + h[7] * sy + h[8] * sz;
+    *x = fmaf(h[2], sz, fmaf(h[0], sx, h[1] * sy));
+    *y = fmaf(h[5], sz, fmaf(h[3], sx, h[4] * sy));
+    *z = fmaf(h[8], sz, fmaf(h[6], sx, h[7] * sy));
   }
 }
 

@@ -1,0 +1,58 @@
+"""Seeded input structures shared by the CPU and GPU parity tests (all large-box)."""
+import numpy as np
+
+from conftest import GOLDEN
+from gpumd_b200.structures import diamond, fcc, nep_type_order, read_xyz, rocksalt_pbte
+
+
+def shear(s, xy=0.15, yz=-0.1, xz=0.05):
+    """Same fractional coordinates in a triclinic box."""
+    Hm = s["h"].reshape(3, 3).copy()
+    Hn = Hm.copy()
+    Hn[0, 1] = xy * Hm[0, 0]
+    Hn[1, 2] = yz * Hm[1, 1]
+    Hn[0, 2] = xz * Hm[0, 0]
+    frac = np.linalg.solve(Hm, s["pos"])
+    s = dict(s)
+    s["pos"] = np.ascontiguousarray(Hn @ frac)
+    s["h"] = Hn.reshape(9)
+    return s
+
+
+def bazro3_supercell(reps=3, seed=5):
+    order = nep_type_order(GOLDEN / "nep_BaZrO3.txt")
+    b = read_xyz(GOLDEN / "BaZrO3-nat40-rattled.xyz", order)
+    L = b["h"][0]
+    shifts = np.array([[i, j, k] for i in range(reps) for j in range(reps) for k in range(reps)], float) * L
+    pos = (b["pos"].T[None, :, :] + shifts[:, None, :]).reshape(-1, 3)
+    pos += np.random.default_rng(seed).normal(0, 0.02, pos.shape)
+    pos = np.mod(pos, L * reps)
+    return dict(pos=np.ascontiguousarray(pos.T), type=np.tile(b["type"], reps ** 3).astype(np.int32),
+                h=np.diag([L * reps] * 3).reshape(9).astype(np.float64), pbc=np.array([1, 1, 1], np.int32))
+
+
+def slab(s):
+    """Open boundary along z: widen the box by 12 A of vacuum and switch pbc_z off."""
+    s = dict(s)
+    h = s["h"].copy()
+    h[8] += 12.0
+    s["h"] = h
+    s["pbc"] = np.array([1, 1, 0], np.int32)
+    return s
+
+
+# name -> (model file, structure factory)
+NEP_CASES = {
+    # the headline model: 2 types, D=30, rc 8/4, 3-body only
+    "PbTe": ("nep_PbTe.txt", lambda: rocksalt_pbte(4, rattle=0.05, seed=1)),
+    "PbTe_triclinic": ("nep_PbTe.txt", lambda: shear(rocksalt_pbte(4, rattle=0.05, seed=2))),
+    "PbTe_slab": ("nep_PbTe.txt", lambda: slab(rocksalt_pbte(4, rattle=0.05, seed=4))),
+    # 1 type, basis 10/8 (padded to 13/9), n_max 10/8, 4- and 5-body terms, D=65
+    "carbon": ("nep_C_2022_NEP4.txt", lambda: diamond(5, a=3.57, rattle=0.05, seed=3, symbol="C")),
+    # 3 types (shared-memory accumulator path), n_max 8/6, D=44, ~170 radial neighbours
+    "BaZrO3": ("nep_BaZrO3.txt", lambda: bazro3_supercell()),
+    # 16 types, universal ZBL, 4- and 5-body terms (config C4's model)
+    "UNEP": ("nep_UNEP_v1.txt", lambda: fcc(
+        6, 3.9, rattle=0.08, seed=7, num_types=16,
+        symbols=nep_type_order(GOLDEN / "nep_UNEP_v1.txt"))),
+}

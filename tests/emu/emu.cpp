@@ -1,0 +1,447 @@
+// tests/emu/emu.cpp -- TEST INFRASTRUCTURE ONLY.
+//
+// Compiles the kernel BODIES of libb200md (gpumd_b200/csrc/*.cuh) for the host and drives them
+// with plain loops, so the arithmetic and the list logic can be checked against the oracle in
+// the GPU-less build container (`pytest -m "not gpu"`).  Nothing here is part of the product:
+// libb200md.so never links or loads this file, and this library is never used by bench.py,
+// __graft_entry__.py or the gpumd_b200 package.  The block-cooperative pieces of the real kernels
+// (scan, shared-memory tile sort, atomics, warp reductions) are replaced by serial loops here
+// and are therefore covered only by the `-m gpu` tests.
+#include "../../gpumd_b200/csrc/b2_common.cuh"
+#include "../../gpumd_b200/csrc/b2_integrate.cuh"
+#include "../../gpumd_b200/csrc/b2_lj.cuh"
+#include "../../gpumd_b200/csrc/b2_neighbor.cuh"
+#include "../../gpumd_b200/csrc/b2_nep.cuh"
+#include "../../gpumd_b200/csrc/b2_nep_model.h"
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace {
+
+B2Box make_box(const double h[9], const int pbc[3])
+{
+  B2Box b;
+  double* c = b.h;
+  for (int d = 0; d < 9; ++d)
+    c[d] = h[d];
+  for (int d = 0; d < 3; ++d)
+    b.pbc[d] = pbc[d] ? 1 : 0;
+  c[9] = c[4] * c[8] - c[5] * c[7];
+  c[10] = c[2] * c[7] - c[1] * c[8];
+  c[11] = c[1] * c[5] - c[2] * c[4];
+  c[12] = c[5] * c[6] - c[3] * c[8];
+  c[13] = c[0] * c[8] - c[2] * c[6];
+  c[14] = c[2] * c[3] - c[0] * c[5];
+  c[15] = c[3] * c[7] - c[4] * c[6];
+  c[16] = c[1] * c[6] - c[0] * c[7];
+  c[17] = c[0] * c[4] - c[1] * c[3];
+  const double det = c[0] * c[9] + c[1] * c[12] + c[2] * c[15];
+  for (int d = 9; d < 18; ++d)
+    c[d] /= det;
+  b.volume = std::fabs(det);
+  for (int d = 0; d < 3; ++d) {
+    const int p = (d + 1) % 3, q = (d + 2) % 3;
+    const double u[3] = {c[p], c[p + 3], c[p + 6]}, w[3] = {c[q], c[q + 3], c[q + 6]};
+    const double s0 = u[1] * w[2] - u[2] * w[1], s1 = u[2] * w[0] - u[0] * w[2],
+                 s2 = u[0] * w[1] - u[1] * w[0];
+    b.thickness[d] = b.volume / std::sqrt(s0 * s0 + s1 * s1 + s2 * s2);
+  }
+  b.ortho = c[1] == 0 && c[2] == 0 && c[3] == 0 && c[5] == 0 && c[6] == 0 && c[7] == 0;
+  for (int d = 0; d < 18; ++d)
+    b.hf[d] = (float)c[d];
+  return b;
+}
+
+struct EmuNeighbor {
+  int n = 0, mn_skin = 0;
+  double rc = 0, skin = 1.0;
+  std::vector<B2Atom> atoms, atoms_tmp;
+  std::vector<double> snap;
+  std::vector<int> perm, perm_tmp, cell_of, order_tmp, cell_count, cell_fill, cell_start, nn_skin,
+    nl_skin, flags;
+  B2NeighborView v;
+  int rebuilds = 0;
+
+  void init(int n_, double rc_, int mn)
+  {
+    n = n_;
+    rc = rc_;
+    mn_skin = mn;
+    atoms.resize(n);
+    atoms_tmp.resize(n);
+    snap.assign((size_t)3 * n, 0.0);
+    perm.resize(n);
+    for (int i = 0; i < n; ++i)
+      perm[i] = i;
+    perm_tmp.resize(n);
+    cell_of.resize(n);
+    order_tmp.resize(n);
+    nn_skin.resize(n);
+    nl_skin.resize((size_t)mn * n);
+    flags.assign(4, 0);
+    flags[0] = 1;
+  }
+  int update(const B2Box& box, const int* type, const double* pos)
+  {
+    for (int d = 0; d < 3; ++d)
+      if (box.pbc[d] && box.thickness[d] <= 2.5 * (rc + skin))
+        return 4;
+    B2Grid g;
+    for (int d = 0; d < 3; ++d) {
+      int nb = (int)std::floor(box.thickness[d] / (0.5 * (rc + skin)));
+      g.nb[d] = nb < 1 ? 1 : nb;
+      g.scale[d] = g.nb[d];
+    }
+    g.ncell = g.nb[0] * g.nb[1] * g.nb[2];
+    cell_count.assign(g.ncell, 0);
+    cell_fill.assign(g.ncell, 0);
+    cell_start.assign(g.ncell + 1, 0);
+    v.n = n;
+    v.mn_skin = mn_skin;
+    v.atoms = atoms.data();
+    v.atoms_tmp = atoms_tmp.data();
+    v.snap = snap.data();
+    v.perm = perm.data();
+    v.perm_tmp = perm_tmp.data();
+    v.cell_of = cell_of.data();
+    v.order_tmp = order_tmp.data();
+    v.cell_count = cell_count.data();
+    v.cell_fill = cell_fill.data();
+    v.cell_start = cell_start.data();
+    v.nn_skin = nn_skin.data();
+    v.nl_skin = nl_skin.data();
+    v.flags = flags.data();
+    const float trigger = (float)(skin * skin * 0.25);
+    const float cutoff = (float)((rc + skin) * (rc + skin));
+    for (int i = 0; i < n; ++i)
+      b2_body_pack_check(i, v, box, type, pos, pos + n, pos + 2 * (size_t)n, trigger);
+    if (flags[0]) {
+      for (int i = 0; i < n; ++i) {
+        int cx, cy, cz;
+        const int c = b2_cell_of(box, g, atoms[i], &cx, &cy, &cz);
+        cell_of[i] = c;
+        cell_count[c]++;
+      }
+      int run = 0;
+      for (int c = 0; c < g.ncell; ++c) {
+        cell_start[c] = run;
+        run += cell_count[c];
+      }
+      cell_start[g.ncell] = run;
+      for (int i = n - 1; i >= 0; --i) { // deliberately NOT ascending: mimics unordered atomics
+        const int c = cell_of[i];
+        order_tmp[cell_start[c] + cell_fill[c]++] = i;
+      }
+      for (int c = 0; c < g.ncell; ++c)
+        b2_body_sort_cell(c, v);
+      for (int i = 0; i < n; ++i)
+        b2_body_commit(i, v);
+      for (int i = 0; i < n; ++i)
+        b2_body_skin_list(i, v, box, g, cutoff);
+      flags[0] = 0;
+      flags[2]++;
+    }
+    return 0;
+  }
+};
+
+std::string g_err;
+
+} // namespace
+
+struct emu_nep {
+  b2::NepModel m;
+  EmuNeighbor nb;
+  int n = 0;
+  std::vector<int> nn_r, nl_r, nn_a, nl_a;
+  std::vector<float> q, sfx, FpA, U, f12;
+  std::vector<double> acc;
+  std::vector<int> zbl_z;
+  std::vector<float> cov;
+  B2NepView P;
+};
+
+template <int K1>
+static void run_desc_radial(emu_nep* p, const B2Box& box)
+{
+  std::vector<float> scratch((size_t)p->m.nt * K1 + 1);
+  for (int i = 0; i < p->n; ++i) {
+    if (p->m.nt == 1)
+      b2_body_desc_radial<1, K1>(i, p->P, box, scratch.data(), 1, 0);
+    else if (p->m.nt == 2)
+      b2_body_desc_radial<2, K1>(i, p->P, box, scratch.data(), 1, 0);
+    else
+      b2_body_desc_radial<0, K1>(i, p->P, box, scratch.data(), 1, 0);
+  }
+}
+template <int K1>
+static void run_force_radial(emu_nep* p, const B2Box& box)
+{
+  for (int i = 0; i < p->n; ++i) {
+    if (p->m.nt == 1)
+      b2_body_force_radial<1, K1>(i, p->P, box);
+    else if (p->m.nt == 2)
+      b2_body_force_radial<2, K1>(i, p->P, box);
+    else
+      b2_body_force_radial<0, K1>(i, p->P, box);
+  }
+}
+template <int K1>
+static void run_angular(emu_nep* p, const B2Box& box, bool force)
+{
+  std::vector<float> w((size_t)p->m.na1 * B2_NABC + 1);
+  for (int i = 0; i < p->n; ++i) {
+    if (force)
+      b2_body_force_angular<K1>(i, p->P, box, w.data(), 1, 0);
+    else
+      b2_body_desc_angular<K1, 5>(i, p->P, box);
+  }
+}
+template <int DIMP>
+static void run_mlp(emu_nep* p)
+{
+  for (int i = 0; i < p->n; ++i)
+    b2_body_mlp<DIMP>(i, p->P);
+}
+
+extern "C" {
+
+const char* emu_last_error(void) { return g_err.c_str(); }
+
+emu_nep* emu_nep_create(const char* path, int n)
+{
+  emu_nep* p = new emu_nep;
+  g_err = p->m.load(path);
+  if (!g_err.empty()) {
+    delete p;
+    return nullptr;
+  }
+  b2::NepModel& m = p->m;
+  p->n = n;
+  const size_t N = n;
+  const double rc = m.rc_radial_max, rs = rc + 1.0;
+  p->nb.init(n, rc, (int)(m.MN_radial * rs * rs * rs / (rc * rc * rc)));
+  p->nn_r.resize(N);
+  p->nl_r.resize(N * m.MN_radial);
+  p->nn_a.resize(N);
+  p->nl_a.resize(N * m.MN_angular);
+  p->q.resize(N * m.dim);
+  p->sfx.resize(N * m.na1 * B2_NABC);
+  p->FpA.resize(N * m.dim_angular + 1);
+  p->U.resize(N * m.UST);
+  p->f12.resize(N * 3 * m.MN_angular + 1);
+  p->acc.resize(N * 13);
+  p->zbl_z = m.atomic_numbers;
+  p->cov.assign(b2::COVALENT_RADIUS, b2::COVALENT_RADIUS + 94);
+  if (m.zbl_para.empty())
+    m.zbl_para.push_back(0.0f);
+  B2NepView& P = p->P;
+  std::memset(&P, 0, sizeof P);
+  P.nt = m.nt; P.nr1 = m.nr1; P.na1 = m.na1; P.kr1 = m.kr1; P.ka1 = m.ka1;
+  P.K1R = m.K1R; P.K1A = m.K1A; P.KP = m.KP; P.UST = m.UST;
+  P.has222 = m.has222; P.has1111 = m.has1111; P.num_L = m.num_L;
+  P.dim = m.dim; P.dim_ang = m.dim_angular; P.nneu = m.nneu; P.DIMP = m.DIMP;
+  P.zbl_enabled = m.zbl_enabled; P.zbl_flexible = m.zbl_flexible; P.zbl_typewise = m.zbl_typewise;
+  P.zbl_rc_inner = m.zbl_rc_inner; P.zbl_rc_outer = m.zbl_rc_outer;
+  P.zbl_typewise_factor = m.zbl_typewise_factor;
+  P.rc_r = m.rc_r.data(); P.rcinv_r = m.rcinv_r.data(); P.rc2_r = m.rc2_r.data();
+  P.rc_a = m.rc_a.data(); P.rcinv_a = m.rcinv_a.data(); P.rc2_a = m.rc2_a.data();
+  P.c_r = m.c_r.data(); P.c_a = m.c_a.data(); P.w0p = m.w0p.data(); P.b0 = m.b0.data();
+  P.w1 = m.w1.data(); P.bias = m.bias.data(); P.q_scaler = m.q_scaler.data();
+  P.zbl_z = p->zbl_z.data(); P.zbl_para = m.zbl_para.data(); P.cov_radius = p->cov.data();
+  P.n = n; P.mn_r = m.MN_radial; P.mn_a = m.MN_angular;
+  P.nn_r = p->nn_r.data(); P.nl_r = p->nl_r.data(); P.nn_a = p->nn_a.data(); P.nl_a = p->nl_a.data();
+  P.q = p->q.data(); P.sfx = p->sfx.data(); P.FpA = p->FpA.data(); P.U = p->U.data();
+  P.f12 = p->f12.data(); P.acc = p->acc.data();
+  return p;
+}
+
+void emu_nep_destroy(emu_nep* p) { delete p; }
+int emu_nep_rebuilds(emu_nep* p) { return p->nb.flags[2]; }
+int emu_nep_error_bits(emu_nep* p) { return p->nb.flags[1]; }
+
+int emu_nep_compute(
+  emu_nep* p, int n, const double h[9], const int pbc[3], const int* type, const double* pos,
+  double* pe, double* force, double* virial)
+{
+  if (n != p->n)
+    return 1;
+  const B2Box box = make_box(h, pbc);
+  const int rc = p->nb.update(box, type, pos);
+  if (rc)
+    return rc;
+  B2NepView& P = p->P;
+  P.atoms = p->nb.atoms.data();
+  P.perm = p->nb.perm.data();
+  P.nn_skin = p->nb.nn_skin.data();
+  P.nl_skin = p->nb.nl_skin.data();
+  P.flags = p->nb.flags.data();
+  for (int i = 0; i < n; ++i)
+    b2_body_split(i, P, box);
+  switch (p->m.K1R) {
+    case 9: run_desc_radial<9>(p, box); break;
+    case 13: run_desc_radial<13>(p, box); break;
+    default: run_desc_radial<17>(p, box); break;
+  }
+  switch (p->m.K1A) {
+    case 9: run_angular<9>(p, box, false); break;
+    case 13: run_angular<13>(p, box, false); break;
+    default: run_angular<17>(p, box, false); break;
+  }
+  switch (p->m.DIMP) {
+    case 16: run_mlp<16>(p); break;
+    case 32: run_mlp<32>(p); break;
+    case 48: run_mlp<48>(p); break;
+    case 64: run_mlp<64>(p); break;
+    case 80: run_mlp<80>(p); break;
+    case 96: run_mlp<96>(p); break;
+    case 112: run_mlp<112>(p); break;
+    default: run_mlp<128>(p); break;
+  }
+  switch (p->m.K1R) {
+    case 9: run_force_radial<9>(p, box); break;
+    case 13: run_force_radial<13>(p, box); break;
+    default: run_force_radial<17>(p, box); break;
+  }
+  switch (p->m.K1A) {
+    case 9: run_angular<9>(p, box, true); break;
+    case 13: run_angular<13>(p, box, true); break;
+    default: run_angular<17>(p, box, true); break;
+  }
+  for (int i = 0; i < n; ++i)
+    b2_body_reduce_angular(i, P, box);
+  if (p->m.zbl_enabled)
+    for (int i = 0; i < n; ++i)
+      b2_body_zbl(i, P, box);
+  for (int i = 0; i < n; ++i)
+    b2_body_unpack(i, n, P.perm, P.acc, pe, force, virial);
+  return p->nb.flags[1] ? 5 : 0;
+}
+
+static void export_list(
+  int n, const int* perm, const int* nn, const int* nl, int mn, int* NN, int* NL)
+{
+  for (int i = 0; i < n; ++i) {
+    const int a = perm[i];
+    const int cnt = nn[i] < mn ? nn[i] : mn;
+    int* row = NL + (size_t)a * mn;
+    for (int k = 0; k < cnt; ++k) {
+      const int v = perm[nl[(size_t)k * n + i]];
+      int q = k - 1;
+      while (q >= 0 && row[q] > v) {
+        row[q + 1] = row[q];
+        --q;
+      }
+      row[q + 1] = v;
+    }
+    NN[a] = cnt;
+  }
+}
+
+void emu_nep_export_neighbors(
+  emu_nep* p, int mn_r, int* NN_r, int* NL_r, int mn_a, int* NN_a, int* NL_a)
+{
+  export_list(p->n, p->P.perm, p->nn_r.data(), p->nl_r.data(), mn_r, NN_r, NL_r);
+  export_list(p->n, p->P.perm, p->nn_a.data(), p->nl_a.data(), mn_a, NN_a, NL_a);
+}
+
+void emu_nep_export_descriptors(emu_nep* p, float* q)
+{
+  for (int i = 0; i < p->n; ++i)
+    for (int d = 0; d < p->m.dim; ++d)
+      q[(size_t)d * p->n + p->P.perm[i]] = p->q[(size_t)d * p->n + i] * p->m.q_scaler[d];
+}
+
+// skin list of the last rebuild, in caller indices (row-major, ascending) -- neighbour tests
+void emu_nep_export_skin(emu_nep* p, int mn, int* NN, int* NL)
+{
+  export_list(p->n, p->P.perm, p->nb.nn_skin.data(), p->nb.nl_skin.data(), mn, NN, NL);
+}
+
+// ---- LJ -------------------------------------------------------------------------------------
+struct emu_lj {
+  int nt, n;
+  double rc;
+  std::vector<float> s6, s12, c2;
+  EmuNeighbor nb;
+  std::vector<double> acc;
+};
+
+emu_lj* emu_lj_create(int nt, const double* para, int n)
+{
+  emu_lj* p = new emu_lj;
+  p->nt = nt;
+  p->n = n;
+  p->rc = 0;
+  for (int a = 0; a < nt * nt; ++a) {
+    const double eps = para[a * 3], sig = para[a * 3 + 1], cut = para[a * 3 + 2];
+    p->s6.push_back((float)(std::pow(sig, 6.0) * eps * 4.0));
+    p->s12.push_back((float)(std::pow(sig, 12.0) * eps * 4.0));
+    p->c2.push_back((float)(cut * cut));
+    if (p->rc < cut)
+      p->rc = cut;
+  }
+  const double rs = p->rc + 1.0;
+  p->nb.init(n, p->rc, (int)(4.19 * rs * rs * rs * 0.06) + 32);
+  p->acc.resize((size_t)13 * n);
+  return p;
+}
+void emu_lj_destroy(emu_lj* p) { delete p; }
+int emu_lj_compute(
+  emu_lj* p, int n, const double h[9], const int pbc[3], const int* type, const double* pos,
+  double* pe, double* force, double* virial)
+{
+  const B2Box box = make_box(h, pbc);
+  const int rc = p->nb.update(box, type, pos);
+  if (rc)
+    return rc;
+  B2LjView P;
+  P.nt = p->nt;
+  P.s6e4 = p->s6.data();
+  P.s12e4 = p->s12.data();
+  P.rc2 = p->c2.data();
+  P.n = n;
+  P.atoms = p->nb.atoms.data();
+  P.nn_skin = p->nb.nn_skin.data();
+  P.nl_skin = p->nb.nl_skin.data();
+  P.acc = p->acc.data();
+  for (int i = 0; i < n; ++i)
+    b2_body_lj(i, P, box);
+  for (int i = 0; i < n; ++i)
+    b2_body_unpack(i, n, p->nb.perm.data(), p->acc.data(), pe, force, virial);
+  return p->nb.flags[1] ? 5 : 0;
+}
+
+// ---- integrate ------------------------------------------------------------------------------
+void emu_apply_pbc(int n, const double h[9], const int pbc[3], double* pos)
+{
+  const B2Box box = make_box(h, pbc);
+  for (int i = 0; i < n; ++i)
+    b2_body_apply_pbc(i, n, box, pos, pos + n, pos + 2 * (size_t)n);
+}
+void emu_velocity_verlet(
+  int step1, int n, double dt, const double* mass, double* pos, double* vel, const double* f)
+{
+  for (int i = 0; i < n; ++i)
+    b2_body_vv(i, n, step1 != 0, dt, mass, pos, vel, f);
+}
+void emu_find_thermo(
+  int n, int n_temp, double volume, const double* mass, const double* pe, const double* vel,
+  const double* virial, double* thermo)
+{
+  double s[8] = {0};
+  for (int i = 0; i < n; ++i) {
+    double t[8];
+    b2_thermo_terms(i, n, mass, pe, vel, virial, t);
+    for (int k = 0; k < 8; ++k)
+      s[k] += t[k];
+  }
+  thermo[0] = s[0] / (3.0 * n_temp * 8.617343e-5);
+  thermo[1] = s[1];
+  for (int k = 2; k < 8; ++k)
+    thermo[k] = s[k] / volume;
+}
+}

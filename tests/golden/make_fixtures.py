@@ -34,6 +34,8 @@ COPIES = {
     # LJ argon parameters (config C2)
     "potentials/lj/Ar_10A.txt": "lj_Ar_10A.txt",
     "potentials/tersoff/Si_Tersoff_1989.txt": "tersoff_Si_1989.txt",
+    # UNEP-v1 16-metal alloy model (config C4): 16 types, universal ZBL, 4- and 5-body terms
+    "potentials/nep/Song-2024-UNEP-v1-AgAlAuCrCuMgMoNiPbPdPtTaTiVWZr.txt": "nep_UNEP_v1.txt",
 }
 
 

@@ -1,0 +1,164 @@
+"""The kernel BODIES of libb200md (gpumd_b200/csrc/*.cuh), compiled for the host by tests/emu and
+checked against the oracle.  This is the GPU-less proxy for tests/test_gpu_parity.py: same inputs,
+same assertions, but the device scheduling (blocks, shared memory, atomics, scans) is emulated by
+serial loops.  Neighbour sets must be bit-exact; E/F/virial within the reference suite's own
+tolerances."""
+import numpy as np
+import pytest
+
+from cases import NEP_CASES
+from conftest import GOLDEN, TOL, assert_close
+from gpumd_b200.structures import fcc, rocksalt_pbte
+
+
+def check_fv(out, ref):
+    """force: rtol 1e-4 + atol 1e-5 eV/A, virial: rtol 1e-4 + atol 2e-5 eV, with the
+    atol scaled by the largest component when that exceeds 1 -- FP32 accumulation noise is
+    relative to the magnitude of the terms being summed, not to the (possibly cancelling) result."""
+    fs = max(1.0, np.abs(ref["force"]).max())
+    vs = max(1.0, np.abs(ref["virial"]).max())
+    assert_close(out["force"], ref["force"], rtol=TOL["force"]["rtol"],
+                 atol=TOL["force"]["atol"] * fs, what="force")
+    assert_close(out["virial"], ref["virial"], rtol=TOL["virial"]["rtol"],
+                 atol=TOL["virial"]["atol"] * vs, what="virial")
+
+
+def check_nep(oracle, dev, model, s, n):
+    orc = oracle.NepOracle(GOLDEN / model)
+    r32 = orc.compute(s["type"], s["h"], s["pbc"], s["pos"], precision=32, lists=True, descriptors=True)
+    r64 = orc.compute(s["type"], s["h"], s["pbc"], s["pos"], precision=64)
+    rc, out = dev.compute(s["type"], s["h"], s["pbc"], s["pos"])
+    assert rc == 0
+    NNr, NLr, NNa, NLa = dev.neighbors(r32["NL_radial"].shape[1], r32["NL_angular"].shape[1])
+    assert np.array_equal(NNr, r32["NN_radial"]) and np.array_equal(NLr, r32["NL_radial"])
+    assert np.array_equal(NNa, r32["NN_angular"]) and np.array_equal(NLa, r32["NL_angular"])
+    q = dev.descriptors(orc.info["dim"])
+    assert_close(q, r32["q"], rtol=2e-5, atol=2e-6, what="descriptor")
+    # |dE|/N <= 1e-6 eV against the FP32 restatement (the reference GPU's arithmetic); against the
+    # FP64 truth allow the FP32 pair-math noise itself (the restatement's own f32-f64 gap) on top
+    gap = abs(r32["pe"].sum() - r64["pe"].sum()) / n
+    assert abs(out["pe"].sum() - r32["pe"].sum()) / n < TOL["energy_per_atom"]
+    assert abs(out["pe"].sum() - r64["pe"].sum()) / n < TOL["energy_per_atom"] + 2 * gap
+    assert_close(out["pe"].sum(), r32["pe"].sum(), **TOL["energy"], what="energy")
+    check_fv(out, r32)
+    check_fv(out, r64)
+    return out
+
+
+@pytest.mark.parametrize("case", list(NEP_CASES))
+def test_nep_bodies_match_oracle(oracle, emu, case):
+    model, make = NEP_CASES[case]
+    s = make()
+    n = s["type"].shape[0]
+    dev = emu.nep(GOLDEN / model, n)
+    check_nep(oracle, dev, model, s, n)
+
+
+def test_nep_accumulates_into_outputs(oracle, emu):
+    """Potential::compute contract: outputs are += (nep.cu:653,755-770)."""
+    s = rocksalt_pbte(4, rattle=0.05, seed=1)
+    n = s["type"].shape[0]
+    dev = emu.nep(GOLDEN / "nep_PbTe.txt", n)
+    _, a = dev.compute(s["type"], s["h"], s["pbc"], s["pos"])
+    # second call on the same handle: no rebuild, same answer
+    _, b = dev.compute(s["type"], s["h"], s["pbc"], s["pos"])
+    assert dev.rebuilds == 1
+    assert np.array_equal(a["force"], b["force"]) and np.array_equal(a["pe"], b["pe"])
+
+
+def test_skin_list_reuse_and_rebuild(oracle, emu):
+    """Move atoms by less than skin/2: no rebuild, sets still exact.  Move one atom further:
+    the predicated rebuild fires and the sets are exact again."""
+    s = rocksalt_pbte(4, rattle=0.05, seed=1)
+    n = s["type"].shape[0]
+    dev = emu.nep(GOLDEN / "nep_PbTe.txt", n)
+    orc = oracle.NepOracle(GOLDEN / "nep_PbTe.txt")
+    rng = np.random.default_rng(3)
+    pos = s["pos"].copy()
+    dev.compute(s["type"], s["h"], s["pbc"], pos)
+    for step, amp, expect in ((1, 0.12, 1), (2, 0.12, 1), (3, 0.0, 2)):
+        disp = rng.uniform(-1, 1, pos.shape) * amp / np.sqrt(3)
+        if step == 3:
+            disp[:, 17] = [0.6, 0.0, 0.0]  # > skin/2 from the snapshot for sure
+        pos = np.mod(pos + disp, s["h"][0])
+        r = orc.compute(s["type"], s["h"], s["pbc"], pos, precision=32, lists=True)
+        rc, out = dev.compute(s["type"], s["h"], s["pbc"], pos)
+        assert rc == 0 and dev.rebuilds == expect, (step, dev.rebuilds)
+        NNr, NLr, NNa, NLa = dev.neighbors(r["NL_radial"].shape[1], r["NL_angular"].shape[1])
+        assert np.array_equal(NLr, r["NL_radial"]) and np.array_equal(NLa, r["NL_angular"])
+        assert_close(out["force"], r["force"], **TOL["force"], what="force")
+
+
+def test_cutoff_boundary_membership(oracle, emu):
+    """Pairs placed within a few ulps of the radial and angular cutoffs: membership is decided by
+    the reference's FP32 expression, so the CUDA-side test and the oracle must agree exactly."""
+    base = rocksalt_pbte(4, a=7.4, rattle=0.0, seed=1)  # dilute lattice: 3.7 A nearest neighbours
+    pos = base["pos"].copy()
+    n = pos.shape[1]
+    rng = np.random.default_rng(5)
+    # move the odd atom of 120 pairs so that |r| straddles rc_radial (8) or rc_angular (4)
+    for k in range(120):
+        i, j = 2 * k, 2 * k + 1
+        rc = 8.0 if k % 2 == 0 else 4.0
+        u = rng.normal(size=3)
+        u /= np.linalg.norm(u)
+        eps = (rng.integers(-6, 7)) * 4.8e-7 * (rc / 8.0)
+        pos[:, j] = pos[:, i] + u * (rc + eps)
+    pos = np.mod(pos, base["h"][0])
+    orc = oracle.NepOracle(GOLDEN / "nep_PbTe.txt")
+    r = orc.compute(base["type"], base["h"], base["pbc"], pos, precision=32, lists=True)
+    dev = emu.nep(GOLDEN / "nep_PbTe.txt", n)
+    rc, _ = dev.compute(base["type"], base["h"], base["pbc"], pos)
+    assert rc == 0
+    NNr, NLr, NNa, NLa = dev.neighbors(r["NL_radial"].shape[1], r["NL_angular"].shape[1])
+    assert np.array_equal(NLr, r["NL_radial"]) and np.array_equal(NLa, r["NL_angular"])
+    # the construction really produced boundary cases: some of the engineered pairs are in, some out
+    eng = [(2 * k + 1) in NLr[2 * k, :NNr[2 * k]] for k in range(0, 120, 2)]
+    assert 5 < sum(eng) < 55
+
+
+def test_small_box_is_rejected(emu):
+    s = rocksalt_pbte(3, rattle=0.0)  # 19.7 A < 2.5*(8+1)
+    dev = emu.nep(GOLDEN / "nep_PbTe.txt", s["type"].shape[0])
+    rc, _ = dev.compute(s["type"], s["h"], s["pbc"], s["pos"])
+    assert rc == 4  # B200MD_ERR_SMALL_BOX
+
+
+def test_lj_bodies_match_oracle(oracle, emu):
+    s = fcc(6, 5.30, rattle=0.1, seed=2)  # 31.8 A box > 2.5*(10+1)
+    n = s["type"].shape[0]
+    para = np.array([[[1.032e-2, 3.405, 10.0]]])
+    r = oracle.lj_compute(para, s["type"], s["h"], s["pbc"], s["pos"])
+    rc, out = emu.lj(para, n).compute(s["type"], s["h"], s["pbc"], s["pos"])
+    assert rc == 0
+    assert_close(out["pe"], r["pe"], rtol=1e-5, atol=1e-7, what="pe")
+    assert_close(out["force"], r["force"], **TOL["force"], what="force")
+    assert_close(out["virial"], r["virial"], **TOL["virial"], what="virial")
+
+
+def test_lj_two_types(oracle, emu):
+    s = fcc(6, 5.30, rattle=0.1, seed=9, num_types=2, symbols=("Ar", "Ar"))
+    n = s["type"].shape[0]
+    para = np.array([[[1.0e-2, 3.4, 10.0], [0.8e-2, 3.2, 9.0]], [[0.8e-2, 3.2, 9.0], [1.2e-2, 3.0, 8.0]]])
+    r = oracle.lj_compute(para, s["type"], s["h"], s["pbc"], s["pos"])
+    rc, out = emu.lj(para, n).compute(s["type"], s["h"], s["pbc"], s["pos"])
+    assert rc == 0
+    assert_close(out["force"], r["force"], **TOL["force"], what="force")
+    assert_close(out["pe"], r["pe"], rtol=1e-5, atol=1e-7, what="pe")
+
+
+def test_integrate_bodies(oracle, emu):
+    rng = np.random.default_rng(1)
+    n = 200
+    mass = rng.uniform(1, 200, n)
+    pos, vel, f = rng.normal(size=(3, n)) * 5 + 10, rng.normal(size=(3, n)), rng.normal(size=(3, n))
+    for step1 in (True, False):
+        a = oracle.velocity_verlet(step1, 0.098, mass, pos, vel, f)
+        b = emu.velocity_verlet(step1, 0.098, mass, pos, vel, f)
+        assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])  # FP64, same operations
+    pe, vir = rng.normal(size=n), rng.normal(size=(9, n))
+    assert np.allclose(oracle.find_thermo(n, 123.0, mass, pe, vel, vir),
+                       emu.find_thermo(n, 123.0, mass, pe, vel, vir), rtol=1e-13)
+    h = np.array([20.0, 2.0, 0.0, 0.0, 21.0, 1.0, 0.0, 0.0, 22.0])
+    p = rng.uniform(-5, 27, (3, n))
+    assert np.allclose(oracle.apply_pbc(h, [1, 0, 1], p), emu.apply_pbc(h, [1, 0, 1], p), rtol=0, atol=1e-13)
