@@ -1,0 +1,371 @@
+#!/usr/bin/env python
+"""bench.py -- atom-steps/s of the MD hot path on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--cells C]
+
+Workload (config C3 of BASELINE.md, the one the metric is quoted on): rocksalt PbTe, 50x50x50
+conventional cells = 1 000 000 atoms per GPU, Gaussian rattle 0.02 A (seed 1), velocities at 300 K
+(seed 42), NVE, dt = 1 fs, NEP model tests/golden/nep_PbTe.txt (the reference's
+tests/gpumd/dump_observer/PbTe_species/PbTe.txt).  One "step" = velocity-Verlet half step ->
+Force::compute (position wrap, zero, neighbour maintenance, NEP descriptor / MLP / forces) ->
+second half step -> thermo reduction: exactly what Run::perform_a_run does per step
+(src/main_gpumd/run.cu:250-318), every kernel from libb200md.so.
+
+Printed JSON (one line, rank 0):
+  value      whole-job atom-steps/s, state resident in HBM, CUDA-event timed, max over ranks
+  e2e        the same metric through the host-buffer C-ABI call b200md_nep_compute_host
+             (positions/types H2D from pinned memory, energies/forces/virials D2H, every step)
+  roofline   dominant kernel: SURVEY.md 8(d) algorithmic bytes per atom x atoms / mean launch time
+  cpu_baseline  the reference's own CPU implementation (NEP_CPU, oracle/_ref) on the host cores
+--impl reference times NEP_CPU alone on the same crystal/model/metric (bounded sample per step).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+GOLDEN = ROOT / "tests" / "golden"
+MODEL = GOLDEN / "nep_PbTe.txt"
+METRIC = "atom-steps/sec (1M-atom PbTe NEP NVE per GPU)"
+
+
+def stage_algorithmic_bytes(nn, model):
+    """SURVEY.md 8(d) per-stage algorithmic bytes per atom-step (counting rule stated there).
+    Ng/Nr/Na = measured mean skin/radial/angular list lengths; K = steps per list rebuild."""
+    Ng, Nr, Na = nn["skin"], nn["radial"], nn["angular"]
+    D, Dr, S = model["D"], model["Dr"], model["S"]
+    Da = D - Dr
+    return {
+        "k_split": 36 + 4 * (Ng + Nr + Na),
+        "descriptor+MLP": 52 + 4 * (Nr + Na) + 4 * D + 4 * S,
+        "k_force_radial": 32 + 4 * Nr + 4 * Dr + 192,
+        "k_force_angular": 32 + 4 * Na + 4 * Da + 4 * S + 12 * Na,
+        "k_reduce_angular": 28 + 16 * Na + 192,
+        "VV1": 128, "PBC": 48, "zero": 104, "displacement_check": 48, "VV2": 80, "thermo": 88,
+    }
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.lines = []
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for ln in self.proc.stdout:
+            self.lines.append((time.time(), ln.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for t, ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                clk, cmax = float(f[1]), float(f[2])
+            except ValueError:
+                continue
+            mx.append(cmax)
+            if t0 - 0.05 <= t <= t1 + 0.05:
+                sm.append(clk)
+                for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
+                                      "sw_power_cap"), f[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+        if not sm:  # region shorter than the sampling period: use every sample
+            sm = [float(ln.split(",")[1]) for _, ln in self.lines if len(ln.split(",")) >= 9] or [0.0]
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def crystal(cells):
+    from gpumd_b200.structures import init_velocities, rocksalt_pbte
+    s = rocksalt_pbte(cells, rattle=0.02, seed=1)
+    s["vel"] = init_velocities(s["mass"], 300.0, seed=42)
+    return s
+
+
+def reference_arm(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path (NEP_CPU, compiled from
+    /root/reference into oracle/_ref; falls back to the C restatement if the .so is absent)."""
+    if rank != 0:
+        return
+    from oracle import oracle_py
+    threads = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    kind = "reference" if oracle_py.ref_available() else "port"
+    if kind == "reference":
+        eng = oracle_py.RefNepCpu(MODEL)
+        call = lambda s: eng.compute(s["type"], s["h"], s["pos"])
+    else:
+        eng = oracle_py.NepOracle(MODEL)
+        call = lambda s: eng.compute(s["type"], s["h"], s["pbc"], s["pos"], precision=32)
+        threads = 1
+    # calibrate so that K+W steps take about two minutes at most
+    probe = crystal(8)  # 4096 atoms
+    t0 = time.time()
+    call(probe)
+    rate = probe["type"].shape[0] / max(time.time() - t0, 1e-6)
+    budget_atoms = rate * 120.0 / (args.steps + args.warmup)
+    cells = int(max(4, min(16, np.floor((budget_atoms / 8.0) ** (1.0 / 3.0)))))
+    s = crystal(cells)
+    n = s["type"].shape[0]
+    for _ in range(args.warmup):
+        call(s)
+    t0 = time.time()
+    for _ in range(args.steps):
+        call(s)
+    dt = time.time() - t0
+    value = n * args.steps / dt
+    sample = f"{cells}^3 cells = {n} atoms of the same rattled PbTe crystal, one force evaluation per step"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "atom-steps/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3: rocksalt PbTe NEP (nep_PbTe.txt), NVE 1 fs; CPU arm: force "
+                               "evaluation on a bounded sample", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "atom-steps/s", "cores": threads, "kind": kind,
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "atom-steps/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }))
+
+
+def cpu_baseline(seconds=15.0):
+    from oracle import oracle_py
+    threads = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(threads))
+    if oracle_py.ref_available():
+        kind, eng = "reference", oracle_py.RefNepCpu(MODEL)
+        call = lambda s: eng.compute(s["type"], s["h"], s["pos"])
+    else:
+        kind, eng, threads = "port", oracle_py.NepOracle(MODEL), 1
+        call = lambda s: eng.compute(s["type"], s["h"], s["pbc"], s["pos"], precision=32)
+    s = crystal(12)  # 13 824 atoms
+    n = s["type"].shape[0]
+    call(s)
+    t0 = time.time()
+    reps = 0
+    while time.time() - t0 < seconds and reps < 50:
+        call(s)
+        reps += 1
+    dt = time.time() - t0
+    return {"value": n * reps / dt, "unit": "atom-steps/s", "cores": threads, "kind": kind,
+            "sample": f"{reps} force evaluations of 12^3 cells = {n} atoms (same crystal and model), "
+                      f"{dt:.1f} s"}
+
+
+def ours(args, rank, world):
+    import torch
+    import torch.distributed as dist
+    from gpumd_b200 import build, engine
+    from gpumd_b200.structures import TIME_UNIT_CONVERSION
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (there is no CPU fallback)")
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl")
+    if rank == 0:
+        build.build_lib()
+    if world > 1:
+        dist.barrier()
+
+    s = crystal(args.cells)
+    n = s["type"].shape[0]
+    atom = engine.Atom(s["type"], s["pos"], s["mass"], s["vel"])
+    box = engine.Box(s["h"], s["pbc"])
+    force = engine.Force()
+    pot = force.parse_potential(MODEL, n)
+    ens = engine.Ensemble_NVE(n)
+    thermo = torch.zeros(8, dtype=torch.float64, device="cuda")
+    dt = 1.0 / TIME_UNIT_CONVERSION
+    fargs = (box, atom.position_per_atom, atom.type, atom.potential_per_atom, atom.force_per_atom,
+             atom.virial_per_atom)
+
+    def step():
+        ens.compute1(dt, box, atom, thermo)
+        force.compute(*fargs)
+        ens.compute2(dt, box, atom, thermo)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    force.compute(*fargs)  # first force evaluation is outside the loop, like run.cu:217-248
+    pot.check()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    pot.check()
+
+    # ---------------- timed region: K steps, state resident in HBM ----------------
+    sampler = ClockSampler(local) if rank == 0 else None
+    sync_all()
+    launches0 = engine.launch_count()
+    rebuilds0 = pot.num_rebuilds
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    sync_all()
+    w1 = time.time()
+    ms = e0.elapsed_time(e1)
+    launches = engine.launch_count() - launches0
+    rebuilds = pot.num_rebuilds - rebuilds0
+    clocks = sampler.stop(w0, w1) if sampler else None
+    pot.check()
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = n * world * args.steps / (ms * 1e-3)
+    t_final = thermo.cpu().numpy()
+
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+        return
+
+    # ---------------- per-stage device timing for the roofline block ----------------
+    prof_steps = min(args.steps, 64)
+    pot.profile(True)
+    ev = {k: [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+          for k in ("VV1", "force_call", "VV2+thermo")}
+    acc = {k: 0.0 for k in ev}
+    for _ in range(prof_steps):
+        ev["VV1"][0].record(); ens.compute1(dt, box, atom, thermo); ev["VV1"][1].record()
+        ev["force_call"][0].record(); force.compute(*fargs); ev["force_call"][1].record()
+        ev["VV2+thermo"][0].record(); ens.compute2(dt, box, atom, thermo); ev["VV2+thermo"][1].record()
+        torch.cuda.synchronize()
+        for k in ev:
+            acc[k] += ev[k][0].elapsed_time(ev[k][1])
+    stages = pot.profile_read()
+    pot.profile(False)
+    nn = pot.mean_neighbors()
+    per_stage_ms = {k: v[0] / max(v[1], 1) for k, v in stages.items()}
+    step_ms_prof = sum(acc.values()) / prof_steps
+    model = {"D": pot.dim, "Dr": 5, "S": 120}
+    abytes = stage_algorithmic_bytes(nn, model)
+    top = max(per_stage_ms, key=per_stage_ms.get)
+    key = top if top in abytes else "descriptor+MLP"
+    top_ms = per_stage_ms[top] if key == top else sum(
+        per_stage_ms.get(k, 0.0) for k in ("k_desc_radial", "k_desc_angular", "k_mlp"))
+    peaks_file = ROOT / "MEASURED_PEAKS.json"
+    if peaks_file.exists():
+        peak, peak_src = json.loads(peaks_file.read_text())["hbm_gbs"], "MEASURED_PEAKS.json hbm_gbs (measured)"
+    else:
+        peak, peak_src = 6650.0, "B200_PROFILING.md fallback"
+    achieved = abytes[key] * n / (top_ms * 1e-3) / 1e9
+    traffic = None
+    tf = ROOT / "profiles" / "ncu_traffic.json"
+    if tf.exists():
+        traffic = json.loads(tf.read_text()).get(top)
+    total_bytes = sum(abytes.values()) - abytes["descriptor+MLP"] + abytes["descriptor+MLP"]
+    roofline = {
+        "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_atom": abytes[key], "kernel_ms": top_ms,
+        "step_algorithmic_bytes_per_atom": total_bytes,
+        "step_hbm_frac": total_bytes * n / (ms / args.steps * 1e-3) / 1e9 / peak,
+        "mean_neighbors": nn,
+        "stage_ms": {**{k: round(v, 4) for k, v in per_stage_ms.items()},
+                     **{k: round(v / prof_steps, 4) for k, v in acc.items()}},
+        "stage_share_of_step": {k: round(v / step_ms_prof, 4) for k, v in per_stage_ms.items()},
+    }
+
+    # ---------------- end to end: host buffers through b200md_nep_compute_host ----------------
+    e2e_steps = max(3, min(args.steps, 10))
+    h_type = torch.from_numpy(s["type"].copy()).pin_memory()
+    h_pos = torch.from_numpy(np.ascontiguousarray(s["pos"]).reshape(-1).copy()).pin_memory()
+    h_pe = torch.zeros(n, dtype=torch.float64).pin_memory()
+    h_f = torch.zeros(3 * n, dtype=torch.float64).pin_memory()
+    h_v = torch.zeros(9 * n, dtype=torch.float64).pin_memory()
+    pot2 = engine.NEP(MODEL, n)
+    for _ in range(2):
+        pot2.compute_host(box, h_type, h_pos, h_pe, h_f, h_v)
+    torch.cuda.synchronize()
+    t0 = time.time()
+    for _ in range(e2e_steps):
+        pot2.compute_host(box, h_type, h_pos, h_pe, h_f, h_v)
+    torch.cuda.synchronize()
+    e2e_dt = time.time() - t0
+    e2e = {"value": n * e2e_steps / e2e_dt, "unit": "atom-steps/s",
+           "h2d_bytes_per_step": int(h_type.numel() * 4 + h_pos.numel() * 8),
+           "d2h_bytes_per_step": int((h_pe.numel() + h_f.numel() + h_v.numel()) * 8),
+           "steps": e2e_steps,
+           "what": "b200md_nep_compute_host: one full force evaluation per step (wrap-free input), "
+                   "pinned host buffers, H2D+D2H inside the timed region; 1 GPU"}
+    del pot2
+
+    cpu = cpu_baseline() if not args.no_cpu_baseline else None
+    out = {
+        "metric": METRIC, "value": value, "unit": "atom-steps/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {
+            "workload": f"C3: rocksalt PbTe {args.cells}^3 cells = {n} atoms per GPU, NEP "
+                        "(nep_PbTe.txt, D=30, 30 neurons, rc 8/4 A), NVE dt 1 fs, 300 K",
+            "atoms_per_gpu": n, "state": "FP64 positions/velocities/forces (GPUMD layouts), FP32 pair math",
+            "cache": "inputs larger than L2 (per-step working set > 1 GB vs 126 MB L2); no flush needed",
+            "list_rebuilds_in_timed_region": rebuilds, "parallelism": f"{world} x 1 GPU domain(s)",
+            "final_T_K": float(t_final[0]), "final_U_eV_per_atom": float(t_final[1]) / n,
+        },
+        "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+        "cpu_baseline": cpu,
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=50, help="conventional cells per edge (50 -> 1M atoms)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+    else:
+        ours(args, rank, world)
+
+
+if __name__ == "__main__":
+    main()

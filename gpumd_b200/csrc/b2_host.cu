@@ -57,6 +57,52 @@ B2Box make_box(const double h[9], const int pbc[3])
   return b;
 }
 
+StageProfiler::~StageProfiler()
+{
+  if (created)
+    for (int a = 0; a < MAX_SAMPLES; ++a)
+      for (int b = 0; b < MAX_STAGES; ++b) {
+        cudaEventDestroy(ev[a][b][0]);
+        cudaEventDestroy(ev[a][b][1]);
+      }
+}
+
+void StageProfiler::enable(bool on)
+{
+  if (on && !created) {
+    for (int a = 0; a < MAX_SAMPLES; ++a)
+      for (int b = 0; b < MAX_STAGES; ++b) {
+        cudaEventCreate(&ev[a][b][0]);
+        cudaEventCreate(&ev[a][b][1]);
+      }
+    created = true;
+  }
+  enabled = on;
+  steps = 0;
+  for (int a = 0; a < MAX_SAMPLES; ++a)
+    for (int b = 0; b < MAX_STAGES; ++b)
+      used[a][b] = false;
+}
+
+void StageProfiler::read(float* ms_sum, int* counts)
+{
+  cudaDeviceSynchronize();
+  for (int b = 0; b < MAX_STAGES; ++b) {
+    ms_sum[b] = 0.0f;
+    counts[b] = 0;
+  }
+  const int ns = steps < MAX_SAMPLES ? steps : MAX_SAMPLES;
+  for (int a = 0; a < ns; ++a)
+    for (int b = 0; b < MAX_STAGES; ++b)
+      if (used[a][b]) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, ev[a][b][0], ev[a][b][1]) == cudaSuccess) {
+          ms_sum[b] += ms;
+          counts[b] += 1;
+        }
+      }
+}
+
 } // namespace b2
 
 extern "C" const char* b200md_last_error(void) { return b2::g_error.c_str(); }

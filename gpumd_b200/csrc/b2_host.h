@@ -56,4 +56,37 @@ struct DevBuf {
 
 inline int grid_for(long long n, int block) { return (int)((n + block - 1) / block); }
 
+// Optional per-stage device timing (CUDA events on the launching stream) for bench.py's roofline
+// block.  Disabled by default: then begin()/end() are no-ops.
+struct StageProfiler {
+  static constexpr int MAX_STAGES = 16;
+  static constexpr int MAX_SAMPLES = 256; // steps recorded before recording stops
+  bool enabled = false;
+  int steps = 0;
+  cudaEvent_t ev[MAX_SAMPLES][MAX_STAGES][2];
+  bool used[MAX_SAMPLES][MAX_STAGES];
+  bool created = false;
+  ~StageProfiler();
+  void enable(bool on);
+  void next_step()
+  {
+    if (enabled && steps < MAX_SAMPLES)
+      ++steps;
+  }
+  void begin(cudaStream_t st, int stage)
+  {
+    if (enabled && steps > 0 && steps <= MAX_SAMPLES) {
+      cudaEventRecord(ev[steps - 1][stage][0], st);
+      used[steps - 1][stage] = true;
+    }
+  }
+  void end(cudaStream_t st, int stage)
+  {
+    if (enabled && steps > 0 && steps <= MAX_SAMPLES)
+      cudaEventRecord(ev[steps - 1][stage][1], st);
+  }
+  // synchronises; ms_sum[stage] = total milliseconds, counts[stage] = number of samples
+  void read(float* ms_sum, int* counts);
+};
+
 } // namespace b2

@@ -187,6 +187,7 @@ struct b200md_nep {
   DevBuf<int> h_type;
   DevBuf<double> h_pos, h_out;
   B2NepView view;
+  StageProfiler prof;
   int ang_block = BLK;
   size_t ang_smem = 0, rad_smem = 0;
 };
@@ -265,21 +266,36 @@ int launch_mlp(const b200md_nep* p, cudaStream_t st)
       return rc_;             \
   } while (0)
 
+// stage ids reported by b200md_nep_profile_read / b200md_nep_stage_name
+enum { ST_NEIGHBOR, ST_SPLIT, ST_DESC_R, ST_DESC_A, ST_MLP, ST_FORCE_R, ST_FORCE_A, ST_REDUCE_A,
+       ST_ZBL, ST_UNPACK, ST_COUNT };
+const char* const STAGE_NAMES[ST_COUNT] = {
+  "neighbor_update", "k_split", "k_desc_radial", "k_desc_angular", "k_mlp", "k_force_radial",
+  "k_force_angular", "k_reduce_angular", "k_zbl", "k_unpack"};
+
 int nep_pipeline(b200md_nep* p, const B2Box& box, cudaStream_t st)
 {
   const int n = p->n;
+  StageProfiler& pf = p->prof;
+  pf.begin(st, ST_SPLIT);
   k_split<<<grid_for(n, BLK), BLK, 0, st>>>(p->view, box);
   B2_LAUNCHED();
+  pf.end(st, ST_SPLIT);
+  pf.begin(st, ST_DESC_R);
   switch (p->model.K1R) {
     case 9: B2_TRY(dispatch_desc_radial<9>(p, box, st)); break;
     case 13: B2_TRY(dispatch_desc_radial<13>(p, box, st)); break;
     default: B2_TRY(dispatch_desc_radial<17>(p, box, st)); break;
   }
+  pf.end(st, ST_DESC_R);
+  pf.begin(st, ST_DESC_A);
   switch (p->model.K1A) {
     case 9: B2_TRY(launch_angular<9>(p, box, st, false)); break;
     case 13: B2_TRY(launch_angular<13>(p, box, st, false)); break;
     default: B2_TRY(launch_angular<17>(p, box, st, false)); break;
   }
+  pf.end(st, ST_DESC_A);
+  pf.begin(st, ST_MLP);
   switch (p->model.DIMP) {
     case 16: B2_TRY(launch_mlp<16>(p, st)); break;
     case 32: B2_TRY(launch_mlp<32>(p, st)); break;
@@ -290,21 +306,30 @@ int nep_pipeline(b200md_nep* p, const B2Box& box, cudaStream_t st)
     case 112: B2_TRY(launch_mlp<112>(p, st)); break;
     default: B2_TRY(launch_mlp<128>(p, st)); break;
   }
+  pf.end(st, ST_MLP);
+  pf.begin(st, ST_FORCE_R);
   switch (p->model.K1R) {
     case 9: B2_TRY(dispatch_force_radial<9>(p, box, st)); break;
     case 13: B2_TRY(dispatch_force_radial<13>(p, box, st)); break;
     default: B2_TRY(dispatch_force_radial<17>(p, box, st)); break;
   }
+  pf.end(st, ST_FORCE_R);
+  pf.begin(st, ST_FORCE_A);
   switch (p->model.K1A) {
     case 9: B2_TRY(launch_angular<9>(p, box, st, true)); break;
     case 13: B2_TRY(launch_angular<13>(p, box, st, true)); break;
     default: B2_TRY(launch_angular<17>(p, box, st, true)); break;
   }
+  pf.end(st, ST_FORCE_A);
+  pf.begin(st, ST_REDUCE_A);
   k_reduce_angular<<<grid_for(n, BLK), BLK, 0, st>>>(p->view, box);
   B2_LAUNCHED();
+  pf.end(st, ST_REDUCE_A);
   if (p->model.zbl_enabled) {
+    pf.begin(st, ST_ZBL);
     k_zbl<<<grid_for(n, BLK), BLK, 0, st>>>(p->view, box);
     B2_LAUNCHED();
+    pf.end(st, ST_ZBL);
   }
   return B200MD_OK;
 }
@@ -493,11 +518,16 @@ int b200md_nep_compute(
 {
   cudaStream_t st = (cudaStream_t)stream;
   const B2Box box = make_box(h, pbc);
+  p->prof.next_step();
+  p->prof.begin(st, ST_NEIGHBOR);
   B2_TRY(p->nb.update(box, d_type, d_position, n, st));
+  p->prof.end(st, ST_NEIGHBOR);
   B2_TRY(nep_pipeline(p, box, st));
+  p->prof.begin(st, ST_UNPACK);
   k_unpack<<<grid_for(n, 256), 256, 0, st>>>(
     n, p->nb.perm.p, p->acc.p, d_potential, d_force, d_virial);
   B2_LAUNCHED();
+  p->prof.end(st, ST_UNPACK);
   return B200MD_OK;
 }
 
@@ -547,6 +577,51 @@ int b200md_nep_export_descriptors(b200md_nep* p, float* d_q, void* stream)
 {
   k_export_q<<<grid_for(p->n, 128), 128, 0, (cudaStream_t)stream>>>(p->view, d_q);
   B2_LAUNCHED();
+  return B200MD_OK;
+}
+
+int b200md_nep_profile(b200md_nep* p, int enable)
+{
+  p->prof.enable(enable != 0);
+  return B200MD_OK;
+}
+
+int b200md_nep_profile_read(b200md_nep* p, int max_stages, float* ms_sum, int* counts)
+{
+  float ms[StageProfiler::MAX_STAGES];
+  int cn[StageProfiler::MAX_STAGES];
+  p->prof.read(ms, cn);
+  const int m = max_stages < ST_COUNT ? max_stages : ST_COUNT;
+  for (int k = 0; k < m; ++k) {
+    ms_sum[k] = ms[k];
+    counts[k] = cn[k];
+  }
+  return m;
+}
+
+const char* b200md_nep_stage_name(int stage)
+{
+  return (stage >= 0 && stage < ST_COUNT) ? STAGE_NAMES[stage] : "";
+}
+
+/* mean neighbour counts of the last compute (skin, radial, angular) -- inputs of the
+ * algorithmic-bytes formula in DESIGN.md */
+int b200md_nep_mean_neighbors(b200md_nep* p, double out3[3])
+{
+  const size_t N = (size_t)p->n;
+  std::vector<int> a(N), b(N), c(N);
+  B2_CUDA(cudaDeviceSynchronize());
+  B2_CUDA(cudaMemcpy(a.data(), p->nb.nn_skin.p, sizeof(int) * N, cudaMemcpyDeviceToHost));
+  B2_CUDA(cudaMemcpy(b.data(), p->nn_r.p, sizeof(int) * N, cudaMemcpyDeviceToHost));
+  B2_CUDA(cudaMemcpy(c.data(), p->nn_a.p, sizeof(int) * N, cudaMemcpyDeviceToHost));
+  double s[3] = {0, 0, 0};
+  for (size_t i = 0; i < N; ++i) {
+    s[0] += a[i];
+    s[1] += b[i];
+    s[2] += c[i];
+  }
+  for (int k = 0; k < 3; ++k)
+    out3[k] = s[k] / (double)N;
   return B200MD_OK;
 }
 

@@ -131,6 +131,22 @@ class NEP(Potential):
     def num_rebuilds(self):
         return self._L.b200md_nep_info(self._h, 6)
 
+    def profile(self, enable=True):
+        _lib.check(self._L.b200md_nep_profile(self._h, 1 if enable else 0))
+
+    def profile_read(self):
+        """{stage name: (total ms, samples)} recorded since profile(True)."""
+        ms = (C.c_float * 16)()
+        cnt = (C.c_int * 16)()
+        m = self._L.b200md_nep_profile_read(self._h, 16, ms, cnt)
+        return {self._L.b200md_nep_stage_name(k).decode(): (float(ms[k]), int(cnt[k]))
+                for k in range(m) if cnt[k] > 0}
+
+    def mean_neighbors(self):
+        out = (C.c_double * 3)()
+        _lib.check(self._L.b200md_nep_mean_neighbors(self._h, out))
+        return dict(skin=out[0], radial=out[1], angular=out[2])
+
     def export_neighbors(self, mn_r=None, mn_a=None):
         """(NN_radial, NL_radial[n,mn_r], NN_angular, NL_angular[n,mn_a]) of the last compute, in the
         caller's atom indices, ascending; -1 padded."""

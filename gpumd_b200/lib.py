@@ -27,6 +27,10 @@ SIGNATURES = {
     "b200md_nep_export_neighbors": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]),
     "b200md_nep_export_descriptors": (C.c_int, [_vp, _vp, _vp]),
     "b200md_nep_check": (C.c_int, [_vp, _vp]),
+    "b200md_nep_profile": (C.c_int, [_vp, C.c_int]),
+    "b200md_nep_profile_read": (C.c_int, [_vp, C.c_int, C.POINTER(C.c_float), _ip]),
+    "b200md_nep_stage_name": (C.c_char_p, [C.c_int]),
+    "b200md_nep_mean_neighbors": (C.c_int, [_vp, _dp]),
     "b200md_lj_create": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_vp)]),
     "b200md_lj_destroy": (None, [_vp]),
     "b200md_lj_rc": (C.c_double, [_vp]),

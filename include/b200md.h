@@ -59,9 +59,9 @@ int b200md_nep_compute(
   b200md_nep* p, int n, const double h[9], const int pbc[3], const int* d_type,
   const double* d_position, double* d_potential, double* d_force, double* d_virial, void* stream);
 
-/* Same call with HOST buffers (pageable or pinned): copies type/position in, runs the path,
- * ACCUMULATES into the host outputs after copying them... no: OVERWRITES potential[n],
- * force[3n], virial[9n] with the result.  This is the end-to-end entry bench.py times. */
+/* Same call with HOST buffers (pageable or pinned): copies type/position to the device, runs the
+ * path, and OVERWRITES the host arrays potential[n], force[3n], virial[9n] with the result
+ * (synchronous).  This is the end-to-end entry bench.py times. */
 int b200md_nep_compute_host(
   b200md_nep* p, int n, const double h[9], const int pbc[3], const int* type,
   const double* position, double* potential, double* force, double* virial);
@@ -77,6 +77,16 @@ int b200md_nep_export_descriptors(b200md_nep* p, float* d_q, void* stream);
 
 /* synchronise and report latched device-side errors (B200MD_ERR_OVERFLOW) */
 int b200md_nep_check(b200md_nep* p, void* stream);
+
+/* Measurement hooks (no reference counterpart; the reference has no tracing).
+ * b200md_nep_profile(p,1) makes every following b200md_nep_compute record CUDA events around each
+ * stage on the launching stream (up to 256 calls); b200md_nep_profile_read synchronises and returns
+ * the number of stages, filling ms_sum[stage] (total milliseconds) and counts[stage] (samples).
+ * b200md_nep_mean_neighbors: mean skin / radial / angular list lengths of the last call. */
+int b200md_nep_profile(b200md_nep* p, int enable);
+int b200md_nep_profile_read(b200md_nep* p, int max_stages, float* ms_sum, int* counts);
+const char* b200md_nep_stage_name(int stage);
+int b200md_nep_mean_neighbors(b200md_nep* p, double out3[3]);
 
 /* ------------------------------------------------------------------------------------------
  * LJ potential.  Replaces class LJ : Potential (src/force/lj.cuh:31-49):

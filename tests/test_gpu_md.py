@@ -1,0 +1,130 @@
+"""MD-level and full-size checks on the GPU: NVE conservation (the reference's own bound,
+tests_pytest/test_md_conservation.py:27,57-64), parity after many steps, and the size-independent
+properties at BASELINE.json's 1M-atom size."""
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, TOL
+from gpumd_b200.structures import TIME_UNIT_CONVERSION, fcc, init_velocities, rocksalt_pbte
+from test_kernel_bodies_cpu import check_fv
+
+pytestmark = pytest.mark.gpu
+
+
+def run_nve(eng, s, pot_file, steps, dt_fs, temperature, seed=42, every=None):
+    import torch
+    n = s["type"].shape[0]
+    vel = init_velocities(s["mass"], temperature, seed)
+    atom = eng.Atom(s["type"], s["pos"], s["mass"], vel)
+    box = eng.Box(s["h"], s["pbc"])
+    force = eng.Force()
+    pot = force.parse_potential(pot_file, n)
+    ens = eng.Ensemble_NVE(n)
+    thermo = torch.zeros(8, dtype=torch.float64, device="cuda")
+    dt = dt_fs / TIME_UNIT_CONVERSION
+    args = (box, atom.position_per_atom, atom.type, atom.potential_per_atom, atom.force_per_atom,
+            atom.virial_per_atom)
+    force.compute(*args)
+    ens.find_thermo(box.get_volume(), atom, thermo)
+    rows = [thermo.cpu().numpy().copy()]
+    for step in range(steps):
+        ens.compute1(dt, box, atom, thermo)
+        force.compute(*args)
+        ens.compute2(dt, box, atom, thermo)
+        if every and (step + 1) % every == 0:
+            rows.append(thermo.cpu().numpy().copy())
+    pot.check()
+    rows.append(thermo.cpu().numpy().copy())
+    return atom, pot, np.array(rows)
+
+
+def total_energy(rows, n):
+    return 1.5 * n * 8.617343e-5 * rows[:, 0] + rows[:, 1]
+
+
+def test_nve_conservation_pbte(oracle, eng_mod):
+    s = rocksalt_pbte(6, rattle=0.02, seed=1)  # 1728 atoms
+    n = s["type"].shape[0]
+    atom, pot, rows = run_nve(eng_mod, s, GOLDEN / "nep_PbTe.txt", 200, 1.0, 300.0, every=10)
+    e = total_energy(rows, n)
+    dt = 1.0
+    assert np.abs(e - e[0]).max() < 2e-3 * dt * dt * n  # reference bound: 2e-3*dt^2*N eV
+    assert np.abs(e - e[0]).max() < 5e-5 * n  # and far tighter in practice
+    assert pot.num_rebuilds >= 1
+    # after 200 steps the device state still matches an oracle evaluation at the same positions
+    pos = atom.position_per_atom.cpu().numpy().reshape(3, n)
+    r = oracle.NepOracle(GOLDEN / "nep_PbTe.txt").compute(s["type"], s["h"], s["pbc"], pos)
+    check_fv(dict(force=atom.force_per_atom.cpu().numpy().reshape(3, n),
+                  virial=atom.virial_per_atom.cpu().numpy().reshape(9, n)), r)
+    # total momentum stays zero
+    v = atom.velocity_per_atom.cpu().numpy().reshape(3, n)
+    assert np.abs((v * s["mass"]).sum(axis=1)).max() < 1e-6 * np.sqrt(n)
+
+
+def test_nve_conservation_lj(oracle, eng_mod):
+    s = fcc(8, 5.30, rattle=0.0, seed=1)  # 2048 atoms, 42.4 A box
+    n = s["type"].shape[0]
+    atom, pot, rows = run_nve(eng_mod, s, GOLDEN / "lj_Ar_10A.txt", 300, 5.0, 80.0, every=10)
+    e = total_energy(rows, n)
+    assert np.abs(e - e[0]).max() < 2e-5 * n
+    assert pot.num_rebuilds >= 2  # atoms diffuse past skin/2 within 300 x 5 fs at 80 K
+    pos = atom.position_per_atom.cpu().numpy().reshape(3, n)
+    r = oracle.lj_compute(np.array([[[1.032e-2, 3.405, 10.0]]]), s["type"], s["h"], s["pbc"], pos)
+    check_fv(dict(force=atom.force_per_atom.cpu().numpy().reshape(3, n),
+                  virial=atom.virial_per_atom.cpu().numpy().reshape(9, n)), r)
+
+
+@pytest.fixture(scope="module")
+def eng_mod():
+    import torch
+    from gpumd_b200 import build, engine
+    build.build_lib()
+    assert torch.cuda.is_available()
+    return engine
+
+
+def test_full_size_properties_pbte_1m(oracle, eng_mod):
+    """BASELINE config C3 size (1 000 000 atoms): properties that do not need an O(N) oracle run --
+    Newton's third law (sum of forces = 0), symmetric neighbour relation, virial symmetry of the
+    pair part, agreement of a spatial sub-block with an oracle evaluation of that block's
+    neighbourhood, determinism."""
+    import torch
+    eng = eng_mod
+    s = rocksalt_pbte(50, rattle=0.02, seed=1)
+    n = s["type"].shape[0]
+    assert n == 1_000_000
+    pot = eng.NEP(GOLDEN / "nep_PbTe.txt", n)
+    atom = eng.Atom(s["type"], s["pos"], s["mass"])
+    box = eng.Box(s["h"], s["pbc"])
+    args = (box, atom.type, atom.position_per_atom, atom.potential_per_atom, atom.force_per_atom,
+            atom.virial_per_atom)
+    pot.compute(*args)
+    pot.check()
+    f = atom.force_per_atom.cpu().numpy().reshape(3, n)
+    pe = atom.potential_per_atom.cpu().numpy()
+    assert np.isfinite(f).all() and np.isfinite(pe).all()
+    # FP32 per-atom sums: residual ~ sqrt(N) * 1e-6 * |f|
+    assert np.abs(f.sum(axis=1)).max() < 2e-3
+    NNr, NLr, NNa, NLa = pot.export_neighbors()
+    assert NNr.min() >= 40 and NNr.max() <= 80 and NNa.max() <= 10
+    # symmetric relation: j in list(i) <=> i in list(j), checked on a sample
+    rng = np.random.default_rng(0)
+    for i in rng.integers(0, n, 200):
+        for j in NLr[i, :NNr[i]][::7]:
+            assert i in NLr[j, :NNr[j]]
+    # a sub-block: oracle on all atoms within rc_r + rc_r of a probe region, compare inner atoms
+    pos = s["pos"]
+    centre = np.array([100.0, 120.0, 140.0])
+    d = pos - centre[:, None]
+    inner = np.nonzero((np.abs(d) < 6.0).all(axis=0))[0]
+    shell = np.nonzero((np.abs(d) < 6.0 + 16.5).all(axis=0))[0]
+    sub = dict(pos=np.ascontiguousarray(pos[:, shell]), type=s["type"][shell],
+               h=s["h"], pbc=np.array([0, 0, 0], np.int32))
+    r = oracle.NepOracle(GOLDEN / "nep_PbTe.txt").compute(sub["type"], sub["h"], sub["pbc"], sub["pos"])
+    where = np.searchsorted(shell, inner)
+    assert np.allclose(f[:, inner], r["force"][:, where], rtol=1e-4, atol=1e-5)
+    assert np.allclose(pe[inner], r["pe"][where], rtol=1e-5, atol=1e-6)
+    # determinism: a second evaluation is bit-identical
+    atom.force_per_atom.zero_(); atom.potential_per_atom.zero_(); atom.virial_per_atom.zero_()
+    pot.compute(*args)
+    assert np.array_equal(f, atom.force_per_atom.cpu().numpy().reshape(3, n))

@@ -1,0 +1,231 @@
+"""Parity tests proper: the CUDA path, called through the C-ABI (gpumd_b200.engine -> libb200md.so),
+against the oracle on the same seeded inputs.  Neighbour sets bit-exact; E/F/virial within the
+tolerances stated in conftest.TOL (the reference suite's own, tests_pytest/conftest.py:51-62)."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from cases import NEP_CASES
+from conftest import GOLDEN, TOL, assert_close
+from gpumd_b200.structures import fcc, init_velocities, rocksalt_pbte
+from test_kernel_bodies_cpu import check_fv
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import torch
+    from gpumd_b200 import build, engine
+    build.build_lib()
+    assert torch.cuda.is_available()
+    return engine
+
+
+class GpuNep:
+    """Adapter with the same surface as tests/emu_py.EmuNep, over the real library."""
+
+    def __init__(self, eng, model, n):
+        import torch
+        self.torch = torch
+        self.eng = eng
+        self.n = n
+        self.pot = eng.NEP(GOLDEN / model, n)
+
+    def compute(self, type_, h, pbc, pos):
+        torch = self.torch
+        n = self.n
+        box = self.eng.Box(h, pbc)
+        ty = torch.as_tensor(np.ascontiguousarray(type_, np.int32), device="cuda")
+        p = torch.as_tensor(np.ascontiguousarray(pos, np.float64).reshape(-1), device="cuda")
+        pe = torch.zeros(n, dtype=torch.float64, device="cuda")
+        f = torch.zeros(3 * n, dtype=torch.float64, device="cuda")
+        v = torch.zeros(9 * n, dtype=torch.float64, device="cuda")
+        self.pot.compute(box, ty, p, pe, f, v)
+        self.pot.check()
+        return 0, dict(pe=pe.cpu().numpy(), force=f.cpu().numpy().reshape(3, n),
+                       virial=v.cpu().numpy().reshape(9, n))
+
+    def neighbors(self, mn_r, mn_a):
+        return self.pot.export_neighbors(mn_r, mn_a)
+
+    def descriptors(self, dim):
+        return self.pot.export_descriptors()
+
+    @property
+    def rebuilds(self):
+        return self.pot.num_rebuilds
+
+
+@pytest.mark.parametrize("case", list(NEP_CASES))
+def test_nep_matches_oracle(oracle, eng, case):
+    from test_kernel_bodies_cpu import check_nep
+    model, make = NEP_CASES[case]
+    s = make()
+    n = s["type"].shape[0]
+    check_nep(oracle, GpuNep(eng, model, n), model, s, n)
+
+
+def test_nep_accumulates_and_is_deterministic(oracle, eng):
+    import torch
+    s = rocksalt_pbte(4, rattle=0.05, seed=1)
+    n = s["type"].shape[0]
+    dev = GpuNep(eng, "nep_PbTe.txt", n)
+    _, a = dev.compute(s["type"], s["h"], s["pbc"], s["pos"])
+    _, b = dev.compute(s["type"], s["h"], s["pbc"], s["pos"])
+    assert dev.rebuilds == 1
+    # gather-only kernels: bit-identical run to run
+    assert np.array_equal(a["force"], b["force"]) and np.array_equal(a["virial"], b["virial"])
+    # += contract (nep.cu:653,755-770): pre-loaded outputs are added to, not overwritten
+    box = eng.Box(s["h"], s["pbc"])
+    ty = torch.as_tensor(s["type"], device="cuda")
+    p = torch.as_tensor(s["pos"].reshape(-1), device="cuda")
+    pe = torch.full((n,), 1.0, dtype=torch.float64, device="cuda")
+    f = torch.full((3 * n,), 2.0, dtype=torch.float64, device="cuda")
+    v = torch.full((9 * n,), 3.0, dtype=torch.float64, device="cuda")
+    dev.pot.compute(box, ty, p, pe, f, v)
+    assert np.allclose(pe.cpu().numpy() - 1.0, a["pe"], rtol=0, atol=1e-12)
+    assert np.allclose(f.cpu().numpy().reshape(3, n) - 2.0, a["force"], rtol=0, atol=1e-12)
+    assert np.allclose(v.cpu().numpy().reshape(9, n) - 3.0, a["virial"], rtol=0, atol=1e-12)
+
+
+def test_skin_list_reuse_and_rebuild(oracle, eng):
+    s = rocksalt_pbte(4, rattle=0.05, seed=1)
+    n = s["type"].shape[0]
+    dev = GpuNep(eng, "nep_PbTe.txt", n)
+    orc = oracle.NepOracle(GOLDEN / "nep_PbTe.txt")
+    rng = np.random.default_rng(3)
+    pos = s["pos"].copy()
+    dev.compute(s["type"], s["h"], s["pbc"], pos)
+    for step, amp, expect in ((1, 0.12, 1), (2, 0.12, 1), (3, 0.0, 2)):
+        disp = rng.uniform(-1, 1, pos.shape) * amp / np.sqrt(3)
+        if step == 3:
+            disp[:, 17] = [0.6, 0.0, 0.0]
+        pos = np.mod(pos + disp, s["h"][0])
+        r = orc.compute(s["type"], s["h"], s["pbc"], pos, precision=32, lists=True)
+        _, out = dev.compute(s["type"], s["h"], s["pbc"], pos)
+        assert dev.rebuilds == expect, (step, dev.rebuilds)
+        NNr, NLr, NNa, NLa = dev.neighbors(r["NL_radial"].shape[1], r["NL_angular"].shape[1])
+        assert np.array_equal(NLr, r["NL_radial"]) and np.array_equal(NLa, r["NL_angular"])
+        check_fv(out, r)
+
+
+def test_cutoff_boundary_membership(oracle, eng):
+    base = rocksalt_pbte(4, a=7.4, rattle=0.0, seed=1)
+    pos = base["pos"].copy()
+    n = pos.shape[1]
+    rng = np.random.default_rng(5)
+    for k in range(120):
+        i, j = 2 * k, 2 * k + 1
+        rc = 8.0 if k % 2 == 0 else 4.0
+        u = rng.normal(size=3)
+        u /= np.linalg.norm(u)
+        pos[:, j] = pos[:, i] + u * (rc + rng.integers(-6, 7) * 4.8e-7 * (rc / 8.0))
+    pos = np.mod(pos, base["h"][0])
+    r = oracle.NepOracle(GOLDEN / "nep_PbTe.txt").compute(
+        base["type"], base["h"], base["pbc"], pos, precision=32, lists=True)
+    dev = GpuNep(eng, "nep_PbTe.txt", n)
+    dev.compute(base["type"], base["h"], base["pbc"], pos)
+    NNr, NLr, NNa, NLa = dev.neighbors(r["NL_radial"].shape[1], r["NL_angular"].shape[1])
+    assert np.array_equal(NLr, r["NL_radial"]) and np.array_equal(NLa, r["NL_angular"])
+
+
+def test_small_box_fails_loudly(eng):
+    """The 250-atom / 40-atom golden single points are small-box cases (nep_small_box.cuh): the CUDA
+    path must refuse them, not approximate them."""
+    from gpumd_b200 import lib
+    s = rocksalt_pbte(3, rattle=0.0)
+    dev = GpuNep(eng, "nep_PbTe.txt", s["type"].shape[0])
+    with pytest.raises(lib.B200mdError, match="small-box"):
+        dev.compute(s["type"], s["h"], s["pbc"], s["pos"])
+
+
+def test_host_buffer_entry_point(oracle, eng):
+    """b200md_nep_compute_host: the end-to-end call bench.py times (host buffers in and out)."""
+    import torch
+    s = rocksalt_pbte(4, rattle=0.05, seed=6)
+    n = s["type"].shape[0]
+    pot = eng.NEP(GOLDEN / "nep_PbTe.txt", n)
+    pe, f, v = np.full(n, 9.0), np.full(3 * n, 9.0), np.full(9 * n, 9.0)
+    pot.compute_host(eng.Box(s["h"], s["pbc"]), s["type"], np.ascontiguousarray(s["pos"]).reshape(-1),
+                     pe, f, v)
+    r = oracle.NepOracle(GOLDEN / "nep_PbTe.txt").compute(s["type"], s["h"], s["pbc"], s["pos"])
+    check_fv(dict(force=f.reshape(3, n), virial=v.reshape(9, n)), r)
+    assert abs(pe.sum() - r["pe"].sum()) / n < TOL["energy_per_atom"]
+
+
+def _lj(eng, n):
+    return eng.LJ(GOLDEN / "lj_Ar_10A.txt", n)
+
+
+def test_lj_matches_oracle(oracle, eng):
+    import torch
+    s = fcc(6, 5.30, rattle=0.1, seed=2)
+    n = s["type"].shape[0]
+    para = np.array([[[1.032e-2, 3.405, 10.0]]])
+    r = oracle.lj_compute(para, s["type"], s["h"], s["pbc"], s["pos"])
+    pot = _lj(eng, n)
+    atom = eng.Atom(s["type"], s["pos"], s["mass"])
+    pot.compute(eng.Box(s["h"], s["pbc"]), atom.type, atom.position_per_atom,
+                atom.potential_per_atom, atom.force_per_atom, atom.virial_per_atom)
+    pot.check()
+    out = dict(force=atom.force_per_atom.cpu().numpy().reshape(3, n),
+               virial=atom.virial_per_atom.cpu().numpy().reshape(9, n))
+    assert_close(atom.potential_per_atom.cpu().numpy(), r["pe"], rtol=1e-5, atol=1e-7, what="pe")
+    check_fv(out, r)
+
+
+def test_integrator_kernels(oracle, eng):
+    """velocity-Verlet (FP64, bit-exact) and the fused thermo reduction vs the oracle."""
+    import torch
+    rng = np.random.default_rng(1)
+    n = 100_003  # not a multiple of anything
+    mass = rng.uniform(1, 200, n)
+    pos, vel = rng.normal(size=(3, n)) * 5 + 10, rng.normal(size=(3, n))
+    atom = eng.Atom(np.zeros(n, np.int32), pos, mass, vel)
+    f = rng.normal(size=(3, n))
+    atom.force_per_atom.copy_(torch.as_tensor(f.reshape(-1)))
+    ens = eng.Ensemble_NVE(n)
+    box = eng.Box(np.diag([30.0, 31.0, 32.0]).reshape(9))
+    ens.compute1(0.098, box, atom)
+    p1, v1 = oracle.velocity_verlet(True, 0.098, mass, pos, vel, f)
+    assert np.array_equal(atom.position_per_atom.cpu().numpy().reshape(3, n), p1)
+    assert np.array_equal(atom.velocity_per_atom.cpu().numpy().reshape(3, n), v1)
+    pe, vir = rng.normal(size=n), rng.normal(size=(9, n))
+    atom.potential_per_atom.copy_(torch.as_tensor(pe))
+    atom.virial_per_atom.copy_(torch.as_tensor(vir.reshape(-1)))
+    thermo = torch.zeros(8, dtype=torch.float64, device="cuda")
+    for _ in range(3):  # the ticket must re-arm between calls
+        atom.velocity_per_atom.copy_(torch.as_tensor(v1.reshape(-1)))
+        ens.compute2(0.098, box, atom, thermo)
+        p2, v2 = oracle.velocity_verlet(False, 0.098, mass, p1, v1, f)
+        want = oracle.find_thermo(n, box.get_volume(), mass, pe, v2, vir)
+        assert np.allclose(thermo.cpu().numpy(), want, rtol=1e-12, atol=1e-9)
+    a = thermo.cpu().numpy().copy()
+    atom.velocity_per_atom.copy_(torch.as_tensor(v1.reshape(-1)))
+    ens.compute2(0.098, box, atom, thermo)
+    assert np.array_equal(a, thermo.cpu().numpy())  # deterministic reduction order
+
+
+def test_force_driver_wraps_positions(oracle, eng):
+    import torch
+    s = rocksalt_pbte(4, rattle=0.05, seed=8)
+    n = s["type"].shape[0]
+    L = s["h"][0]
+    pos = s["pos"].copy()
+    pos[0, :50] += L  # outside the box by one period
+    pos[2, 50:90] -= L
+    atom = eng.Atom(s["type"], pos, s["mass"])
+    force = eng.Force()
+    force.parse_potential(GOLDEN / "nep_PbTe.txt", n)
+    box = eng.Box(s["h"], s["pbc"])
+    atom.force_per_atom.fill_(123.0)  # Force::compute zeroes the outputs first (force.cu:794-801)
+    force.compute(box, atom.position_per_atom, atom.type, atom.potential_per_atom,
+                  atom.force_per_atom, atom.virial_per_atom)
+    force.potentials[0].check()
+    wrapped = atom.position_per_atom.cpu().numpy().reshape(3, n)
+    assert np.allclose(wrapped, oracle.apply_pbc(s["h"], s["pbc"], pos), rtol=0, atol=1e-12)
+    r = oracle.NepOracle(GOLDEN / "nep_PbTe.txt").compute(s["type"], s["h"], s["pbc"], wrapped)
+    check_fv(dict(force=atom.force_per_atom.cpu().numpy().reshape(3, n),
+                  virial=atom.virial_per_atom.cpu().numpy().reshape(9, n)), r)
