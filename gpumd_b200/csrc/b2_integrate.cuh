@@ -34,11 +34,13 @@ B2_HD void b2_body_apply_pbc(int i, int n, const B2Box& b, double* x, double* y,
   z[i] = b.h[6] * sx + b.h[7] * sy + b.h[8] * sz;
 }
 
+// `stride` = distance between the x, y, z blocks of the SoA arrays (= n for GPUMD's own arrays;
+// larger when only the first n atoms of a longer local array are owned, domain decomposition)
 B2_HD void b2_body_vv(
-  int i, int n, bool step1, double dt, const double* mass, double* pos, double* vel,
+  int i, int stride, bool step1, double dt, const double* mass, double* pos, double* vel,
   const double* f)
 {
-  const size_t N = (size_t)n;
+  const size_t N = (size_t)stride;
   const double minv = 1.0 / mass[i];
   const double half = dt * 0.5;
 #pragma unroll
@@ -53,10 +55,10 @@ B2_HD void b2_body_vv(
 
 // per-atom contributions to the 8 sums: m v^2, U, W_ab + m v_a v_b (ab = xx,yy,zz,xy,xz,yz)
 B2_HD void b2_thermo_terms(
-  int i, int n, const double* mass, const double* pe, const double* vel, const double* virial,
+  int i, int stride, const double* mass, const double* pe, const double* vel, const double* virial,
   double* t)
 {
-  const size_t N = (size_t)n;
+  const size_t N = (size_t)stride;
   const double m = mass[i];
   const double vx = vel[i], vy = vel[N + i], vz = vel[2 * N + i];
   t[0] = (vx * vx + vy * vy + vz * vz) * m;

@@ -53,12 +53,27 @@ __global__ void __launch_bounds__(BLK) k_zero(size_t count, double* p)
 }
 
 __global__ void __launch_bounds__(BLK) k_vv(
-  int n, int step1, double dt, const double* __restrict__ mass, double* pos, double* vel,
-  const double* __restrict__ f)
+  int n, int stride, int step1, double dt, const double* __restrict__ mass, double* pos,
+  double* vel, const double* __restrict__ f)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n)
-    b2_body_vv(i, n, step1 != 0, dt, mass, pos, vel, f);
+    b2_body_vv(i, stride, step1 != 0, dt, mass, pos, vel, f);
+}
+
+// halo pack: out[d*m + k] = pos[d*stride + idx[k]] + shift[d]  (ghost positions for a neighbour
+// domain; the shift carries the periodic image / local-frame offset)
+__global__ void __launch_bounds__(BLK) k_halo_pack(
+  int m, const int* __restrict__ idx, int stride, const double* __restrict__ pos, double sx,
+  double sy, double sz, double* out)
+{
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < m) {
+    const int a = idx[k];
+    out[k] = pos[a] + sx;
+    out[(size_t)m + k] = pos[(size_t)stride + a] + sy;
+    out[2 * (size_t)m + k] = pos[2 * (size_t)stride + a] + sz;
+  }
 }
 
 __global__ void __launch_bounds__(BLK) k_scale(size_t count, double factor, double* v)
@@ -73,14 +88,14 @@ __global__ void __launch_bounds__(BLK) k_scale(size_t count, double factor, doub
 // ensemble.cu:434-633,655).  Warp-shuffle tree -> per-block partials in `scratch` -> the last
 // block to finish (ticket) sums the partials in a fixed order, so the result is deterministic.
 __global__ void __launch_bounds__(THERMO_BLK) k_thermo(
-  int n, int n_temperature, double volume, const double* __restrict__ mass,
+  int n, int stride, int n_temperature, double volume, const double* __restrict__ mass,
   const double* __restrict__ pe, const double* __restrict__ vel, const double* __restrict__ virial,
   double* thermo, double* partial, unsigned int* ticket)
 {
   double s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     double t[8];
-    b2_thermo_terms(i, n, mass, pe, vel, virial, t);
+    b2_thermo_terms(i, stride, mass, pe, vel, virial, t);
 #pragma unroll
     for (int k = 0; k < 8; ++k)
       s[k] += t[k];
@@ -305,13 +320,19 @@ int b200md_lj_check(b200md_lj* p, void* stream)
   return B200MD_OK;
 }
 
-int b200md_apply_pbc(int n, const double h[9], const int pbc[3], double* d_position, void* stream)
+int b200md_apply_pbc_strided(
+  int n, int stride, const double h[9], const int pbc[3], double* d_position, void* stream)
 {
   const B2Box box = make_box(h, pbc);
   k_apply_pbc<<<grid_for(n, BLK), BLK, 0, (cudaStream_t)stream>>>(
-    n, box, d_position, d_position + n, d_position + 2 * (size_t)n);
+    n, box, d_position, d_position + stride, d_position + 2 * (size_t)stride);
   B2_LAUNCHED();
   return B200MD_OK;
+}
+
+int b200md_apply_pbc(int n, const double h[9], const int pbc[3], double* d_position, void* stream)
+{
+  return b200md_apply_pbc_strided(n, n, h, pbc, d_position, stream);
 }
 
 int b200md_zero_properties(
@@ -328,12 +349,32 @@ int b200md_zero_properties(
   return B200MD_OK;
 }
 
+int b200md_velocity_verlet_strided(
+  int is_step1, int n, int stride, double time_step, const double* d_mass, double* d_position,
+  double* d_velocity, const double* d_force, void* stream)
+{
+  k_vv<<<grid_for(n, BLK), BLK, 0, (cudaStream_t)stream>>>(
+    n, stride, is_step1, time_step, d_mass, d_position, d_velocity, d_force);
+  B2_LAUNCHED();
+  return B200MD_OK;
+}
+
 int b200md_velocity_verlet(
   int is_step1, int n, double time_step, const double* d_mass, double* d_position,
   double* d_velocity, const double* d_force, void* stream)
 {
-  k_vv<<<grid_for(n, BLK), BLK, 0, (cudaStream_t)stream>>>(
-    n, is_step1, time_step, d_mass, d_position, d_velocity, d_force);
+  return b200md_velocity_verlet_strided(
+    is_step1, n, n, time_step, d_mass, d_position, d_velocity, d_force, stream);
+}
+
+int b200md_halo_pack(
+  int m, const int* d_index, int stride, const double* d_position, const double shift[3],
+  double* d_out, void* stream)
+{
+  if (m <= 0)
+    return B200MD_OK;
+  k_halo_pack<<<grid_for(m, BLK), BLK, 0, (cudaStream_t)stream>>>(
+    m, d_index, stride, d_position, shift[0], shift[1], shift[2], d_out);
   B2_LAUNCHED();
   return B200MD_OK;
 }
@@ -348,12 +389,22 @@ int b200md_find_thermo(
   const double* d_velocity, const double* d_virial, double* d_thermo8, void* d_scratch,
   void* stream)
 {
+  return b200md_find_thermo_strided(
+    n, n, n_temperature, volume, d_mass, d_potential, d_velocity, d_virial, d_thermo8, d_scratch,
+    stream);
+}
+
+int b200md_find_thermo_strided(
+  int n, int stride, int n_temperature, double volume, const double* d_mass,
+  const double* d_potential, const double* d_velocity, const double* d_virial, double* d_thermo8,
+  void* d_scratch, void* stream)
+{
   // scratch layout: [ticket (64 bytes, must be zero before the FIRST call)] [8*blocks doubles]
   unsigned int* ticket = (unsigned int*)d_scratch;
   double* partial = (double*)((char*)d_scratch + 64);
   const int g = thermo_blocks(n);
   k_thermo<<<g, THERMO_BLK, 0, (cudaStream_t)stream>>>(
-    n, n_temperature, volume, d_mass, d_potential, d_velocity, d_virial, d_thermo8, partial,
+    n, stride, n_temperature, volume, d_mass, d_potential, d_velocity, d_virial, d_thermo8, partial,
     ticket);
   B2_LAUNCHED();
   return B200MD_OK;

@@ -24,6 +24,15 @@ __global__ void k_init_perm(int n, int* perm, int* flags)
 
 __global__ void k_force_rebuild(int* flags) { flags[0] = 1; }
 
+__global__ void k_reset_perm(int n, int* perm, int* flags)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n)
+    perm[i] = i;
+  if (i == 0)
+    flags[0] = 1;
+}
+
 __global__ void __launch_bounds__(BLK) k_pack_check(
   B2NeighborView v, B2Box box, const int* __restrict__ type, const double* __restrict__ x,
   const double* __restrict__ y, const double* __restrict__ z, float trigger_d2)
@@ -182,6 +191,7 @@ B2Grid make_grid(const B2Box& box, double cell_size)
 int Neighbor::init(int num_atoms, double rc_, int mn_skin_)
 {
   n = num_atoms;
+  capacity = num_atoms;
   rc = rc_;
   mn_skin = mn_skin_;
   B2_CUDA(atoms.reserve(n));
@@ -225,9 +235,14 @@ B2NeighborView Neighbor::view() const
 int Neighbor::update(
   const B2Box& box, const int* d_type, const double* d_pos, int n_in, cudaStream_t st)
 {
-  if (n_in != n) {
-    set_error("number of atoms differs from the value given at construction");
+  if (n_in > capacity || n_in <= 0) {
+    set_error("number of atoms exceeds the capacity given at construction");
     return B200MD_ERR_ARG;
+  }
+  if (n_in != n) {
+    const int rc_inv = invalidate(n_in, st);
+    if (rc_inv != B200MD_OK)
+      return rc_inv;
   }
   // large-box requirement of the reference: nep.cu:1304-1312 (small boxes use explicit images)
   for (int d = 0; d < 3; ++d) {
@@ -284,6 +299,18 @@ int Neighbor::update(
   k_skin_list<<<grid_for(n, 128), 128, 0, st>>>(v, box, g, cutoff);
   B2_LAUNCHED();
   k_rebuild_done<<<1, 1, 0, st>>>(flags.p);
+  B2_LAUNCHED();
+  return B200MD_OK;
+}
+
+int Neighbor::invalidate(int n_new, cudaStream_t st)
+{
+  if (n_new > capacity || n_new <= 0) {
+    set_error("number of atoms exceeds the capacity given at construction");
+    return B200MD_ERR_ARG;
+  }
+  n = n_new;
+  k_reset_perm<<<grid_for(n, BLK), BLK, 0, st>>>(n, perm.p, flags.p);
   B2_LAUNCHED();
   return B200MD_OK;
 }

@@ -10,7 +10,8 @@ B2Grid make_grid(const B2Box& box, double cell_size);
 class Neighbor
 {
 public:
-  int n = 0;
+  int n = 0;        // atoms of the current system (<= capacity)
+  int capacity = 0; // atoms the buffers were sized for
   int mn_skin = 0;
   double rc = 0.0;
   double skin = 1.0; // src/force/neighbor.cuh:212
@@ -27,6 +28,8 @@ public:
   // Neighbor::find_neighbor_global, src/force/neighbor.cu:756-800 (fully asynchronous here)
   int update(const B2Box& box, const int* d_type, const double* d_pos, int n, cudaStream_t st);
   int check(cudaStream_t st, int* err_bits, int* rebuilds);
+  // forget the current ordering and lists (the caller changed the atom set or its order)
+  int invalidate(int n_new, cudaStream_t st);
   B2NeighborView view() const;
 };
 

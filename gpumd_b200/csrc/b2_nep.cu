@@ -521,6 +521,8 @@ int b200md_nep_compute(
   p->prof.next_step();
   p->prof.begin(st, ST_NEIGHBOR);
   B2_TRY(p->nb.update(box, d_type, d_position, n, st));
+  p->n = n; // n may be anything up to the capacity given at construction (domain decomposition)
+  p->view.n = n;
   p->prof.end(st, ST_NEIGHBOR);
   B2_TRY(nep_pipeline(p, box, st));
   p->prof.begin(st, ST_UNPACK);
@@ -622,6 +624,14 @@ int b200md_nep_mean_neighbors(b200md_nep* p, double out3[3])
   }
   for (int k = 0; k < 3; ++k)
     out3[k] = s[k] / (double)N;
+  return B200MD_OK;
+}
+
+int b200md_nep_invalidate(b200md_nep* p, int n_new, void* stream)
+{
+  B2_TRY(p->nb.invalidate(n_new, (cudaStream_t)stream));
+  p->n = n_new;
+  p->view.n = n_new;
   return B200MD_OK;
 }
 

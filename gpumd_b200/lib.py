@@ -44,6 +44,11 @@ SIGNATURES = {
     "b200md_thermo_scratch_bytes": (C.c_longlong, [C.c_int]),
     "b200md_find_thermo": (C.c_int, [C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200md_scale_velocity": (C.c_int, [C.c_int, C.c_double, _vp, _vp]),
+    "b200md_apply_pbc_strided": (C.c_int, [C.c_int, C.c_int, _dp, _ip, _vp, _vp]),
+    "b200md_velocity_verlet_strided": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    "b200md_find_thermo_strided": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200md_halo_pack": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _dp, _vp, _vp]),
+    "b200md_nep_invalidate": (C.c_int, [_vp, C.c_int, _vp]),
 }
 
 _LIB = None

@@ -134,6 +134,31 @@ int b200md_find_thermo(
   void* stream);
 int b200md_scale_velocity(int n, double factor, double* d_velocity, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Spatial-domain sharding (replaces the hub-and-spoke scatter/gather of NEP_MULTIGPU,
+ * src/force/nep_multigpu.cu:1249-1310,1552-1582,1764-1802).  A rank keeps ONE set of local SoA
+ * arrays of length `stride` = owned + ghost atoms; the first n entries are owned.  The *_strided
+ * variants act on the owned part in place; b200md_halo_pack gathers the positions a neighbour
+ * domain needs (out[d*m + k] = position[d*stride + index[k]] + shift[d]) into a send buffer for
+ * ncclSend/Recv.  Thermo: call b200md_find_thermo_strided with the GLOBAL n_temperature and
+ * volume; the 8 outputs are then additive over ranks (ncclAllReduce SUM).
+ * b200md_nep_invalidate: the caller changed the local atom set/order (migration): drop the cell
+ * order and lists; n_new <= the num_atoms given at creation.
+ * ------------------------------------------------------------------------------------------ */
+int b200md_apply_pbc_strided(
+  int n, int stride, const double h[9], const int pbc[3], double* d_position, void* stream);
+int b200md_velocity_verlet_strided(
+  int is_step1, int n, int stride, double time_step, const double* d_mass, double* d_position,
+  double* d_velocity, const double* d_force, void* stream);
+int b200md_find_thermo_strided(
+  int n, int stride, int n_temperature, double volume, const double* d_mass,
+  const double* d_potential, const double* d_velocity, const double* d_virial, double* d_thermo8,
+  void* d_scratch, void* stream);
+int b200md_halo_pack(
+  int m, const int* d_index, int stride, const double* d_position, const double shift[3],
+  double* d_out, void* stream);
+int b200md_nep_invalidate(b200md_nep* p, int n_new, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,8 +6,11 @@ set -u
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > gpurun_out/gpu.txt 2>&1
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
-echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -25 | tee gpurun_out/pytest_gpu.txt
+echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -q ${PYTEST_ARGS:-} 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.txt
 echo "== bench"; timeout 600 python bench.py --steps ${BENCH_STEPS:-100} --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+if [ "${RUN_REF:-0}" = "1" ]; then
+echo "== reference gpumd"; timeout 1500 python scripts/run_reference_gpumd.py ${REF_ARGS:-} 2>&1 | tail -60
+fi
 if [ "${SKIP_NCU:-0}" != "1" ]; then
 echo "== ncu launch list"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/launches.csv \

@@ -1,0 +1,132 @@
+#!/usr/bin/env python
+"""Run the UNMODIFIED reference gpumd (oracle/_ref/gpumd_ref, built by oracle/Makefile.gpumd_ref)
+on the GPU box, on inputs written by our own generators, and collect
+  (1) single-point E / per-atom force / virial dumps  -> tests/golden/refgpu_*.npz candidates
+  (2) short NVE thermo trajectories from given velocities
+  (3) its "Speed of this run" line at the BASELINE sizes (the reference-GPU bar).
+Outputs go to gpurun_out/refgpu/.  Baseline/oracle infrastructure only -- never on the product path.
+
+    python scripts/run_reference_gpumd.py [--skip-speed]
+"""
+import argparse
+import json
+import re
+import shutil
+import subprocess
+import sys
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from gpumd_b200.structures import (TIME_UNIT_CONVERSION, fcc, init_velocities, nep_type_order,  # noqa: E402
+                                   read_xyz, rocksalt_pbte)
+
+GOLDEN = ROOT / "tests" / "golden"
+BIN = ROOT / "oracle" / "_ref" / "gpumd_ref"
+OUT = ROOT / "gpurun_out" / "refgpu"
+
+
+def write_model(path, s, symbols, vel=None):
+    n = s["type"].shape[0]
+    h = s["h"].reshape(3, 3)
+    lat = " ".join(f"{v:.17g}" for v in h.T.reshape(-1))  # lattice= rows are a, b, c
+    props = "species:S:1:pos:R:3" + (":vel:R:3" if vel is not None else "")
+    pbc = " ".join("T" if p else "F" for p in s["pbc"])
+    with open(path, "w") as f:
+        f.write(f"{n}\n")
+        f.write(f'pbc="{pbc}" lattice="{lat}" properties={props}\n')
+        pos = s["pos"]
+        if vel is None:
+            for i in range(n):
+                f.write(f"{symbols[s['type'][i]]} {pos[0, i]:.17g} {pos[1, i]:.17g} {pos[2, i]:.17g}\n")
+        else:
+            v = vel / TIME_UNIT_CONVERSION  # model.xyz velocities are in A/fs (read_xyz.cu:380-387)
+            for i in range(n):
+                f.write(f"{symbols[s['type'][i]]} {pos[0, i]:.17g} {pos[1, i]:.17g} {pos[2, i]:.17g} "
+                        f"{v[0, i]:.17g} {v[1, i]:.17g} {v[2, i]:.17g}\n")
+
+
+def run_case(name, s, symbols, potential, run_in, vel=None, timeout=900):
+    d = OUT / name
+    shutil.rmtree(d, ignore_errors=True)
+    d.mkdir(parents=True)
+    shutil.copyfile(potential, d / "potential.txt")
+    write_model(d / "model.xyz", s, symbols, vel)
+    (d / "run.in").write_text("potential potential.txt\n" + run_in)
+    t0 = time.time()
+    r = subprocess.run([str(BIN)], cwd=d, capture_output=True, text=True, timeout=timeout)
+    wall = time.time() - t0
+    (d / "stdout.txt").write_text(r.stdout[-20000:] + "\n--- stderr ---\n" + r.stderr[-5000:])
+    speed = re.findall(r"Speed of this run = ([0-9.eE+-]+) atom\*step/second", r.stdout)
+    info = {"case": name, "returncode": r.returncode, "wall_s": wall,
+            "speed_atom_step_per_s": [float(x) for x in speed], "n_atoms": int(s["type"].shape[0])}
+    (d / "model.xyz").unlink()  # large; regenerated from the seeded generators
+    return d, info
+
+
+def collect_single_point(d, s, symbols):
+    out = read_xyz(d / "dump.xyz", symbols)
+    np.savez_compressed(
+        d / "single_point.npz", type=s["type"], h=s["h"], pbc=s["pbc"], pos=s["pos"],
+        energy=out["energy"], virial=out.get("virial"), force=out["forces"],
+        wrapped_pos=out["pos"])
+    (d / "dump.xyz").unlink()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--skip-speed", action="store_true")
+    args = ap.parse_args()
+    if not BIN.exists():
+        raise SystemExit(f"{BIN} missing: build it with make -C oracle -f Makefile.gpumd_ref")
+    OUT.mkdir(parents=True, exist_ok=True)
+    infos = []
+    sp = "velocity 1\nensemble nve\ntime_step 0\ndump_xyz 1 dump.xyz precision double force\nrun 1\n"
+
+    # ---- (1) single points on the large-box path ----
+    pbte_sym = nep_type_order(GOLDEN / "nep_PbTe.txt")
+    s = rocksalt_pbte(12, rattle=0.05, seed=21)  # 13 824 atoms, 78.8 A box
+    d, i = run_case("sp_pbte", s, pbte_sym, GOLDEN / "nep_PbTe.txt", sp)
+    collect_single_point(d, s, pbte_sym); infos.append(i)
+
+    unep_sym = nep_type_order(GOLDEN / "nep_UNEP_v1.txt")
+    s = fcc(12, 3.9, rattle=0.08, seed=22, num_types=16, symbols=unep_sym)  # 6912 atoms, 46.8 A
+    d, i = run_case("sp_unep", s, unep_sym, GOLDEN / "nep_UNEP_v1.txt", sp)
+    collect_single_point(d, s, unep_sym); infos.append(i)
+
+    s = fcc(14, 5.30, rattle=0.1, seed=23)  # 10 976 Ar atoms, 74.2 A
+    d, i = run_case("sp_lj", s, ["Ar"], GOLDEN / "lj_Ar_10A.txt", sp)
+    collect_single_point(d, s, ["Ar"]); infos.append(i)
+
+    # ---- (2) NVE trajectories from given velocities: thermo.out every 10 steps ----
+    md = "ensemble nve\ntime_step {dt}\ndump_thermo 10\nrun {steps}\n"
+    s = rocksalt_pbte(20, rattle=0.02, seed=1)  # 64 000 atoms
+    vel = init_velocities(s["mass"], 300.0, seed=42)
+    d, i = run_case("md_pbte", s, pbte_sym, GOLDEN / "nep_PbTe.txt", md.format(dt=1, steps=200), vel)
+    infos.append(i)
+    s = fcc(25, 5.30, rattle=0.0, seed=1)  # 62 500 atoms
+    vel = init_velocities(s["mass"], 80.0, seed=42)
+    d, i = run_case("md_lj", s, ["Ar"], GOLDEN / "lj_Ar_10A.txt", md.format(dt=5, steps=200), vel)
+    infos.append(i)
+
+    # ---- (3) throughput at the BASELINE sizes ----
+    if not args.skip_speed:
+        s = rocksalt_pbte(50, rattle=0.02, seed=1)  # C3: 1 000 000 atoms
+        vel = init_velocities(s["mass"], 300.0, seed=42)
+        d, i = run_case("speed_pbte_1m", s, pbte_sym, GOLDEN / "nep_PbTe.txt",
+                        "ensemble nve\ntime_step 1\ndump_thermo 100\nrun 200\n", vel, timeout=1500)
+        infos.append(i)
+        s = fcc(63, 5.30, rattle=0.0, seed=1)  # C2: 1 000 188 atoms
+        vel = init_velocities(s["mass"], 80.0, seed=42)
+        d, i = run_case("speed_lj_1m", s, ["Ar"], GOLDEN / "lj_Ar_10A.txt",
+                        "ensemble nve\ntime_step 5\ndump_thermo 100\nrun 200\n", vel, timeout=1500)
+        infos.append(i)
+    (OUT / "summary.json").write_text(json.dumps(infos, indent=1))
+    print(json.dumps(infos, indent=1))
+
+
+if __name__ == "__main__":
+    main()

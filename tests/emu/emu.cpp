@@ -426,7 +426,7 @@ void emu_velocity_verlet(
   int step1, int n, double dt, const double* mass, double* pos, double* vel, const double* f)
 {
   for (int i = 0; i < n; ++i)
-    b2_body_vv(i, n, step1 != 0, dt, mass, pos, vel, f);
+    b2_body_vv(i, n, step1 != 0, dt, mass, pos, vel, f); // stride = n
 }
 void emu_find_thermo(
   int n, int n_temp, double volume, const double* mass, const double* pe, const double* vel,
