@@ -103,8 +103,12 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def crystal(cells):
-    from gpumd_b200.structures import init_velocities, rocksalt_pbte
+def crystal(cells, workload="pbte"):
+    from gpumd_b200.structures import fcc, init_velocities, rocksalt_pbte
+    if workload == "lj":  # config C2: fcc argon, a = 5.30 A, 80 K
+        s = fcc(cells, 5.30, rattle=0.0, seed=1)
+        s["vel"] = init_velocities(s["mass"], 80.0, seed=42)
+        return s
     s = rocksalt_pbte(cells, rattle=0.02, seed=1)
     s["vel"] = init_velocities(s["mass"], 300.0, seed=42)
     return s
@@ -181,6 +185,51 @@ def cpu_baseline(seconds=15.0):
                       f"{dt:.1f} s"}
 
 
+def lj_side_bench(args, engine, torch):
+    """--workload lj: config C2 (1M-atom LJ argon NVE, dt 5 fs) -- a secondary line, not the
+    BASELINE metric; same step definition and timing rules."""
+    from gpumd_b200.structures import TIME_UNIT_CONVERSION
+    cells = 63 if args.cells == 50 else args.cells
+    s = crystal(cells, "lj")
+    n = s["type"].shape[0]
+    atom = engine.Atom(s["type"], s["pos"], s["mass"], s["vel"])
+    box = engine.Box(s["h"], s["pbc"])
+    force = engine.Force()
+    pot = force.parse_potential(GOLDEN / "lj_Ar_10A.txt", n)
+    ens = engine.Ensemble_NVE(n)
+    thermo = torch.zeros(8, dtype=torch.float64, device="cuda")
+    dt = 5.0 / TIME_UNIT_CONVERSION
+    fargs = (box, atom.position_per_atom, atom.type, atom.potential_per_atom, atom.force_per_atom,
+             atom.virial_per_atom)
+
+    def step():
+        ens.compute1(dt, box, atom, thermo)
+        force.compute(*fargs)
+        ens.compute2(dt, box, atom, thermo)
+
+    force.compute(*fargs)
+    for _ in range(max(args.warmup, 3)):
+        step()
+    pot.check()
+    torch.cuda.synchronize()
+    r0 = pot.num_rebuilds
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    pot.check()
+    ms = e0.elapsed_time(e1)
+    print(json.dumps({
+        "metric": "atom-steps/sec (1M-atom LJ argon NVE, config C2)", "value": n * args.steps / (ms * 1e-3),
+        "unit": "atom-steps/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"C2: fcc Ar {cells}^3 cells = {n} atoms, LJ rc 10 A, NVE dt 5 fs, 80 K",
+                   "list_rebuilds_in_timed_region": pot.num_rebuilds - r0,
+                   "final_T_K": float(thermo.cpu().numpy()[0])}}))
+
+
 def ours(args, rank, world):
     import torch
     import torch.distributed as dist
@@ -198,6 +247,8 @@ def ours(args, rank, world):
     if world > 1:
         dist.barrier()
 
+    if args.workload == "lj":
+        return lj_side_bench(args, engine, torch)
     s = crystal(args.cells)
     n = s["type"].shape[0]
     atom = engine.Atom(s["type"], s["pos"], s["mass"], s["vel"])
@@ -358,6 +409,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=50, help="conventional cells per edge (50 -> 1M atoms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="pbte", choices=["pbte", "lj"],
+                    help="pbte = the BASELINE metric (C3); lj = secondary C2 line")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -17,6 +17,12 @@
 #define B2_LDG(p) (*(p))
 #endif
 
+#if !defined(__CUDACC__)
+struct float4 {
+  float x, y, z, w;
+};
+#endif
+
 #if defined(__CUDA_ARCH__)
 #define B2_ATOMIC_OR(p, v) atomicOr((p), (v))
 #else
@@ -135,6 +141,81 @@ B2_HD void b2_r12(
   y12 = (float)(a2.y - a1.y);
   z12 = (float)(a2.z - a1.z);
   b2_mic(b, x12, y12, z12);
+}
+
+// Per-thread register copy of what the pair geometry needs.  Orthogonal boxes (the common case)
+// get a branch-free minimum image with identical results to b2_mic: exactly one of the two
+// comparisons can be true, and an open direction has an infinite half-length.
+struct B2Geo {
+  int ortho;
+  float Lx, Ly, Lz, hx, hy, hz;
+};
+
+B2_HD B2Geo b2_geo(const B2Box& b)
+{
+  B2Geo g;
+  g.ortho = b.ortho;
+  g.Lx = b.hf[0];
+  g.Ly = b.hf[4];
+  g.Lz = b.hf[8];
+  g.hx = b.pbc[0] ? b.hf[0] * 0.5f : INFINITY;
+  g.hy = b.pbc[1] ? b.hf[4] * 0.5f : INFINITY;
+  g.hz = b.pbc[2] ? b.hf[8] * 0.5f : INFINITY;
+  return g;
+}
+
+B2_HD void b2_r12(
+  const B2Geo& g, const B2Box& b, const B2Atom& a1, const B2Atom& a2, float& x12, float& y12,
+  float& z12)
+{
+  x12 = (float)(a2.x - a1.x);
+  y12 = (float)(a2.y - a1.y);
+  z12 = (float)(a2.z - a1.z);
+  if (g.ortho) {
+    x12 += (x12 < -g.hx) ? g.Lx : ((x12 > g.hx) ? -g.Lx : 0.0f);
+    y12 += (y12 < -g.hy) ? g.Ly : ((y12 > g.hy) ? -g.Ly : 0.0f);
+    z12 += (z12 < -g.hz) ? g.Lz : ((z12 > g.hz) ? -g.Lz : 0.0f);
+  } else {
+    b2_mic(b, x12, y12, z12);
+  }
+}
+
+// 32-byte record through the read-only path as two 128-bit loads
+B2_HD B2Atom b2_load_atom(const B2Atom* p)
+{
+#if defined(__CUDA_ARCH__)
+  const int4* q = reinterpret_cast<const int4*>(p);
+  const int4 lo = __ldg(q), hi = __ldg(q + 1);
+  B2Atom a;
+  a.x = __hiloint2double(lo.y, lo.x);
+  a.y = __hiloint2double(lo.w, lo.z);
+  a.z = __hiloint2double(hi.y, hi.x);
+  a.type = hi.z;
+  a.pad = hi.w;
+  return a;
+#else
+  return *p;
+#endif
+}
+
+// sin(pi x), cos(pi x)
+B2_HD void b2_sincospi(float x, float& s, float& c)
+{
+#if defined(__CUDA_ARCH__)
+  sincospif(x, &s, &c);
+#else
+  s = sinf(3.14159265358979f * x);
+  c = cosf(3.14159265358979f * x);
+#endif
+}
+
+B2_HD float b2_cospi(float x)
+{
+#if defined(__CUDA_ARCH__)
+  return cospif(x);
+#else
+  return cosf(3.14159265358979f * x);
+#endif
 }
 
 // d^2 with the fma nesting nvcc emits for `x*x + y*y + z*z` (checked on the PTX of the reference

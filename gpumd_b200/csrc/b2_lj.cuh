@@ -19,16 +19,22 @@ struct B2LjView {
 B2_HD void b2_body_lj(int i, const B2LjView& P, const B2Box& box)
 {
   const size_t N = (size_t)P.n;
+  const B2Geo geo = b2_geo(box);
   const B2Atom a1 = P.atoms[i];
   const int row = a1.type * P.nt;
   const int nn = P.nn_skin[i];
   float pe = 0.0f, fx = 0.0f, fy = 0.0f, fz = 0.0f;
   float vxx = 0.0f, vyy = 0.0f, vzz = 0.0f, vxy = 0.0f, vxz = 0.0f, vyz = 0.0f;
+  // software pipeline: record of candidate k+1 and index of candidate k+2 in flight
+  int jn = nn > 0 ? P.nl_skin[i] : i;
+  B2Atom an = b2_load_atom(&P.atoms[jn]);
+  int j2 = nn > 1 ? P.nl_skin[N + i] : i;
   for (int k = 0; k < nn; ++k) {
-    const int j = P.nl_skin[(size_t)k * N + i];
-    const B2Atom a2 = P.atoms[j];
+    const B2Atom a2 = an;
+    an = b2_load_atom(&P.atoms[j2]);
+    j2 = (k + 2 < nn) ? P.nl_skin[(size_t)(k + 2) * N + i] : i;
     float x12, y12, z12;
-    b2_r12(box, a1, a2, x12, y12, z12);
+    b2_r12(geo, box, a1, a2, x12, y12, z12);
     const float d2 = b2_d2(x12, y12, z12);
     const int pair = row + a2.type;
     if (d2 >= B2_LDG(&P.rc2[pair]))

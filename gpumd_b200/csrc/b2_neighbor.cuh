@@ -160,6 +160,7 @@ B2_HD void b2_axis_walk(int c, int nb, int pbc, int out[5], int* cnt)
 B2_HD void b2_body_skin_list(
   int i, const B2NeighborView& v, const B2Box& box, const B2Grid& g, float cutoff2)
 {
+  const B2Geo geo = b2_geo(box);
   const B2Atom a1 = v.atoms[i];
   int cx, cy, cz;
   b2_cell_of(box, g, a1, &cx, &cy, &cz);
@@ -178,7 +179,7 @@ B2_HD void b2_body_skin_list(
           if (j == i)
             continue;
           float x12, y12, z12;
-          b2_r12(box, a1, v.atoms[j], x12, y12, z12);
+          b2_r12(geo, box, a1, v.atoms[j], x12, y12, z12);
           if (b2_d2(x12, y12, z12) < cutoff2) {
             if (count < v.mn_skin)
               v.nl_skin[(size_t)count * v.n + i] = j;

@@ -41,21 +41,40 @@ __global__ void __launch_bounds__(BLK) k_desc_angular(B2NepView P, B2Box box)
 }
 
 // One tile of MLP_BLK consecutive (cell-sorted) atoms per block.  The tile is counting-sorted by
-// type in shared memory so that the lanes of a warp read the same weight rows (uniform loads).
-template <int DIMP>
+// type in shared memory so that the lanes of a warp read the same weight rows (broadcast loads).
+// STAGE: the weights of all types are first copied to shared memory (models where they fit).
+template <int DIMP, bool STAGE>
 __global__ void __launch_bounds__(MLP_BLK) k_mlp(B2NepView P)
 {
+  extern __shared__ float4 mlp_smem4[];
   __shared__ int order[MLP_BLK];
   __shared__ int cnt[B2_MAX_TYPES + 1];
   const int tid = threadIdx.x;
   const int base = blockIdx.x * MLP_BLK;
   const int i = base + tid;
+  const float* w0 = P.w0p;
+  const float* b0 = P.b0;
+  const float* w1 = P.w1;
+  if (STAGE) {
+    float* sm = reinterpret_cast<float*>(mlp_smem4);
+    const int nw0 = P.nt * P.nneu * DIMP, nb = P.nt * P.nneu;
+    const float4* src4 = reinterpret_cast<const float4*>(P.w0p);
+    for (int k = tid; k < nw0 / 4; k += MLP_BLK)
+      mlp_smem4[k] = __ldg(&src4[k]);
+    for (int k = tid; k < nb; k += MLP_BLK) {
+      sm[nw0 + k] = __ldg(&P.b0[k]);
+      sm[nw0 + nb + k] = __ldg(&P.w1[k]);
+    }
+    w0 = sm;
+    b0 = sm + nw0;
+    w1 = sm + nw0 + nb;
+  }
   int mine = i;
+  int t = 0, rank = 0;
   if (P.nt > 1) {
     if (tid <= B2_MAX_TYPES)
       cnt[tid] = 0;
     __syncthreads();
-    int t = 0, rank = 0;
     if (i < P.n) {
       t = P.atoms[i].type;
       rank = atomicAdd(&cnt[t], 1);
@@ -72,12 +91,12 @@ __global__ void __launch_bounds__(MLP_BLK) k_mlp(B2NepView P)
     __syncthreads();
     if (i < P.n)
       order[cnt[t] + rank] = i;
-    __syncthreads();
-    if (i < P.n)
-      mine = order[tid];
   }
+  __syncthreads();
+  if (P.nt > 1 && i < P.n)
+    mine = order[tid];
   if (i < P.n)
-    b2_body_mlp<DIMP>(mine, P);
+    b2_body_mlp<DIMP, !STAGE>(mine, P, w0, b0, w1);
 }
 
 template <int NT, int K1>
@@ -254,7 +273,15 @@ int launch_angular(const b200md_nep* p, const B2Box& box, cudaStream_t st, bool 
 template <int DIMP>
 int launch_mlp(const b200md_nep* p, cudaStream_t st)
 {
-  k_mlp<DIMP><<<grid_for(p->n, MLP_BLK), MLP_BLK, 0, st>>>(p->view);
+  const size_t bytes = (size_t)p->model.nt * p->model.nneu * (DIMP + 2) * sizeof(float);
+  if (bytes <= 96 * 1024) {
+    auto kern = k_mlp<DIMP, true>;
+    if (bytes > 48 * 1024)
+      B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    kern<<<grid_for(p->n, MLP_BLK), MLP_BLK, bytes, st>>>(p->view);
+  } else {
+    k_mlp<DIMP, false><<<grid_for(p->n, MLP_BLK), MLP_BLK, 0, st>>>(p->view);
+  }
   B2_LAUNCHED();
   return B200MD_OK;
 }

@@ -97,25 +97,35 @@ struct B2NepView {
 // ---------------------------------------------------------------------------------------------
 B2_HD void b2_body_split(int i, const B2NepView& P, const B2Box& box)
 {
+  const B2Geo geo = b2_geo(box);
+  const size_t N = (size_t)P.n;
   const B2Atom a1 = P.atoms[i];
   const int nn = P.nn_skin[i];
   const int row = a1.type * P.nt;
   int cr = 0, ca = 0;
+  // software pipeline: the record of candidate k+1 and the index of candidate k+2 are in flight
+  // while candidate k is tested (the loads are dependent: index -> record)
+  int jn = nn > 0 ? P.nl_skin[i] : i;
+  B2Atom an = b2_load_atom(&P.atoms[jn]);
+  int j2 = nn > 1 ? P.nl_skin[N + i] : i;
   for (int k = 0; k < nn; ++k) {
-    const int j = P.nl_skin[(size_t)k * P.n + i];
-    const B2Atom a2 = P.atoms[j];
+    const int j = jn;
+    const B2Atom a2 = an;
+    jn = j2;
+    an = b2_load_atom(&P.atoms[jn]);
+    j2 = (k + 2 < nn) ? P.nl_skin[(size_t)(k + 2) * N + i] : i;
     float x12, y12, z12;
-    b2_r12(box, a1, a2, x12, y12, z12);
+    b2_r12(geo, box, a1, a2, x12, y12, z12);
     const float d2 = b2_d2(x12, y12, z12);
     const int pair = row + a2.type;
     if (d2 >= B2_LDG(&P.rc2_r[pair]))
       continue;
     if (cr < P.mn_r)
-      P.nl_r[(size_t)cr * P.n + i] = j;
+      P.nl_r[(size_t)cr * N + i] = j;
     ++cr;
     if (d2 < B2_LDG(&P.rc2_a[pair])) {
       if (ca < P.mn_a)
-        P.nl_a[(size_t)ca * P.n + i] = j;
+        P.nl_a[(size_t)ca * N + i] = j;
       ++ca;
     }
   }
@@ -139,7 +149,7 @@ B2_HD void b2_basis(float d, float rc, float rcinv, float* fn)
 {
   float fc = 0.0f;
   if (d < rc)
-    fc = 0.5f * cosf(3.1415927f * (d * rcinv)) + 0.5f;
+    fc = 0.5f * b2_cospi(d * rcinv) + 0.5f;
   const float y = d * rcinv - 1.0f;
   const float x = 2.0f * y * y - 1.0f;
   const float hfc = 0.5f * fc;
@@ -162,12 +172,7 @@ B2_HD void b2_basis_d(float d, float rc, float rcinv, float* fn, float* fnp)
   float fc = 0.0f, fcp = 0.0f;
   if (d < rc) {
     float s, c;
-#if defined(__CUDA_ARCH__)
-    sincosf(3.1415927f * (d * rcinv), &s, &c);
-#else
-    s = sinf(3.1415927f * (d * rcinv));
-    c = cosf(3.1415927f * (d * rcinv));
-#endif
+    b2_sincospi(d * rcinv, s, c);
     fc = 0.5f * c + 0.5f;
     fcp = -1.5707963f * s * rcinv;
   }
@@ -207,6 +212,7 @@ template <int NT, int K1>
 B2_HD void b2_body_desc_radial(
   int i, const B2NepView& P, const B2Box& box, float* acc, int stride, int lane)
 {
+  const B2Geo geo = b2_geo(box);
   const B2Atom a1 = P.atoms[i];
   const int t1 = a1.type;
   const int nn = P.nn_r[i];
@@ -221,11 +227,15 @@ B2_HD void b2_body_desc_radial(
     for (int m = 0; m < P.nt * K1; ++m)
       acc[(size_t)m * stride + lane] = 0.0f;
   }
+  int jn = nn > 0 ? P.nl_r[i] : i;
+  B2Atom an = b2_load_atom(&P.atoms[jn]);
+  int j2 = nn > 1 ? P.nl_r[(size_t)P.n + i] : i;
   for (int s = 0; s < nn; ++s) {
-    const int j = P.nl_r[(size_t)s * P.n + i];
-    const B2Atom a2 = P.atoms[j];
+    const B2Atom a2 = an;
+    an = b2_load_atom(&P.atoms[j2]);
+    j2 = (s + 2 < nn) ? P.nl_r[(size_t)(s + 2) * P.n + i] : i;
     float x12, y12, z12;
-    b2_r12(box, a1, a2, x12, y12, z12);
+    b2_r12(geo, box, a1, a2, x12, y12, z12);
     const float d = sqrtf(b2_d2(x12, y12, z12));
     const int t2 = a2.type;
     const int pair = t1 * P.nt + t2;
@@ -371,6 +381,7 @@ template <int K1, int NCH>
 B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
 {
   const float C3B[B2_NABC] = {B2_C3B_LIST};
+  const B2Geo geo = b2_geo(box);
   const B2Atom a1 = P.atoms[i];
   const int t1 = a1.type;
   const int nn = P.nn_a[i];
@@ -383,9 +394,9 @@ B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
         s[c][abc] = 0.0f;
     for (int m = 0; m < nn; ++m) {
       const int j = P.nl_a[(size_t)m * P.n + i];
-      const B2Atom a2 = P.atoms[j];
+      const B2Atom a2 = b2_load_atom(&P.atoms[j]);
       float x12, y12, z12;
-      b2_r12(box, a1, a2, x12, y12, z12);
+      b2_r12(geo, box, a1, a2, x12, y12, z12);
       const float d = sqrtf(b2_d2(x12, y12, z12));
       const int pair = t1 * P.nt + a2.type;
       float fn[K1];
@@ -450,8 +461,11 @@ B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
 // per-atom MLP (apply_ann_one_layer[_nep5], nep_utilities.cuh:169-194, 285-310; nep.cu:583-657)
 // plus the radial pre-contraction U_i[t][k] = sum_n Fp_i[n] c[t_i,t,n,k].
 // ---------------------------------------------------------------------------------------------
-template <int DIMP>
-B2_HD void b2_body_mlp(int i, const B2NepView& P)
+// w0_all / b0_all / w1_all: [nt][nneu][DIMP], [nt][nneu], [nt][nneu] -- either the global tables
+// (GLOBAL_W = true, read through the read-only path) or a shared-memory copy staged by the block.
+template <int DIMP, bool GLOBAL_W>
+B2_HD void b2_body_mlp(
+  int i, const B2NepView& P, const float* w0_all, const float* b0_all, const float* w1_all)
 {
   const int t = P.atoms[i].type;
   float q[DIMP], Fp[DIMP];
@@ -460,23 +474,35 @@ B2_HD void b2_body_mlp(int i, const B2NepView& P)
     q[d] = (d < P.dim) ? P.q[(size_t)d * P.n + i] * B2_LDG(&P.q_scaler[d]) : 0.0f;
     Fp[d] = 0.0f;
   }
-  const float* w0 = P.w0p + (size_t)t * P.nneu * DIMP;
-  const float* b0 = P.b0 + (size_t)t * P.nneu;
-  const float* w1 = P.w1 + (size_t)t * P.nneu;
+  const float4* w0 = reinterpret_cast<const float4*>(w0_all + (size_t)t * P.nneu * DIMP);
+  const float* b0 = b0_all + (size_t)t * P.nneu;
+  const float* w1 = w1_all + (size_t)t * P.nneu;
   float F = 0.0f;
   for (int n = 0; n < P.nneu; ++n) {
-    const float* row = w0 + (size_t)n * DIMP;
+    const float4* row = w0 + (size_t)n * (DIMP / 4);
+    float4 w[DIMP / 4];
+#pragma unroll
+    for (int d = 0; d < DIMP / 4; ++d)
+      w[d] = GLOBAL_W ? B2_LDG(&row[d]) : row[d];
     float dot = 0.0f;
 #pragma unroll
-    for (int d = 0; d < DIMP; ++d)
-      dot = fmaf(B2_LDG(&row[d]), q[d], dot);
-    const float x1 = tanhf(dot - B2_LDG(&b0[n]));
-    const float w1n = B2_LDG(&w1[n]);
+    for (int d = 0; d < DIMP / 4; ++d) {
+      dot = fmaf(w[d].x, q[4 * d], dot);
+      dot = fmaf(w[d].y, q[4 * d + 1], dot);
+      dot = fmaf(w[d].z, q[4 * d + 2], dot);
+      dot = fmaf(w[d].w, q[4 * d + 3], dot);
+    }
+    const float x1 = tanhf(dot - (GLOBAL_W ? B2_LDG(&b0[n]) : b0[n]));
+    const float w1n = GLOBAL_W ? B2_LDG(&w1[n]) : w1[n];
     F = fmaf(w1n, x1, F);
     const float coef = w1n * (1.0f - x1 * x1);
 #pragma unroll
-    for (int d = 0; d < DIMP; ++d)
-      Fp[d] = fmaf(coef, B2_LDG(&row[d]), Fp[d]);
+    for (int d = 0; d < DIMP / 4; ++d) {
+      Fp[4 * d] = fmaf(coef, w[d].x, Fp[4 * d]);
+      Fp[4 * d + 1] = fmaf(coef, w[d].y, Fp[4 * d + 1]);
+      Fp[4 * d + 2] = fmaf(coef, w[d].z, Fp[4 * d + 2]);
+      Fp[4 * d + 3] = fmaf(coef, w[d].w, Fp[4 * d + 3]);
+    }
   }
   F -= B2_LDG(&P.bias[t]);
   P.acc[i] = (double)F;
@@ -515,6 +541,9 @@ B2_HD void b2_body_mlp(int i, const B2NepView& P)
 template <int NT, int K1>
 B2_HD void b2_body_force_radial(int i, const B2NepView& P, const B2Box& box)
 {
+  constexpr int KP4 = (K1 + 3) / 4; // float4 loads per U row (KP = 4*KP4)
+  const B2Geo geo = b2_geo(box);
+  const size_t N = (size_t)P.n;
   const B2Atom a1 = P.atoms[i];
   const int t1 = a1.type;
   const int nn = P.nn_r[i];
@@ -529,18 +558,41 @@ B2_HD void b2_body_force_radial(int i, const B2NepView& P, const B2Box& box)
   }
   float fx = 0.0f, fy = 0.0f, fz = 0.0f;
   float vxx = 0.0f, vyy = 0.0f, vzz = 0.0f, vxy = 0.0f, vxz = 0.0f, vyz = 0.0f;
+  // software pipeline (dependent loads index -> record / U row): neighbour s+1's record and U row
+  // and neighbour s+2's index are in flight while neighbour s is evaluated
+  const float4* Ubase = reinterpret_cast<const float4*>(P.U + (size_t)t1 * P.KP);
+  const size_t ust4 = (size_t)P.UST / 4;
+  int jn = nn > 0 ? P.nl_r[i] : i;
+  B2Atom an = b2_load_atom(&P.atoms[jn]);
+  float4 un[KP4];
+#pragma unroll
+  for (int q = 0; q < KP4; ++q)
+    un[q] = B2_LDG(&Ubase[(size_t)jn * ust4 + q]);
+  int j2 = nn > 1 ? P.nl_r[N + i] : i;
   for (int s = 0; s < nn; ++s) {
-    const int j = P.nl_r[(size_t)s * P.n + i];
-    const B2Atom a2 = P.atoms[j];
+    const B2Atom a2 = an;
+    float Uj[KP4 * 4];
+#pragma unroll
+    for (int q = 0; q < KP4; ++q) {
+      Uj[4 * q] = un[q].x;
+      Uj[4 * q + 1] = un[q].y;
+      Uj[4 * q + 2] = un[q].z;
+      Uj[4 * q + 3] = un[q].w;
+    }
+    an = b2_load_atom(&P.atoms[j2]);
+#pragma unroll
+    for (int q = 0; q < KP4; ++q)
+      un[q] = B2_LDG(&Ubase[(size_t)j2 * ust4 + q]);
+    j2 = (s + 2 < nn) ? P.nl_r[(size_t)(s + 2) * N + i] : i;
+
     float x12, y12, z12;
-    b2_r12(box, a1, a2, x12, y12, z12);
+    b2_r12(geo, box, a1, a2, x12, y12, z12);
     const float d = sqrtf(b2_d2(x12, y12, z12));
     const float dinv = 1.0f / d;
     const int t2 = a2.type;
     const int pair = t1 * P.nt + t2;
     float fnp[K1];
     b2_basis_d<K1, false>(d, B2_LDG(&P.rc_r[pair]), B2_LDG(&P.rcinv_r[pair]), nullptr, fnp);
-    const float* Uj = P.U + (size_t)j * P.UST + t1 * P.KP;
     float A = 0.0f, Bv = 0.0f;
     if (NT == 1) {
 #pragma unroll
@@ -577,7 +629,6 @@ B2_HD void b2_body_force_radial(int i, const B2NepView& P, const B2Box& box)
     vyz = fmaf(y12 * z12, sB, vyz);
   }
   double* a = P.acc + i;
-  const size_t N = (size_t)P.n;
   a[1 * N] = fx;
   a[2 * N] = fy;
   a[3 * N] = fz;
@@ -646,15 +697,16 @@ B2_HD void b2_body_force_angular(
       w[(size_t)(n * B2_NABC + abc) * stride + lane] = wv[abc];
   }
   // ---- pairs ----
+  const B2Geo geo = b2_geo(box);
   const B2Atom a1 = P.atoms[i];
   const int t1 = a1.type;
   const int nn = P.nn_a[i];
   const size_t plane = (size_t)P.mn_a * N;
   for (int m = 0; m < nn; ++m) {
     const int j = P.nl_a[(size_t)m * N + i];
-    const B2Atom a2 = P.atoms[j];
+    const B2Atom a2 = b2_load_atom(&P.atoms[j]);
     float x12, y12, z12;
-    b2_r12(box, a1, a2, x12, y12, z12);
+    b2_r12(geo, box, a1, a2, x12, y12, z12);
     const float d = sqrtf(b2_d2(x12, y12, z12));
     const float dinv = 1.0f / d;
     const int pair = t1 * P.nt + a2.type;
@@ -810,6 +862,7 @@ B2_HD void b2_zbl_pair(
 B2_HD void b2_body_zbl(int i, const B2NepView& P, const B2Box& box)
 {
   const size_t N = (size_t)P.n;
+  const B2Geo geo = b2_geo(box);
   const B2Atom a1 = P.atoms[i];
   const int ty1 = a1.type;
   const int zi = B2_LDG(&P.zbl_z[ty1]);
@@ -819,9 +872,9 @@ B2_HD void b2_body_zbl(int i, const B2NepView& P, const B2Box& box)
   float vxx = 0.0f, vyy = 0.0f, vzz = 0.0f, vxy = 0.0f, vxz = 0.0f, vyz = 0.0f;
   for (int m = 0; m < nn; ++m) {
     const int j = P.nl_a[(size_t)m * N + i];
-    const B2Atom a2 = P.atoms[j];
+    const B2Atom a2 = b2_load_atom(&P.atoms[j]);
     float x12, y12, z12;
-    b2_r12(box, a1, a2, x12, y12, z12);
+    b2_r12(geo, box, a1, a2, x12, y12, z12);
     const float d = sqrtf(b2_d2(x12, y12, z12));
     const float dinv = 1.0f / d;
     const int ty2 = a2.type;

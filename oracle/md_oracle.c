@@ -6,8 +6,9 @@
  *   position wrap          src/force/force.cu:424-459
  *   velocity-Verlet        src/integrate/ensemble.cu:176-214
  *   thermo reduction       src/integrate/ensemble.cu:434-633
- * LJ has no golden vector in the reference's own tests: parity for it is
- * "unpinned" -- the restatement is checked only against analytic values in tests/.
+ * LJ has no golden vector in the reference's own tests.  It is pinned instead
+ * against the output of the reference itself run on a B200 (tests/golden/refgpu_sp_lj.npz, made by
+ * scripts/run_reference_gpumd.py with oracle/_ref/gpumd_ref) and against the closed form.
  */
 #include "oracle.h"
 #include "oracle_internal.h"
@@ -132,16 +133,19 @@ void oracle_apply_pbc(int N, const double h[9], const int pbc[3], double* pos)
 void oracle_velocity_verlet(
   int is_step1, int N, double dt, const double* mass, double* pos, double* vel, const double* f)
 {
+  /* nvcc contracts `vx += ax * time_step_half` and `g_x[i] += vx * time_step`
+     (ensemble.cu:203-212) into FMAs by default; restated explicitly so the device result can be
+     compared bit for bit */
   const double half = dt * 0.5;
   for (int i = 0; i < N; ++i) {
     const double minv = 1.0 / mass[i];
     for (int d = 0; d < 3; ++d) {
       double v = vel[(size_t)d * N + i];
       const double a = f[(size_t)d * N + i] * minv;
-      v += a * half;
+      v = fma(a, half, v);
       vel[(size_t)d * N + i] = v;
       if (is_step1)
-        pos[(size_t)d * N + i] += v * dt;
+        pos[(size_t)d * N + i] = fma(v, dt, pos[(size_t)d * N + i]);
     }
   }
 }

@@ -8,6 +8,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --fo
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -q ${PYTEST_ARGS:-} 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.txt
 echo "== bench"; timeout 600 python bench.py --steps ${BENCH_STEPS:-100} --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
+echo "== bench lj"; timeout 300 python bench.py --workload lj --steps 100 --warmup 5 > gpurun_out/bench_lj.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_lj.json
 if [ "${RUN_REF:-0}" = "1" ]; then
 echo "== reference gpumd"; timeout 1500 python scripts/run_reference_gpumd.py ${REF_ARGS:-} 2>&1 | tail -60
 fi
@@ -17,7 +18,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
   python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 tail -3 gpurun_out/ncu_bench.log
 echo "== ncu full: radial kernels"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:'k_force_radial|k_desc_radial|k_split' -s 6 -c 6 \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-k_force_radial|k_desc_radial|k_split}" -s ${NCU_SKIP:-6} -c ${NCU_COUNT:-6} \
   -o gpurun_out/prof_radial -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 fi

@@ -204,7 +204,7 @@ template <int DIMP>
 static void run_mlp(emu_nep* p)
 {
   for (int i = 0; i < p->n; ++i)
-    b2_body_mlp<DIMP>(i, p->P);
+    b2_body_mlp<DIMP, true>(i, p->P, p->P.w0p, p->P.b0, p->P.w1);
 }
 
 extern "C" {

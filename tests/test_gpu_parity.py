@@ -176,6 +176,34 @@ def test_lj_matches_oracle(oracle, eng):
     check_fv(out, r)
 
 
+@pytest.mark.parametrize("case,model", [("sp_pbte", "nep_PbTe.txt"), ("sp_unep", "nep_UNEP_v1.txt")])
+def test_nep_matches_reference_gpu_single_point(eng, case, model):
+    """Directly against the reference gpumd's own output on B200 (tests/golden/refgpu_sp_*.npz)."""
+    d = np.load(GOLDEN / f"refgpu_{case}.npz")
+    n = d["type"].shape[0]
+    _, out = GpuNep(eng, model, n).compute(d["type"], d["h"], d["pbc"], d["pos"])
+    assert_close(out["pe"].sum(), float(d["energy"]), **TOL["energy"], what="energy")
+    assert abs(out["pe"].sum() - float(d["energy"])) / n < TOL["energy_per_atom"]
+    fs = max(1.0, np.abs(d["force"]).max())
+    assert_close(out["force"], d["force"], rtol=1e-4, atol=1e-5 * fs, what="force")
+    v = out["virial"].sum(axis=1)
+    v33 = np.array([v[0], v[3], v[4], v[6], v[1], v[5], v[7], v[8], v[2]])
+    assert_close(v33, d["virial"], rtol=1e-4, atol=2e-2, what="virial")
+
+
+def test_lj_matches_reference_gpu_single_point(eng):
+    d = np.load(GOLDEN / "refgpu_sp_lj.npz")
+    n = d["type"].shape[0]
+    pot = eng.LJ(GOLDEN / "lj_Ar_10A.txt", n)
+    atom = eng.Atom(d["type"], d["pos"], np.full(n, 39.948))
+    pot.compute(eng.Box(d["h"], d["pbc"]), atom.type, atom.position_per_atom,
+                atom.potential_per_atom, atom.force_per_atom, atom.virial_per_atom)
+    pot.check()
+    assert abs(atom.potential_per_atom.sum().item() - float(d["energy"])) / n < 1e-7
+    assert_close(atom.force_per_atom.cpu().numpy().reshape(3, n), d["force"], rtol=1e-4, atol=1e-6,
+                 what="force")
+
+
 def test_integrator_kernels(oracle, eng):
     """velocity-Verlet (FP64, bit-exact) and the fused thermo reduction vs the oracle."""
     import torch

@@ -71,6 +71,35 @@ def test_oracle_matches_reference_nep_cpu(oracle, model, structure):
     assert_close(r["virial"], ref["virial"], rtol=1e-5, atol=5e-6, what="virial")
 
 
+@pytest.mark.parametrize("case,model", [("sp_pbte", "nep_PbTe.txt"), ("sp_unep", "nep_UNEP_v1.txt")])
+def test_oracle_matches_reference_gpu_large_box(oracle, case, model):
+    """tests/golden/refgpu_sp_*.npz: energy / per-atom forces / virial written by the UNMODIFIED
+    reference gpumd (oracle/_ref/gpumd_ref, built from /root/reference with -arch=sm_100) on a B200,
+    large-box path (find_neighbor_list_large_box ... find_force_ZBL), inputs from our generators
+    (scripts/run_reference_gpumd.py).  This pins the FP32 restatement against the real GPU code."""
+    d = np.load(GOLDEN / f"refgpu_{case}.npz")
+    n = d["type"].shape[0]
+    r = oracle.NepOracle(GOLDEN / model).compute(d["type"], d["h"], d["pbc"], d["pos"], precision=32)
+    assert abs(r["pe"].sum() - float(d["energy"])) / n < 2e-7
+    assert_close(r["force"], d["force"], rtol=1e-5, atol=1e-5, what="force")
+    v = r["virial"].sum(axis=1)
+    v33 = np.array([v[0], v[3], v[4], v[6], v[1], v[5], v[7], v[8], v[2]])
+    assert_close(v33, d["virial"], rtol=1e-5, atol=5e-3, what="virial")
+
+
+def test_lj_oracle_matches_reference_gpu(oracle):
+    """LJ single point of the reference gpumd on B200 (10 976 Ar atoms): pins the LJ restatement,
+    which has no golden vector in the reference's own tests."""
+    d = np.load(GOLDEN / "refgpu_sp_lj.npz")
+    n = d["type"].shape[0]
+    r = oracle.lj_compute(np.array([[[1.032e-2, 3.405, 10.0]]]), d["type"], d["h"], d["pbc"], d["pos"])
+    assert abs(r["pe"].sum() - float(d["energy"])) / n < 1e-9
+    assert_close(r["force"], d["force"], rtol=1e-6, atol=5e-7, what="force")
+    v = r["virial"].sum(axis=1)
+    v33 = np.array([v[0], v[3], v[4], v[6], v[1], v[5], v[7], v[8], v[2]])
+    assert_close(v33, d["virial"], rtol=1e-6, atol=1e-4, what="virial")
+
+
 def test_oracle_f32_vs_f64(oracle):
     s = rocksalt_pbte(4, rattle=0.05, seed=1)
     m = oracle.NepOracle(GOLDEN / "nep_PbTe.txt")
