@@ -67,5 +67,25 @@ def build_lib(force=False, verbose=False):
     return LIB
 
 
+HOST = PKG / "host"
+EXE = PKG / "b200md"
+
+
+def build_host(force=False):
+    """The C++ host layer (adapter classes + standalone driver) -> gpumd_b200/b200md."""
+    nvcc = _nvcc()
+    srcs = [HOST / f for f in ("potential.cpp", "force.cpp", "ensemble.cpp", "run.cpp")]
+    deps = srcs + list(HOST.glob("*.h")) + [PKG.parent / "include" / "b200md.h", LIB]
+    if force or _stale(EXE, deps):
+        cmd = [nvcc, "-O2", "-std=c++17", "-x", "cu", "-gencode", "arch=compute_100a,code=sm_100a"] + \
+            [str(s) for s in srcs] + ["-o", str(EXE), "-L" + str(PKG), "-lb200md",
+                                      "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN", "-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("host build failed:\n" + r.stdout + r.stderr)
+    return EXE
+
+
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose=True))
+    print(build_host(force="--force" in sys.argv))

@@ -99,6 +99,14 @@ __global__ void __launch_bounds__(MLP_BLK) k_mlp(B2NepView P)
     b2_body_mlp<DIMP, !STAGE>(mine, P, w0, b0, w1);
 }
 
+template <int K1>
+__global__ void __launch_bounds__(BLK) k_utable(B2NepView P)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.n)
+    b2_body_utable<K1>(i, P);
+}
+
 template <int NT, int K1>
 __global__ void __launch_bounds__(BLK) k_force_radial(B2NepView P, B2Box box)
 {
@@ -200,7 +208,7 @@ struct b200md_nep {
     zbl_para, cov_radius;
   DevBuf<int> zbl_z;
   DevBuf<int> nn_r, nl_r, nn_a, nl_a;
-  DevBuf<float> q, sfx, FpA, U, f12;
+  DevBuf<float> q, sfx, FpR, FpA, U, f12;
   DevBuf<double> acc;
   // staging for the host-buffer entry point
   DevBuf<int> h_type;
@@ -333,6 +341,12 @@ int nep_pipeline(b200md_nep* p, const B2Box& box, cudaStream_t st)
     case 112: B2_TRY(launch_mlp<112>(p, st)); break;
     default: B2_TRY(launch_mlp<128>(p, st)); break;
   }
+  switch (p->model.K1R) {
+    case 9: k_utable<9><<<grid_for(n, BLK), BLK, 0, st>>>(p->view); break;
+    case 13: k_utable<13><<<grid_for(n, BLK), BLK, 0, st>>>(p->view); break;
+    default: k_utable<17><<<grid_for(n, BLK), BLK, 0, st>>>(p->view); break;
+  }
+  B2_LAUNCHED();
   pf.end(st, ST_MLP);
   pf.begin(st, ST_FORCE_R);
   switch (p->model.K1R) {
@@ -396,6 +410,7 @@ int nep_setup(b200md_nep* p, int num_atoms)
   B2_CUDA(p->nl_a.reserve(N * m.MN_angular));
   B2_CUDA(p->q.reserve(N * m.dim));
   B2_CUDA(p->sfx.reserve(N * m.na1 * B2_NABC));
+  B2_CUDA(p->FpR.reserve(N * m.nr1));
   B2_CUDA(p->FpA.reserve(N * m.dim_angular));
   B2_CUDA(p->U.reserve(N * m.UST));
   B2_CUDA(p->f12.reserve(N * 3 * m.MN_angular));
@@ -454,6 +469,7 @@ int nep_setup(b200md_nep* p, int num_atoms)
   P.nl_a = p->nl_a.p;
   P.q = p->q.p;
   P.sfx = p->sfx.p;
+  P.FpR = p->FpR.p;
   P.FpA = p->FpA.p;
   P.U = p->U.p;
   P.f12 = p->f12.p;

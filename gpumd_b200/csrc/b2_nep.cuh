@@ -85,6 +85,7 @@ struct B2NepView {
   int* nl_a; // [mn_a * n]
   float* q;   // [dim * n]   unscaled descriptors
   float* sfx; // [na1*24 * n] angular sums s[n][abc]
+  float* FpR; // [nr1 * n]     dU/dq, radial part (input of k_utable)
   float* FpA; // [dim_ang * n] dU/dq (already multiplied by q_scaler), angular part
   float* U;   // [n * UST]   pre-contracted radial table
   float* f12; // [3 * mn_a * n]
@@ -509,27 +510,39 @@ B2_HD void b2_body_mlp(
 #pragma unroll
   for (int d = 0; d < DIMP; ++d)
     Fp[d] *= B2_LDG(&P.q_scaler[d]);
-  // angular part of dU/dq
+  // dU/dq: radial part first (input of the U-table contraction), then the angular part
 #pragma unroll
   for (int d = 0; d < DIMP; ++d) {
-    if (d >= P.nr1 && d < P.dim)
+    if (d < P.nr1)
+      P.FpR[(size_t)d * P.n + i] = Fp[d];
+    else if (d < P.dim)
       P.FpA[(size_t)(d - P.nr1) * P.n + i] = Fp[d];
   }
-  // radial pre-contraction
+}
+
+// radial pre-contraction U_i[t2][k] = sum_n Fp_i[n] c[t_i,t2,n,k]  (one AoS row per atom, see
+// b2_body_force_radial)
+template <int K1>
+B2_HD void b2_body_utable(int i, const B2NepView& P)
+{
+  constexpr int KP = (K1 + 3) / 4 * 4;
+  const int t = P.atoms[i].type;
   float* U = P.U + (size_t)i * P.UST;
   for (int t2 = 0; t2 < P.nt; ++t2) {
-    const float* c = P.c_r + (size_t)(t * P.nt + t2) * P.nr1 * P.K1R;
-    for (int k = 0; k < P.KP; ++k) {
-      float u = 0.0f;
-      if (k < P.K1R) {
+    const float* c = P.c_r + (size_t)(t * P.nt + t2) * P.nr1 * K1;
+    float u[KP];
 #pragma unroll
-        for (int n = 0; n < DIMP; ++n) {
-          if (n < P.nr1)
-            u = fmaf(Fp[n], B2_LDG(&c[n * P.K1R + k]), u);
-        }
-      }
-      U[t2 * P.KP + k] = u;
+    for (int k = 0; k < KP; ++k)
+      u[k] = 0.0f;
+    for (int n = 0; n < P.nr1; ++n) {
+      const float f = P.FpR[(size_t)n * P.n + i];
+#pragma unroll
+      for (int k = 0; k < K1; ++k)
+        u[k] = fmaf(f, B2_LDG(&c[n * K1 + k]), u[k]);
     }
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+      U[t2 * KP + k] = u[k];
   }
 }
 

@@ -1,0 +1,40 @@
+// ensemble.h -- the Ensemble plugin interface (src/integrate/ensemble.cuh:26-157) and the NVE
+// integrator (src/integrate/ensemble_nve.cu:31-95) on top of libb200md's kernels.
+#pragma once
+#include "../../include/b200md.h"
+#include "model.h"
+#include <vector>
+
+class Ensemble
+{
+public:
+  virtual ~Ensemble() = default;
+  virtual void compute1(
+    const double time_step, const std::vector<Group>& group, Box& box, Atom& atom,
+    GPU_Vector<double>& thermo) = 0;
+  virtual void compute2(
+    const double time_step, const std::vector<Group>& group, Box& box, Atom& atom,
+    GPU_Vector<double>& thermo) = 0;
+  int type = 0;
+  int fixed_group = -1;
+  int move_group = -1;
+  double temperature = 0.0;
+
+protected:
+  // Ensemble::velocity_verlet, ensemble.cu:348-397 (plain variant) and find_thermo, :636-673
+  void velocity_verlet(const bool is_step1, const double time_step, Atom& atom);
+  void find_thermo(const double volume, Atom& atom, GPU_Vector<double>& thermo);
+  GPU_Vector<char> scratch_;
+};
+
+class Ensemble_NVE_B200 : public Ensemble
+{
+public:
+  explicit Ensemble_NVE_B200(int t = 0) { type = t; }
+  void compute1(
+    const double time_step, const std::vector<Group>& group, Box& box, Atom& atom,
+    GPU_Vector<double>& thermo) override;
+  void compute2(
+    const double time_step, const std::vector<Group>& group, Box& box, Atom& atom,
+    GPU_Vector<double>& thermo) override;
+};

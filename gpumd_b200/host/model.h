@@ -1,0 +1,45 @@
+// model.h -- Box / Atom / Group with the members the hot path touches
+// (src/model/box.cuh:18-35, src/model/atom.cuh:21-52, src/model/group.cuh:20-37).
+#pragma once
+#include "gpu_vector.h"
+#include <string>
+#include <vector>
+
+class Box
+{
+public:
+  int pbc_x = 1, pbc_y = 1, pbc_z = 1;
+  double cpu_h[18] = {0}; // [0..8] row-major (lattice vectors are columns), [9..17] inverse
+  double get_volume() const
+  {
+    const double* h = cpu_h;
+    const double v = h[0] * (h[4] * h[8] - h[5] * h[7]) + h[1] * (h[5] * h[6] - h[3] * h[8]) +
+                     h[2] * (h[3] * h[7] - h[4] * h[6]);
+    return v < 0 ? -v : v;
+  }
+  void pbc(int out[3]) const
+  {
+    out[0] = pbc_x;
+    out[1] = pbc_y;
+    out[2] = pbc_z;
+  }
+};
+
+class Group
+{
+public:
+  int number = 0;
+  std::vector<int> cpu_size;
+};
+
+class Atom
+{
+public:
+  int number_of_atoms = 0;
+  std::vector<int> cpu_type;
+  std::vector<double> cpu_mass, cpu_position_per_atom, cpu_velocity_per_atom;
+  std::vector<std::string> cpu_atom_symbol;
+  GPU_Vector<int> type;
+  GPU_Vector<double> mass, position_per_atom, velocity_per_atom, force_per_atom, virial_per_atom,
+    potential_per_atom;
+};

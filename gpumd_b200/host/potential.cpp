@@ -1,0 +1,93 @@
+// potential.cpp -- NEP_B200 / LJ_B200: forward the Potential virtuals to the C-ABI.
+// Error convention of the reference: print and exit(1) (src/utilities/error.cuh:22-62).
+#include "potential.h"
+#include <cstdio>
+#include <cstdlib>
+
+void b2h_fail(const char* where)
+{
+  fprintf(stderr, "Error in %s:\n    %s\n", where, b200md_last_error());
+  exit(1);
+}
+
+NEP_B200::NEP_B200(const char* file_potential, const int num_atoms)
+{
+  if (b200md_nep_create(file_potential, num_atoms, &handle_) != B200MD_OK)
+    b2h_fail("NEP_B200");
+  N1 = 0;
+  N2 = num_atoms;
+  rc = b200md_nep_rc(handle_);
+  printf("Use the b200md NEP backend with %d atom type(s), D = %d, %d neurons.\n",
+         b200md_nep_info(handle_, 0), b200md_nep_info(handle_, 1), b200md_nep_info(handle_, 2));
+}
+
+NEP_B200::~NEP_B200() { b200md_nep_destroy(handle_); }
+
+void NEP_B200::compute(
+  Box& box, const GPU_Vector<int>& type, const GPU_Vector<double>& position,
+  GPU_Vector<double>& potential, GPU_Vector<double>& force, GPU_Vector<double>& virial)
+{
+  int pbc[3];
+  box.pbc(pbc);
+  // legacy default stream, like every reference kernel
+  if (b200md_nep_compute(
+        handle_, (int)type.size(), box.cpu_h, pbc, type.data(), position.data(), potential.data(),
+        force.data(), virial.data(), nullptr) != B200MD_OK)
+    b2h_fail("NEP_B200::compute");
+  // the reference looks at its neighbour counts every 1000 calls (nep.cu:1014-1034); same cadence
+  // for the latched capacity check, which needs a synchronisation
+  if (++num_calls_ % 1000 == 1)
+    check();
+}
+
+int NEP_B200::type_of(const std::string& symbol) const
+{
+  for (int t = 0; t < b200md_nep_info(handle_, 0); ++t)
+    if (symbol == b200md_nep_symbol(handle_, t))
+      return t;
+  return -1;
+}
+
+void NEP_B200::check()
+{
+  if (b200md_nep_check(handle_, nullptr) != B200MD_OK)
+    b2h_fail("NEP_B200::check");
+}
+
+LJ_B200::LJ_B200(const char* file_potential, const int num_atoms)
+{
+  if (b200md_lj_create(file_potential, num_atoms, &handle_) != B200MD_OK)
+    b2h_fail("LJ_B200");
+  N1 = 0;
+  N2 = num_atoms;
+  rc = b200md_lj_rc(handle_);
+  printf("Use the b200md LJ backend with %d atom type(s).\n", b200md_lj_info(handle_, 0));
+}
+
+LJ_B200::~LJ_B200() { b200md_lj_destroy(handle_); }
+
+void LJ_B200::compute(
+  Box& box, const GPU_Vector<int>& type, const GPU_Vector<double>& position,
+  GPU_Vector<double>& potential, GPU_Vector<double>& force, GPU_Vector<double>& virial)
+{
+  int pbc[3];
+  box.pbc(pbc);
+  if (b200md_lj_compute(
+        handle_, (int)type.size(), box.cpu_h, pbc, type.data(), position.data(), potential.data(),
+        force.data(), virial.data(), nullptr) != B200MD_OK)
+    b2h_fail("LJ_B200::compute");
+}
+
+int LJ_B200::type_of(const std::string& symbol) const
+{
+  for (int t = 0; t < b200md_lj_info(handle_, 0); ++t)
+    if (symbol == b200md_lj_symbol(handle_, t))
+      return t;
+  return -1;
+}
+
+void LJ_B200::check()
+{
+  if (b200md_lj_check(handle_, nullptr) != B200MD_OK)
+    b2h_fail("LJ_B200::check");
+}

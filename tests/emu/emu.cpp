@@ -157,7 +157,7 @@ struct emu_nep {
   EmuNeighbor nb;
   int n = 0;
   std::vector<int> nn_r, nl_r, nn_a, nl_a;
-  std::vector<float> q, sfx, FpA, U, f12;
+  std::vector<float> q, sfx, FpR, FpA, U, f12;
   std::vector<double> acc;
   std::vector<int> zbl_z;
   std::vector<float> cov;
@@ -230,6 +230,7 @@ emu_nep* emu_nep_create(const char* path, int n)
   p->nl_a.resize(N * m.MN_angular);
   p->q.resize(N * m.dim);
   p->sfx.resize(N * m.na1 * B2_NABC);
+  p->FpR.resize(N * m.nr1 + 1);
   p->FpA.resize(N * m.dim_angular + 1);
   p->U.resize(N * m.UST);
   p->f12.resize(N * 3 * m.MN_angular + 1);
@@ -254,7 +255,7 @@ emu_nep* emu_nep_create(const char* path, int n)
   P.zbl_z = p->zbl_z.data(); P.zbl_para = m.zbl_para.data(); P.cov_radius = p->cov.data();
   P.n = n; P.mn_r = m.MN_radial; P.mn_a = m.MN_angular;
   P.nn_r = p->nn_r.data(); P.nl_r = p->nl_r.data(); P.nn_a = p->nn_a.data(); P.nl_a = p->nl_a.data();
-  P.q = p->q.data(); P.sfx = p->sfx.data(); P.FpA = p->FpA.data(); P.U = p->U.data();
+  P.q = p->q.data(); P.sfx = p->sfx.data(); P.FpR = p->FpR.data(); P.FpA = p->FpA.data(); P.U = p->U.data();
   P.f12 = p->f12.data(); P.acc = p->acc.data();
   return p;
 }
@@ -300,6 +301,14 @@ int emu_nep_compute(
     case 96: run_mlp<96>(p); break;
     case 112: run_mlp<112>(p); break;
     default: run_mlp<128>(p); break;
+  }
+  for (int i = 0; i < n; ++i) {
+    if (p->m.K1R == 9)
+      b2_body_utable<9>(i, P);
+    else if (p->m.K1R == 13)
+      b2_body_utable<13>(i, P);
+    else
+      b2_body_utable<17>(i, P);
   }
   switch (p->m.K1R) {
     case 9: run_force_radial<9>(p, box); break;
