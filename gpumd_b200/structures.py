@@ -10,6 +10,9 @@ import re
 
 import numpy as np
 
+K_B = 8.617343e-5           # eV/K, src/utilities/common.cuh:21
+TIME_UNIT_CONVERSION = 1.018051e+1  # fs per natural time unit, common.cuh:26
+
 MASS = {  # subset of MASS_TABLE, src/model/read_xyz.cu:36-142 (amu)
     "H": 1.008, "C": 12.011, "O": 15.999, "Al": 26.9815385, "Si": 28.085, "Ar": 39.948,
     "Ti": 47.867, "V": 50.9415, "Cr": 51.9961, "Ni": 58.6934, "Cu": 63.546, "Zr": 91.224,
@@ -65,6 +68,26 @@ def read_xyz(path, type_order=None):
     if m:
         out["virial"] = np.array([float(v) for v in m.group(1).split()])
     return out
+
+
+def write_xyz(path, s, symbols, vel=None):
+    """model.xyz in GPUMD's dialect; vel (natural units) is written in A/fs (read_xyz.cu:380-387)."""
+    n = s["type"].shape[0]
+    h = np.asarray(s["h"], dtype=np.float64).reshape(3, 3)
+    lat = " ".join(f"{v:.17g}" for v in h.T.reshape(-1))  # lattice= lists a, b, c
+    props = "species:S:1:pos:R:3" + (":vel:R:3" if vel is not None else "")
+    pbc = " ".join("T" if p else "F" for p in s["pbc"])
+    pos = s["pos"]
+    cols = [pos[0], pos[1], pos[2]]
+    if vel is not None:
+        v = np.asarray(vel) / TIME_UNIT_CONVERSION
+        cols += [v[0], v[1], v[2]]
+    sym = np.asarray(symbols)[s["type"]]
+    with open(path, "w") as f:
+        f.write(f"{n}\n")
+        f.write(f'pbc="{pbc}" lattice="{lat}" properties={props}\n')
+        for i in range(n):
+            f.write(sym[i] + " " + " ".join(f"{c[i]:.17g}" for c in cols) + "\n")
 
 
 def nep_type_order(nep_txt):
@@ -131,9 +154,6 @@ def diamond(reps, a=5.431, rattle=0.0, seed=1, symbol="Si"):
     s["mass"] = np.full(pos.shape[0], MASS[symbol])
     return s
 
-
-K_B = 8.617343e-5           # eV/K, src/utilities/common.cuh:21
-TIME_UNIT_CONVERSION = 1.018051e+1  # fs per natural time unit, common.cuh:26
 
 
 def init_velocities(mass, temperature, seed=42):

@@ -21,8 +21,8 @@ import numpy as np
 
 ROOT = Path(__file__).resolve().parents[1]
 sys.path.insert(0, str(ROOT))
-from gpumd_b200.structures import (TIME_UNIT_CONVERSION, fcc, init_velocities, nep_type_order,  # noqa: E402
-                                   read_xyz, rocksalt_pbte)
+from gpumd_b200.structures import (fcc, init_velocities, nep_type_order, read_xyz,  # noqa: E402
+                                   rocksalt_pbte, write_xyz)
 
 GOLDEN = ROOT / "tests" / "golden"
 BIN = ROOT / "oracle" / "_ref" / "gpumd_ref"
@@ -30,23 +30,7 @@ OUT = ROOT / "gpurun_out" / "refgpu"
 
 
 def write_model(path, s, symbols, vel=None):
-    n = s["type"].shape[0]
-    h = s["h"].reshape(3, 3)
-    lat = " ".join(f"{v:.17g}" for v in h.T.reshape(-1))  # lattice= rows are a, b, c
-    props = "species:S:1:pos:R:3" + (":vel:R:3" if vel is not None else "")
-    pbc = " ".join("T" if p else "F" for p in s["pbc"])
-    with open(path, "w") as f:
-        f.write(f"{n}\n")
-        f.write(f'pbc="{pbc}" lattice="{lat}" properties={props}\n')
-        pos = s["pos"]
-        if vel is None:
-            for i in range(n):
-                f.write(f"{symbols[s['type'][i]]} {pos[0, i]:.17g} {pos[1, i]:.17g} {pos[2, i]:.17g}\n")
-        else:
-            v = vel / TIME_UNIT_CONVERSION  # model.xyz velocities are in A/fs (read_xyz.cu:380-387)
-            for i in range(n):
-                f.write(f"{symbols[s['type'][i]]} {pos[0, i]:.17g} {pos[1, i]:.17g} {pos[2, i]:.17g} "
-                        f"{v[0, i]:.17g} {v[1, i]:.17g} {v[2, i]:.17g}\n")
+    write_xyz(path, s, symbols, vel)
 
 
 def run_case(name, s, symbols, potential, run_in, vel=None, timeout=900):
