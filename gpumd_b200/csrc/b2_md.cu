@@ -83,6 +83,75 @@ __global__ void __launch_bounds__(BLK) k_scale(size_t count, double factor, doub
     v[i] *= factor;
 }
 
+// ---- thermostats: the scale factor is produced ON THE DEVICE from thermo[0], so no half step
+// needs a device->host copy (the reference copies T to the host and integrates the chain there,
+// ensemble_nhc.cu:173-237) ----------------------------------------------------------------------
+
+// Berendsen: factor = sqrt(1 + coupling*(T0/T - 1)), ensemble_ber.cu:70-86
+__global__ void __launch_bounds__(BLK) k_berendsen(
+  int n, int stride, double t_target, double coupling, const double* __restrict__ thermo, double* v)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double factor = sqrt(1.0 + coupling * (t_target / thermo[0] - 1.0));
+    v[i] *= factor;
+    v[(size_t)stride + i] *= factor;
+    v[2 * (size_t)stride + i] *= factor;
+  }
+}
+
+// Nose-Hoover chain of length 4, Suzuki-Yoshida order 7 x 4 RESPA sub-steps (the scheme of
+// ensemble_nhc.cu:101-171, after Tuckerman); state = {eta[4], v_eta[4], Q[4], factor}.
+__global__ void k_nhc_chain(
+  double* state, const double* __restrict__ thermo, double dof, double kT, double dt_half)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0)
+    return;
+  constexpr int M = 4;
+  const double w[7] = {0.784513610477560, 0.235573213359357, -1.17767998417887, 1.31518632068391,
+                       -1.17767998417887, 0.235573213359357, 0.784513610477560};
+  double* eta = state;
+  double* ve = state + M;
+  const double* Q = state + 2 * M;
+  double ek2 = thermo[0] * dof * 8.617343e-5; // 2 x kinetic energy from the instantaneous T
+  double factor = 1.0;
+  for (int a = 0; a < 7; ++a) {
+    const double dt2 = dt_half * w[a] / 4.0, dt4 = 0.5 * dt2, dt8 = 0.5 * dt4;
+    for (int b = 0; b < 4; ++b) {
+      ve[M - 1] += dt4 * (ve[M - 2] * ve[M - 2] / Q[M - 2] - kT);
+      for (int m = M - 2; m >= 0; --m) {
+        const double damp = exp(-dt8 * ve[m + 1] / Q[m + 1]);
+        const double G = (m == 0) ? ek2 - dof * kT : ve[m - 1] * ve[m - 1] / Q[m - 1] - kT;
+        ve[m] = damp * (damp * ve[m] + dt4 * G);
+      }
+      for (int m = M - 1; m >= 0; --m)
+        eta[m] += dt2 * ve[m] / Q[m];
+      const double f = exp(-dt2 * ve[0] / Q[0]);
+      ek2 *= f * f;
+      factor *= f;
+      for (int m = 0; m < M - 1; ++m) {
+        const double damp = exp(-dt8 * ve[m + 1] / Q[m + 1]);
+        const double G = (m == 0) ? ek2 - dof * kT : ve[m - 1] * ve[m - 1] / Q[m - 1] - kT;
+        ve[m] = damp * (damp * ve[m] + dt4 * G);
+      }
+      ve[M - 1] += dt4 * (ve[M - 2] * ve[M - 2] / Q[M - 2] - kT);
+    }
+  }
+  state[3 * M] = factor;
+}
+
+__global__ void __launch_bounds__(BLK) k_scale_by(
+  int n, int stride, const double* __restrict__ factor, double* v)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    const double f = factor[0];
+    v[i] *= f;
+    v[(size_t)stride + i] *= f;
+    v[2 * (size_t)stride + i] *= f;
+  }
+}
+
 // One pass over mass / velocity / potential / 6 virial rows for all 8 outputs (the reference
 // launches <<<8,1024>>>, one block per output, each striding over all atoms:
 // ensemble.cu:434-633,655).  Warp-shuffle tree -> per-block partials in `scratch` -> the last
@@ -406,6 +475,66 @@ int b200md_find_thermo_strided(
   k_thermo<<<g, THERMO_BLK, 0, (cudaStream_t)stream>>>(
     n, stride, n_temperature, volume, d_mass, d_potential, d_velocity, d_virial, d_thermo8, partial,
     ticket);
+  B2_LAUNCHED();
+  return B200MD_OK;
+}
+
+int b200md_berendsen_temperature(
+  int n, int stride, double temperature, double temperature_coupling, const double* d_thermo,
+  double* d_velocity, void* stream)
+{
+  // temperature_coupling is tau_T / time_step as in run.in; the kernel uses its inverse
+  // (Ensemble_BER::Ensemble_BER, ensemble_ber.cu:26-35)
+  if (temperature_coupling <= 0.0) {
+    set_error("temperature coupling must be positive");
+    return B200MD_ERR_ARG;
+  }
+  k_berendsen<<<grid_for(n, BLK), BLK, 0, (cudaStream_t)stream>>>(
+    n, stride, temperature, 1.0 / temperature_coupling, d_thermo, d_velocity);
+  B2_LAUNCHED();
+  return B200MD_OK;
+}
+
+struct b200md_nhc {
+  DevBuf<double> state; // eta[4], v_eta[4], Q[4], factor
+  double dof = 0.0, kT = 0.0;
+};
+
+int b200md_nhc_create(
+  long long n_global, double temperature, double temperature_coupling, double time_step,
+  b200md_nhc** out)
+{
+  // Ensemble_NHC::Ensemble_NHC, ensemble_nhc.cu:31-50
+  b200md_nhc* p = new (std::nothrow) b200md_nhc;
+  if (!p || p->state.reserve(16) != cudaSuccess) {
+    delete p;
+    set_error("b200md_nhc_create: allocation failed");
+    return B200MD_ERR_CUDA;
+  }
+  const double kT = 8.617343e-5 * temperature;
+  const double tau = time_step * temperature_coupling;
+  const double dof = 3.0 * (double)n_global;
+  double h[16] = {0, 0, 0, 0, 1.0, -1.0, 1.0, -1.0, 0, 0, 0, 0, 1.0, 0, 0, 0};
+  for (int i = 0; i < 4; ++i)
+    h[8 + i] = kT * tau * tau;
+  h[8] *= dof;
+  B2_CUDA(cudaMemcpy(p->state.p, h, sizeof h, cudaMemcpyHostToDevice));
+  p->dof = dof;
+  p->kT = kT;
+  *out = p;
+  return B200MD_OK;
+}
+
+void b200md_nhc_destroy(b200md_nhc* p) { delete p; }
+
+int b200md_nhc_half_step(
+  b200md_nhc* p, int n, int stride, double time_step, const double* d_thermo, double* d_velocity,
+  void* stream)
+{
+  cudaStream_t st = (cudaStream_t)stream;
+  k_nhc_chain<<<1, 32, 0, st>>>(p->state.p, d_thermo, p->dof, p->kT, 0.5 * time_step);
+  B2_LAUNCHED();
+  k_scale_by<<<grid_for(n, BLK), BLK, 0, st>>>(n, stride, p->state.p + 12, d_velocity);
   B2_LAUNCHED();
   return B200MD_OK;
 }

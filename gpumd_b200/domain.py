@@ -68,6 +68,7 @@ class SlabDomain:
         self.own_pos = torch.as_tensor(np.ascontiguousarray(p, dtype=np.float64), device=dev)
         v = np.zeros_like(p) if vel is None else vel[:, mine]
         self.own_vel = torch.as_tensor(np.ascontiguousarray(v, dtype=np.float64), device=dev)
+        self.own_force = torch.zeros_like(self.own_vel)
         self.own_id = torch.as_tensor(mine.astype(np.int64), device=dev)
         self.exchange()
 
@@ -118,7 +119,8 @@ class SlabDomain:
         def pick(mask, shift):
             p = self.own_pos[:, mask].clone()
             p[0] += shift
-            return [p, self.own_vel[:, mask], self.own_mass[mask], self.own_type[mask], self.own_id[mask]]
+            return [p, self.own_vel[:, mask], self.own_mass[mask], self.own_type[mask], self.own_id[mask],
+                    self.own_force[:, mask]]
 
         fr, fl = self._sendrecv_var(pick(go_left, +self.w), pick(go_right, -self.w))
         self.own_pos = torch.cat([self.own_pos[:, stay], fr[0], fl[0]], dim=1).contiguous()
@@ -126,6 +128,7 @@ class SlabDomain:
         self.own_mass = torch.cat([self.own_mass[stay], fr[2], fl[2]]).contiguous()
         self.own_type = torch.cat([self.own_type[stay], fr[3], fl[3]]).contiguous()
         self.own_id = torch.cat([self.own_id[stay], fr[4], fl[4]]).contiguous()
+        self.own_force = torch.cat([self.own_force[:, stay], fr[5], fl[5]], dim=1).contiguous()
         self.n_own = int(self.own_type.shape[0])
 
         # ghost send lists (indices into the owned arrays)
@@ -150,6 +153,8 @@ class SlabDomain:
         self.pe = torch.zeros(n_loc, dtype=torch.float64, device=dev)
         self.pos.view(3, n_loc)[:, :self.n_own] = self.own_pos
         self.vel.view(3, n_loc)[:, :self.n_own] = self.own_vel
+        self.force.view(3, n_loc)[:, :self.n_own] = self.own_force  # forces travel with the atoms
+        self.ref_pos = self.own_pos.clone()  # positions at this exchange (displacement trigger)
         self.send_left = torch.zeros(3 * self.idx_left.numel(), dtype=torch.float64, device=dev)
         self.send_right = torch.zeros(3 * self.idx_right.numel(), dtype=torch.float64, device=dev)
         self.recv_right = torch.zeros(3 * self.n_ghost_right, dtype=torch.float64, device=dev)
@@ -161,6 +166,21 @@ class SlabDomain:
         n, m = self.n_own, self.n_loc
         self.own_pos = self.pos.view(3, m)[:, :n].clone()
         self.own_vel = self.vel.view(3, m)[:, :n].clone()
+        self.own_force = self.force.view(3, m)[:, :n].clone()
+
+    def needs_exchange(self, fraction=0.7):
+        """True on every rank when any owned atom anywhere has moved further than
+        fraction * skin/2 since the last exchange (one small all-reduce + one host read)."""
+        n, m = self.n_own, self.n_loc
+        d = self.pos.view(3, m)[:, :n] - self.ref_pos
+        if self.pbc[1]:
+            d[1] -= self.L[1] * torch.round(d[1] / self.L[1])
+        if self.pbc[2]:
+            d[2] -= self.L[2] * torch.round(d[2] / self.L[2])
+        worst = (d * d).sum(dim=0).max().reshape(1)
+        dist.all_reduce(worst, op=dist.ReduceOp.MAX)
+        lim = fraction * 0.5 * self.skin
+        return bool(worst.item() > lim * lim)
 
     # ------------------------------------------------------------------ per step
     def _pack(self, idx, out, shift_x):
@@ -271,5 +291,13 @@ class DomainMD:
         if d.n_loc > self.capacity:
             raise RuntimeError("local atom count exceeds the capacity of the potential instance")
         self._lib.check(self.L.b200md_nep_invalidate(self.pot._h, d.n_loc, self._st()))
-        self.compute_force()  # forces of the re-ordered local system for the next half step
         self.steps_since_exchange = 0
+
+    def maybe_exchange(self, check_every=5):
+        """Displacement-triggered migration: checked every `check_every` steps (the only host
+        synchronisation of the multi-GPU loop)."""
+        if self.steps_since_exchange and self.steps_since_exchange % check_every == 0:
+            if self.dom.needs_exchange():
+                self.exchange()
+                return True
+        return False

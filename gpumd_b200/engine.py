@@ -261,5 +261,55 @@ class Ensemble_NVE:
             _ptr(self._scratch), _stream()))
 
 
+class Ensemble_BER(Ensemble_NVE):
+    """nvt_ber, src/integrate/ensemble_ber.cu:178-233: velocity-Verlet, thermo, Berendsen scaling
+    with the factor computed on the device from thermo[0]."""
+
+    def __init__(self, num_atoms, temperature, temperature_coupling):
+        super().__init__(num_atoms)
+        self.temperature = float(temperature)
+        self.temperature_coupling = float(temperature_coupling)
+
+    def compute2(self, time_step, box, atom, thermo):
+        super().compute2(time_step, box, atom, thermo)
+        n = atom.number_of_atoms
+        _lib.check(self._L.b200md_berendsen_temperature(
+            n, n, self.temperature, self.temperature_coupling, _ptr(thermo),
+            _ptr(atom.velocity_per_atom), _stream()))
+
+
+class Ensemble_NHC(Ensemble_NVE):
+    """nvt_nhc, src/integrate/ensemble_nhc.cu:173-237 (chain integrated on the device)."""
+
+    def __init__(self, num_atoms, temperature, temperature_coupling, time_step):
+        super().__init__(num_atoms)
+        h = C.c_void_p()
+        _lib.check(self._L.b200md_nhc_create(int(num_atoms), float(temperature),
+                                             float(temperature_coupling), float(time_step), C.byref(h)))
+        self._nhc = h
+
+    def __del__(self):
+        if getattr(self, "_nhc", None):
+            self._L.b200md_nhc_destroy(self._nhc)
+            self._nhc = None
+
+    def _thermostat(self, time_step, box, atom, thermo):
+        n = atom.number_of_atoms
+        self.find_thermo(box.get_volume(), atom, thermo)
+        _lib.check(self._L.b200md_nhc_half_step(
+            self._nhc, n, n, float(time_step), _ptr(thermo), _ptr(atom.velocity_per_atom), _stream()))
+
+    def compute1(self, time_step, box, atom, thermo):
+        self._thermostat(time_step, box, atom, thermo)
+        super().compute1(time_step, box, atom, thermo)
+
+    def compute2(self, time_step, box, atom, thermo):
+        n = atom.number_of_atoms
+        _lib.check(self._L.b200md_velocity_verlet(
+            0, n, float(time_step), _ptr(atom.mass), _ptr(atom.position_per_atom),
+            _ptr(atom.velocity_per_atom), _ptr(atom.force_per_atom), _stream()))
+        self._thermostat(time_step, box, atom, thermo)
+
+
 def launch_count():
     return _lib.load().b200md_launch_count()

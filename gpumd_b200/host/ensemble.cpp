@@ -40,3 +40,58 @@ void Ensemble_NVE_B200::compute2(
   velocity_verlet(false, time_step, atom);
   find_thermo(box.get_volume(), atom, thermo);
 }
+
+void Ensemble_BER_B200::compute1(
+  const double time_step, const std::vector<Group>&, Box&, Atom& atom, GPU_Vector<double>&)
+{
+  velocity_verlet(true, time_step, atom);
+}
+
+void Ensemble_BER_B200::compute2(
+  const double time_step, const std::vector<Group>&, Box& box, Atom& atom,
+  GPU_Vector<double>& thermo)
+{
+  velocity_verlet(false, time_step, atom);
+  find_thermo(box.get_volume(), atom, thermo);
+  const int n = atom.number_of_atoms;
+  if (b200md_berendsen_temperature(
+        n, n, temperature, temperature_coupling, thermo.data(), atom.velocity_per_atom.data(),
+        nullptr) != B200MD_OK)
+    b2h_fail("Ensemble_BER_B200::compute2");
+}
+
+Ensemble_NHC_B200::Ensemble_NHC_B200(int t, int N, double T, double Tc, double time_step)
+{
+  type = t;
+  temperature = T;
+  if (b200md_nhc_create(N, T, Tc, time_step, &nhc_) != B200MD_OK)
+    b2h_fail("Ensemble_NHC_B200");
+}
+
+Ensemble_NHC_B200::~Ensemble_NHC_B200() { b200md_nhc_destroy(nhc_); }
+
+void Ensemble_NHC_B200::thermostat(
+  const double time_step, Box& box, Atom& atom, GPU_Vector<double>& thermo)
+{
+  find_thermo(box.get_volume(), atom, thermo);
+  const int n = atom.number_of_atoms;
+  if (b200md_nhc_half_step(
+        nhc_, n, n, time_step, thermo.data(), atom.velocity_per_atom.data(), nullptr) != B200MD_OK)
+    b2h_fail("Ensemble_NHC_B200::thermostat");
+}
+
+void Ensemble_NHC_B200::compute1(
+  const double time_step, const std::vector<Group>&, Box& box, Atom& atom,
+  GPU_Vector<double>& thermo)
+{
+  thermostat(time_step, box, atom, thermo);
+  velocity_verlet(true, time_step, atom);
+}
+
+void Ensemble_NHC_B200::compute2(
+  const double time_step, const std::vector<Group>&, Box& box, Atom& atom,
+  GPU_Vector<double>& thermo)
+{
+  velocity_verlet(false, time_step, atom);
+  thermostat(time_step, box, atom, thermo);
+}

@@ -27,6 +27,43 @@ protected:
   GPU_Vector<char> scratch_;
 };
 
+// replaces Ensemble_BER for type 1 (nvt_ber), src/integrate/ensemble_ber.cu:178-233
+class Ensemble_BER_B200 : public Ensemble
+{
+public:
+  Ensemble_BER_B200(int t, double T, double Tc)
+  {
+    type = t;
+    temperature = T;
+    temperature_coupling = Tc;
+  }
+  void compute1(
+    const double time_step, const std::vector<Group>& group, Box& box, Atom& atom,
+    GPU_Vector<double>& thermo) override;
+  void compute2(
+    const double time_step, const std::vector<Group>& group, Box& box, Atom& atom,
+    GPU_Vector<double>& thermo) override;
+  double temperature_coupling = 100.0;
+};
+
+// replaces Ensemble_NHC for type 2 (nvt_nhc), src/integrate/ensemble_nhc.cu:173-237
+class Ensemble_NHC_B200 : public Ensemble
+{
+public:
+  Ensemble_NHC_B200(int t, int N, double T, double Tc, double time_step);
+  ~Ensemble_NHC_B200() override;
+  void compute1(
+    const double time_step, const std::vector<Group>& group, Box& box, Atom& atom,
+    GPU_Vector<double>& thermo) override;
+  void compute2(
+    const double time_step, const std::vector<Group>& group, Box& box, Atom& atom,
+    GPU_Vector<double>& thermo) override;
+
+private:
+  void thermostat(const double time_step, Box& box, Atom& atom, GPU_Vector<double>& thermo);
+  b200md_nhc* nhc_ = nullptr;
+};
+
 class Ensemble_NVE_B200 : public Ensemble
 {
 public:

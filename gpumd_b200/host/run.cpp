@@ -8,8 +8,8 @@
 //   initialize_position (model.xyz)                 src/model/read_xyz.cu:145-425, 482-557
 //   Velocity::initialize                            src/main_gpumd/velocity.cu:55-75, 312-347
 //   Dump_Thermo                                     src/measure/dump_thermo.cu:57-129
-// Keywords: potential, velocity <T> [seed <s>], ensemble nve, time_step <fs>, dump_thermo <n>,
-// run <n>.  Anything else is an input error (exit 1), as in the reference.
+// Keywords: potential, velocity <T> [seed <s>], ensemble nve | nvt_ber T T tau | nvt_nhc T T tau,
+// time_step <fs>, dump_thermo <n>, run <n>.  Anything else is an input error (exit 1), as in the reference.
 #include "ensemble.h"
 #include "force.h"
 #include <algorithm>
@@ -276,9 +276,26 @@ private:
         initialize_velocity(a, std::atof(t[1].c_str()), use_seed, use_seed ? std::atoi(t[3].c_str()) : 0);
       }
     } else if (t[0] == "ensemble") {
-      if (t.size() != 2 || t[1] != "nve")
-        input_error("only 'ensemble nve' is supported by the b200md backend.");
-      ensemble_.reset(new Ensemble_NVE_B200(0));
+      // Integrate::parse_ensemble, integrate.cu:406-432,569-600: nvt_* take T1 T2 tau_T/dt
+      if (t.size() == 2 && t[1] == "nve") {
+        ensemble_.reset(new Ensemble_NVE_B200(0));
+      } else if (t.size() == 5 && (t[1] == "nvt_ber" || t[1] == "nvt_nhc")) {
+        const double T1 = std::atof(t[2].c_str()), T2 = std::atof(t[3].c_str());
+        const double Tc = std::atof(t[4].c_str());
+        if (T1 <= 0.0 || T2 <= 0.0)
+          input_error("Temperatures should > 0.");
+        if (T1 != T2)
+          input_error("temperature ramps are not supported by the b200md backend.");
+        if (Tc < 1.0)
+          input_error("Temperature coupling should >= 1.");
+        if (t[1] == "nvt_ber")
+          ensemble_.reset(new Ensemble_BER_B200(1, T1, Tc));
+        else
+          ensemble_.reset(new Ensemble_NHC_B200(2, a.number_of_atoms, T1, Tc, time_step_));
+      } else {
+        input_error("only 'ensemble nve', 'nvt_ber T T tau' and 'nvt_nhc T T tau' are supported "
+                    "by the b200md backend.");
+      }
     } else if (t[0] == "time_step") {
       if (t.size() < 2)
         input_error("time_step should have at least 1 parameter.");

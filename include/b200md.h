@@ -134,6 +134,27 @@ int b200md_find_thermo(
   void* stream);
 int b200md_scale_velocity(int n, double factor, double* d_velocity, void* stream);
 
+/* NVT thermostats (global velocity scaling).  `stride` as in the *_strided calls below (= n for a
+ * single domain); d_thermo[0] must hold the instantaneous GLOBAL temperature (b200md_find_thermo,
+ * all-reduced over ranks when sharded).  temperature_coupling = tau_T / time_step as in run.in.
+ *   b200md_berendsen_temperature <- gpu_berendsen_temperature, src/integrate/ensemble_ber.cu:70-86
+ *                                   (Ensemble_BER::compute2, :195-233)
+ *   b200md_nhc_*                 <- Ensemble_NHC (src/integrate/ensemble_nhc.cu:31-50, 101-237):
+ *                                   one call = find chain factor from d_thermo[0] + scale velocities,
+ *                                   i.e. the thermostat half of integrate_nvt_nhc_1 / _2.  The chain
+ *                                   is integrated on the device: no D2H copy per half step. */
+int b200md_berendsen_temperature(
+  int n, int stride, double temperature, double temperature_coupling, const double* d_thermo,
+  double* d_velocity, void* stream);
+typedef struct b200md_nhc b200md_nhc;
+int b200md_nhc_create(
+  long long n_global, double temperature, double temperature_coupling, double time_step,
+  b200md_nhc** out);
+void b200md_nhc_destroy(b200md_nhc* p);
+int b200md_nhc_half_step(
+  b200md_nhc* p, int n, int stride, double time_step, const double* d_thermo, double* d_velocity,
+  void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Spatial-domain sharding (replaces the hub-and-spoke scatter/gather of NEP_MULTIGPU,
  * src/force/nep_multigpu.cu:1249-1310,1552-1582,1764-1802).  A rank keeps ONE set of local SoA

@@ -179,6 +179,56 @@ def find_thermo(n_temp, volume, mass, pe, vel, virial):
     return t
 
 
+# ---------------------------------------------------------------- thermostats (host-side maths)
+
+def nhc_chain(state, ek2, kT, dN, dt2_particle):
+    """Nose-Hoover chain update -- restates `nhc()`, src/integrate/ensemble_nhc.cu:101-171 (run on the
+    host by the reference).  state = dict(pos[4], vel[4], mas[4]) is updated in place; returns the
+    velocity scale factor.  ek2 = 2 x kinetic energy."""
+    M, n_sy, n_respa = 4, 7, 4
+    w = [0.784513610477560, 0.235573213359357, -1.17767998417887, 1.31518632068391,
+         -1.17767998417887, 0.235573213359357, 0.784513610477560]
+    pos, vel, mas = state["pos"], state["vel"], state["mas"]
+    factor = 1.0
+    for n1 in range(n_sy):
+        dt2 = dt2_particle * w[n1] / n_respa
+        dt4 = dt2 * 0.5
+        dt8 = dt4 * 0.5
+        for _ in range(n_respa):
+            G = vel[M - 2] * vel[M - 2] / mas[M - 2] - kT
+            vel[M - 1] += dt4 * G
+            for m in range(M - 2, -1, -1):
+                tmp = np.exp(-dt8 * vel[m + 1] / mas[m + 1])
+                G = ek2 - dN * kT if m == 0 else vel[m - 1] * vel[m - 1] / mas[m - 1] - kT
+                vel[m] = tmp * (tmp * vel[m] + dt4 * G)
+            for m in range(M - 1, -1, -1):
+                pos[m] += dt2 * vel[m] / mas[m]
+            fl = np.exp(-dt2 * vel[0] / mas[0])
+            ek2 *= fl * fl
+            factor *= fl
+            for m in range(M - 1):
+                tmp = np.exp(-dt8 * vel[m + 1] / mas[m + 1])
+                G = ek2 - dN * kT if m == 0 else vel[m - 1] * vel[m - 1] / mas[m - 1] - kT
+                vel[m] = tmp * (tmp * vel[m] + dt4 * G)
+            G = vel[M - 2] * vel[M - 2] / mas[M - 2] - kT
+            vel[M - 1] += dt4 * G
+    return factor
+
+
+def nhc_state(n_atoms, temperature, temperature_coupling, time_step):
+    """Initial chain state, Ensemble_NHC::Ensemble_NHC, src/integrate/ensemble_nhc.cu:31-50."""
+    kT = 8.617343e-5 * temperature
+    tau = time_step * temperature_coupling
+    mas = [kT * tau * tau] * 4
+    mas[0] *= 3.0 * n_atoms
+    return dict(pos=[0.0] * 4, vel=[1.0, -1.0, 1.0, -1.0], mas=mas)
+
+
+def berendsen_factor(temperature, temperature_coupling, t_now):
+    """gpu_berendsen_temperature, src/integrate/ensemble_ber.cu:70-86 (coupling = 1/tau, :34)."""
+    return np.sqrt(1.0 + (1.0 / temperature_coupling) * (temperature / t_now - 1.0))
+
+
 # ---------------------------------------------------------------- the reference's own NEP_CPU
 
 def ref_available():

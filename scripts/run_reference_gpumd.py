@@ -96,6 +96,14 @@ def main():
     d, i = run_case("md_lj", s, ["Ar"], GOLDEN / "lj_Ar_10A.txt", md.format(dt=5, steps=200), vel)
     infos.append(i)
 
+    # NVT from the same start: Nose-Hoover chain and Berendsen (deterministic thermostats)
+    s = rocksalt_pbte(20, rattle=0.02, seed=1)
+    vel = init_velocities(s["mass"], 300.0, seed=42)
+    for name, ens in (("md_pbte_nhc", "nvt_nhc 300 300 100"), ("md_pbte_ber", "nvt_ber 300 300 100")):
+        d, i = run_case(name, s, pbte_sym, GOLDEN / "nep_PbTe.txt",
+                        f"ensemble {ens}\ntime_step 1\ndump_thermo 10\nrun 200\n", vel)
+        infos.append(i)
+
     # ---- (3) throughput at the BASELINE sizes ----
     if not args.skip_speed:
         s = rocksalt_pbte(50, rattle=0.02, seed=1)  # C3: 1 000 000 atoms

@@ -40,8 +40,10 @@ def _worker(rank, world, port, out_dir, steps):
         rows = [md.thermo.cpu().numpy().copy()]
         dt = 2.0 / TIME_UNIT_CONVERSION
         for k in range(steps):
-            if md.steps_since_exchange >= 25:
-                md.exchange()
+            if k == 30:
+                md.exchange()  # a forced migration/re-order in the middle of the run
+            else:
+                md.maybe_exchange(5)
             md.step(dt)
             if (k + 1) % 10 == 0:
                 rows.append(md.thermo.cpu().numpy().copy())

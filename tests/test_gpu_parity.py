@@ -236,6 +236,40 @@ def test_integrator_kernels(oracle, eng):
     assert np.array_equal(a, thermo.cpu().numpy())  # deterministic reduction order
 
 
+def test_thermostat_factors(oracle, eng):
+    """Berendsen and Nose-Hoover-chain velocity scaling: device-side factors vs the host maths of
+    the reference (oracle.berendsen_factor / oracle.nhc_chain), several consecutive half steps."""
+    import torch
+    rng = np.random.default_rng(4)
+    n = 50_000
+    mass = rng.uniform(10, 200, n)
+    from gpumd_b200.structures import K_B, init_velocities
+    vel = init_velocities(mass, 350.0, seed=9)
+    atom = eng.Atom(np.zeros(n, np.int32), rng.uniform(0, 50, (3, n)), mass, vel)
+    box = eng.Box(np.diag([50.0, 50.0, 50.0]).reshape(9))
+    thermo = torch.zeros(8, dtype=torch.float64, device="cuda")
+    dt = 1.0 / 10.18051
+    # --- Berendsen
+    ber = eng.Ensemble_BER(n, 300.0, 100.0)
+    v0 = atom.velocity_per_atom.cpu().numpy().copy()
+    ber.compute2(dt, box, atom, thermo)  # zero forces: VV leaves v unchanged, then scales
+    t_now = float(thermo[0].item())
+    assert abs(t_now - 350.0) < 1e-9
+    f = oracle.berendsen_factor(300.0, 100.0, t_now)
+    assert np.allclose(atom.velocity_per_atom.cpu().numpy(), v0 * f, rtol=1e-14, atol=0)
+    # --- Nose-Hoover chain: 6 half steps, state carried on the device
+    atom.velocity_per_atom.copy_(torch.as_tensor(v0))
+    nhc = eng.Ensemble_NHC(n, 300.0, 100.0, dt)
+    state = oracle.nhc_state(n, 300.0, 100.0, dt)
+    v_ref = v0.copy()
+    for k in range(6):
+        ek2 = (mass * (v_ref.reshape(3, n) ** 2).sum(axis=0)).sum()
+        fac = oracle.nhc_chain(state, ek2, K_B * 300.0, 3.0 * n, 0.5 * dt)
+        v_ref = v_ref * fac
+        nhc._thermostat(dt, box, atom, thermo)
+        assert np.allclose(atom.velocity_per_atom.cpu().numpy(), v_ref, rtol=1e-11, atol=0), k
+
+
 def test_force_driver_wraps_positions(oracle, eng):
     import torch
     s = rocksalt_pbte(4, rattle=0.05, seed=8)
