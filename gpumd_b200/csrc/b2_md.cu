@@ -370,11 +370,21 @@ int b200md_lj_compute(
   cudaStream_t st = (cudaStream_t)stream;
   const B2Box box = make_box(h, pbc);
   B2_TRY(p->nb.update(box, d_type, d_position, n, st));
+  p->n = n;
+  p->view.n = n;
   k_lj<<<grid_for(n, 128), 128, 0, st>>>(p->view, box);
   B2_LAUNCHED();
   k_unpack_lj<<<grid_for(n, BLK), BLK, 0, st>>>(
     n, p->nb.perm.p, p->acc.p, d_potential, d_force, d_virial);
   B2_LAUNCHED();
+  return B200MD_OK;
+}
+
+int b200md_lj_invalidate(b200md_lj* p, int n_new, void* stream)
+{
+  B2_TRY(p->nb.invalidate(n_new, (cudaStream_t)stream));
+  p->n = n_new;
+  p->view.n = n_new;
   return B200MD_OK;
 }
 

@@ -236,7 +236,7 @@ class DomainMD:
         self.L = _lib.load()
         self._lib = _lib
         cap = int(dom.n_loc * capacity_factor) + 1024
-        self.pot = engine.NEP(potential_file, cap)
+        self.pot = engine.Force().parse_potential(potential_file, cap)
         self.capacity = cap
         self.box = engine.Box(dom.local_h, dom.local_pbc)
         self.thermo = torch.zeros(8, dtype=torch.float64, device=dom.device)
@@ -290,7 +290,7 @@ class DomainMD:
         d.exchange()
         if d.n_loc > self.capacity:
             raise RuntimeError("local atom count exceeds the capacity of the potential instance")
-        self._lib.check(self.L.b200md_nep_invalidate(self.pot._h, d.n_loc, self._st()))
+        self.pot.invalidate(d.n_loc)
         self.steps_since_exchange = 0
 
     def maybe_exchange(self, check_every=5):

@@ -38,6 +38,16 @@ SIGNATURES = {
     "b200md_lj_symbol": (C.c_char_p, [_vp, C.c_int]),
     "b200md_lj_compute": (C.c_int, [_vp, C.c_int, _dp, _ip, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200md_lj_check": (C.c_int, [_vp, _vp]),
+    "b200md_lj_invalidate": (C.c_int, [_vp, C.c_int, _vp]),
+    "b200md_tersoff_create": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_vp)]),
+    "b200md_tersoff_destroy": (None, [_vp]),
+    "b200md_tersoff_rc": (C.c_double, [_vp]),
+    "b200md_tersoff_info": (C.c_int, [_vp, C.c_int]),
+    "b200md_tersoff_symbol": (C.c_char_p, [_vp, C.c_int]),
+    "b200md_tersoff_compute": (C.c_int, [_vp, C.c_int, _dp, _ip, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200md_tersoff_invalidate": (C.c_int, [_vp, C.c_int, _vp]),
+    "b200md_tersoff_check": (C.c_int, [_vp, _vp]),
+    "b200md_compute_heat": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "b200md_apply_pbc": (C.c_int, [C.c_int, _dp, _ip, _vp, _vp]),
     "b200md_zero_properties": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp]),
     "b200md_velocity_verlet": (C.c_int, [C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp]),

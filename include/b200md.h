@@ -104,6 +104,33 @@ int b200md_lj_compute(
   b200md_lj* p, int n, const double h[9], const int pbc[3], const int* d_type,
   const double* d_position, double* d_potential, double* d_force, double* d_virial, void* stream);
 int b200md_lj_check(b200md_lj* p, void* stream);
+int b200md_lj_invalidate(b200md_lj* p, int n_new, void* stream); /* see b200md_nep_invalidate */
+
+/* ------------------------------------------------------------------------------------------
+ * Tersoff-1989 potential, FP64.  Replaces class Tersoff1989 : Potential
+ * (src/force/tersoff1989.cuh, tersoff1989.cu:31-586):
+ *   b200md_tersoff_create  <- Tersoff1989::Tersoff1989(FILE*, int num_types, int num_atoms), :31-150
+ *                             (whole potential file: "tersoff_1989 Nt sym..." + 11 numbers per type
+ *                             [+ chi]); 1 or 2 types
+ *   b200md_tersoff_compute <- Tersoff1989::compute, :508-586 (local list + step1 + step2 +
+ *                             find_properties_many_body, potential.cu:35-134)
+ * b200md_compute_heat      <- compute_heat / gpu_compute_heat, src/measure/compute_heat.cu:32-90:
+ *                             d_heat[5 * heat_stride] = jx_in, jx_out, jy_in, jy_out, jz per atom
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b200md_tersoff b200md_tersoff;
+int b200md_tersoff_create(const char* path, int num_atoms, b200md_tersoff** out);
+void b200md_tersoff_destroy(b200md_tersoff* p);
+double b200md_tersoff_rc(const b200md_tersoff* p);
+int b200md_tersoff_info(const b200md_tersoff* p, int what); /* 0 num_types, 6 rebuild count */
+const char* b200md_tersoff_symbol(const b200md_tersoff* p, int t);
+int b200md_tersoff_compute(
+  b200md_tersoff* p, int n, const double h[9], const int pbc[3], const int* d_type,
+  const double* d_position, double* d_potential, double* d_force, double* d_virial, void* stream);
+int b200md_tersoff_invalidate(b200md_tersoff* p, int n_new, void* stream);
+int b200md_tersoff_check(b200md_tersoff* p, void* stream);
+int b200md_compute_heat(
+  int n, int stride, const double* d_virial, const double* d_velocity, double* d_heat,
+  int heat_stride, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Force::compute pre-steps (src/force/force.cu:771-801):

@@ -59,6 +59,17 @@ int oracle_lj_compute(
   int nt, const double* para, int N, const int* type, const double h[9], const int pbc[3],
   const double* position, double* pe, double* force, double* virial);
 
+/* Tersoff-1989 (1 or 2 types), all FP64 -- restates src/force/tersoff1989.cu:31-586 with the
+ * FP64 many-body reduction src/force/potential.cu:35-134.  para: per type 11 numbers
+ * a b lambda mu beta n c d h r1 r2 (file order), then chi when nt == 2. */
+int oracle_tersoff_compute(
+  int nt, const double* para, int N, const int* type, const double h[9], const int pbc[3],
+  const double* position, double* pe, double* force, double* virial);
+
+/* per-atom heat current J_i = W_i . v_i split as in gpu_compute_heat,
+ * src/measure/compute_heat.cu:32-63: heat[5N] = jx_in, jx_out, jy_in, jy_out, jz */
+void oracle_compute_heat(int N, const double* virial, const double* velocity, double* heat);
+
 /* Force::compute's pre-step, src/force/force.cu:424-459: wrap positions into the box. */
 void oracle_apply_pbc(int N, const double h[9], const int pbc[3], double* position);
 

@@ -51,6 +51,8 @@ def lib():
             _ip, _ip, C.c_int, _ip, _ip, C.c_int]
         L.oracle_neighbor_list.argtypes = [C.c_int, _dp, _ip, _dp, C.c_double, _ip, _ip, C.c_int]
         L.oracle_lj_compute.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, _ip, _dp, _dp, _dp, _dp]
+        L.oracle_tersoff_compute.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, _ip, _dp, _dp, _dp, _dp]
+        L.oracle_compute_heat.argtypes = [C.c_int, _dp, _dp, _dp]
         L.oracle_apply_pbc.argtypes = [C.c_int, _dp, _ip, _dp]
         L.oracle_velocity_verlet.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp]
         L.oracle_find_thermo.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp]
@@ -145,6 +147,37 @@ def lj_compute(para, type_, h, pbc, pos):
     if r != 0:
         raise RuntimeError(f"oracle_lj_compute failed: {r}")
     return dict(pe=pe, force=f.reshape(3, n), virial=v.reshape(9, n))
+
+
+def tersoff_parameters(path):
+    """(nt, flat parameter array) from a tersoff_1989 potential file."""
+    toks = open(path).read().split()
+    nt = int(toks[1])
+    vals = [float(v) for v in toks[2 + nt:]]
+    return nt, np.array(vals[:11 if nt == 1 else 23], dtype=np.float64)
+
+
+def tersoff_compute(nt, para, type_, h, pbc, pos):
+    L = lib()
+    n = pos.shape[1]
+    type_ = np.ascontiguousarray(type_, dtype=np.int32)
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(3 * n)
+    para = np.ascontiguousarray(para, dtype=np.float64)
+    h, pbc = _box(h, pbc)
+    pe, f, v = np.zeros(n), np.zeros(3 * n), np.zeros(9 * n)
+    r = L.oracle_tersoff_compute(nt, _d(para), n, _i(type_), _d(h), _i(pbc), _d(pos), _d(pe), _d(f), _d(v))
+    if r != 0:
+        raise RuntimeError(f"oracle_tersoff_compute failed: {r}")
+    return dict(pe=pe, force=f.reshape(3, n), virial=v.reshape(9, n))
+
+
+def compute_heat(virial, vel):
+    L = lib()
+    n = vel.shape[-1] if vel.ndim == 2 else vel.shape[0] // 3
+    heat = np.zeros(5 * n)
+    L.oracle_compute_heat(n, _d(np.ascontiguousarray(virial, np.float64).reshape(-1)),
+                          _d(np.ascontiguousarray(vel, np.float64).reshape(-1)), _d(heat))
+    return heat.reshape(5, n)
 
 
 def apply_pbc(h, pbc, pos):

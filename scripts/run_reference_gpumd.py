@@ -85,6 +85,11 @@ def main():
     d, i = run_case("sp_lj", s, ["Ar"], GOLDEN / "lj_Ar_10A.txt", sp)
     collect_single_point(d, s, ["Ar"]); infos.append(i)
 
+    from gpumd_b200.structures import diamond
+    s = diamond(10, a=5.431, rattle=0.08, seed=24)  # 8000 Si atoms, 54.3 A
+    d, i = run_case("sp_si", s, ["Si"], GOLDEN / "tersoff_Si_1989.txt", sp)
+    collect_single_point(d, s, ["Si"]); infos.append(i)
+
     # ---- (2) NVE trajectories from given velocities: thermo.out every 10 steps ----
     md = "ensemble nve\ntime_step {dt}\ndump_thermo 10\nrun {steps}\n"
     s = rocksalt_pbte(20, rattle=0.02, seed=1)  # 64 000 atoms
@@ -94,6 +99,11 @@ def main():
     s = fcc(25, 5.30, rattle=0.0, seed=1)  # 62 500 atoms
     vel = init_velocities(s["mass"], 80.0, seed=42)
     d, i = run_case("md_lj", s, ["Ar"], GOLDEN / "lj_Ar_10A.txt", md.format(dt=5, steps=200), vel)
+    infos.append(i)
+
+    s = diamond(20, a=5.431, rattle=0.0, seed=1)  # 64 000 Si atoms
+    vel = init_velocities(s["mass"], 300.0, seed=42)
+    d, i = run_case("md_si", s, ["Si"], GOLDEN / "tersoff_Si_1989.txt", md.format(dt=1, steps=200), vel)
     infos.append(i)
 
     # NVT from the same start: Nose-Hoover chain and Berendsen (deterministic thermostats)
@@ -115,6 +125,17 @@ def main():
         vel = init_velocities(s["mass"], 80.0, seed=42)
         d, i = run_case("speed_lj_1m", s, ["Ar"], GOLDEN / "lj_Ar_10A.txt",
                         "ensemble nve\ntime_step 5\ndump_thermo 100\nrun 200\n", vel, timeout=1500)
+        infos.append(i)
+        s = diamond(63, a=5.431, rattle=0.0, seed=1)  # C5: 2 000 376 Si atoms
+        vel = init_velocities(s["mass"], 300.0, seed=42)
+        d, i = run_case("speed_si_2m", s, ["Si"], GOLDEN / "tersoff_Si_1989.txt",
+                        "ensemble nve\ntime_step 1\ndump_thermo 100\nrun 200\n", vel, timeout=1500)
+        infos.append(i)
+        s = fcc(63, 3.9, rattle=0.0, seed=7, num_types=16, symbols=unep_sym)  # C4 per-GPU share: 1 000 188 atoms
+        vel = init_velocities(s["mass"], 300.0, seed=42)
+        d, i = run_case("speed_unep_1m", s, unep_sym, GOLDEN / "nep_UNEP_v1.txt",
+                        "ensemble nvt_ber 300 300 100\ntime_step 1\ndump_thermo 100\nrun 100\n", vel,
+                        timeout=1500)
         infos.append(i)
     (OUT / "summary.json").write_text(json.dumps(infos, indent=1))
     print(json.dumps(infos, indent=1))

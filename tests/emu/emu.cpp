@@ -13,6 +13,7 @@
 #include "../../gpumd_b200/csrc/b2_neighbor.cuh"
 #include "../../gpumd_b200/csrc/b2_nep.cuh"
 #include "../../gpumd_b200/csrc/b2_nep_model.h"
+#include "../../gpumd_b200/csrc/b2_tersoff.cuh"
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -422,6 +423,91 @@ int emu_lj_compute(
   for (int i = 0; i < n; ++i)
     b2_body_unpack(i, n, p->nb.perm.data(), p->acc.data(), pe, force, virial);
   return p->nb.flags[1] ? 5 : 0;
+}
+
+// ---- Tersoff --------------------------------------------------------------------------------
+struct emu_tersoff {
+  int nt, n;
+  double rc;
+  B2TersoffView P;
+  EmuNeighbor nb;
+  std::vector<int> nn, nl;
+  std::vector<double> f12, acc;
+};
+
+static void ters_fill(B2TersoffPara& t, const double* p)
+{
+  t.a = p[0]; t.b = p[1]; t.lambda = p[2]; t.mu = p[3]; t.beta = p[4]; t.n = p[5];
+  t.c2 = p[6] * p[6]; t.d2 = p[7] * p[7]; t.h = p[8]; t.r1 = p[9]; t.r2 = p[10];
+  t.one_plus = 1.0 + t.c2 / t.d2;
+  t.pi_factor = 3.14159265358979 / (t.r2 - t.r1);
+  t.mhn = -0.5 / p[5];
+}
+
+emu_tersoff* emu_tersoff_create(int nt, const double* para, int n)
+{
+  emu_tersoff* p = new emu_tersoff;
+  p->nt = nt;
+  p->n = n;
+  B2TersoffView& P = p->P;
+  std::memset(&P, 0, sizeof P);
+  ters_fill(P.p[0], para);
+  p->rc = P.p[0].r2;
+  if (nt == 2) {
+    ters_fill(P.p[1], para + 11);
+    B2TersoffPara& m = P.p[2];
+    m.a = std::sqrt(P.p[0].a * P.p[1].a);
+    m.b = std::sqrt(P.p[0].b * P.p[1].b) * para[22];
+    m.lambda = 0.5 * (P.p[0].lambda + P.p[1].lambda);
+    m.mu = 0.5 * (P.p[0].mu + P.p[1].mu);
+    m.r1 = std::sqrt(P.p[0].r1 * P.p[1].r1);
+    m.r2 = std::sqrt(P.p[0].r2 * P.p[1].r2);
+    m.pi_factor = 3.14159265358979 / (m.r2 - m.r1);
+    p->rc = P.p[0].r2 > P.p[1].r2 ? P.p[0].r2 : P.p[1].r2;
+  } else {
+    P.p[1] = P.p[0];
+    P.p[2] = P.p[0];
+  }
+  P.rc2 = (float)(p->rc * p->rc);
+  const double rs = p->rc + 1.0;
+  p->nb.init(n, p->rc, (int)(50 * rs * rs * rs / (p->rc * p->rc * p->rc)));
+  p->nn.resize(n);
+  p->nl.resize((size_t)n * B2_TERSOFF_MAXL);
+  p->f12.resize((size_t)3 * n * B2_TERSOFF_MAXL);
+  p->acc.resize((size_t)13 * n);
+  return p;
+}
+void emu_tersoff_destroy(emu_tersoff* p) { delete p; }
+int emu_tersoff_compute(
+  emu_tersoff* p, int n, const double h[9], const int pbc[3], const int* type, const double* pos,
+  double* pe, double* force, double* virial)
+{
+  const B2Box box = make_box(h, pbc);
+  const int rc = p->nb.update(box, type, pos);
+  if (rc)
+    return rc;
+  B2TersoffView& P = p->P;
+  P.n = n;
+  P.atoms = p->nb.atoms.data();
+  P.nn_skin = p->nb.nn_skin.data();
+  P.nl_skin = p->nb.nl_skin.data();
+  P.nn = p->nn.data();
+  P.nl = p->nl.data();
+  P.f12 = p->f12.data();
+  P.acc = p->acc.data();
+  P.flags = p->nb.flags.data();
+  for (int i = 0; i < n; ++i)
+    b2_body_tersoff_partial(i, P, box);
+  for (int i = 0; i < n; ++i)
+    b2_body_tersoff_reduce(i, P, box);
+  for (int i = 0; i < n; ++i)
+    b2_body_unpack(i, n, p->nb.perm.data(), p->acc.data(), pe, force, virial);
+  return p->nb.flags[1] ? 5 : 0;
+}
+void emu_compute_heat(int n, const double* w, const double* v, double* heat)
+{
+  for (int i = 0; i < n; ++i)
+    b2_body_heat(i, n, w, v, heat, n);
 }
 
 // ---- integrate ------------------------------------------------------------------------------

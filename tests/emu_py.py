@@ -87,6 +87,29 @@ class EmuLj:
         return rc, dict(pe=pe, force=f.reshape(3, n), virial=v.reshape(9, n))
 
 
+class EmuTersoff:
+    def __init__(self, E, nt, para, n):
+        self.E = E
+        self.n = n
+        para = np.ascontiguousarray(para, np.float64)
+        self.h = E.emu_tersoff_create(nt, _d(para), n)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.E.emu_tersoff_destroy(self.h)
+            self.h = None
+
+    def compute(self, type_, h, pbc, pos):
+        n = self.n
+        pe, f, v = np.zeros(n), np.zeros(3 * n), np.zeros(9 * n)
+        ty = np.ascontiguousarray(type_, np.int32)
+        p = np.ascontiguousarray(pos, np.float64).reshape(-1)
+        hh = np.ascontiguousarray(h, np.float64).reshape(9)
+        pb = np.ascontiguousarray(pbc, np.int32)
+        rc = self.E.emu_tersoff_compute(self.h, n, _d(hh), _i(pb), _i(ty), _d(p), _d(pe), _d(f), _d(v))
+        return rc, dict(pe=pe, force=f.reshape(3, n), virial=v.reshape(9, n))
+
+
 class Emu:
     def __init__(self, path):
         E = C.CDLL(path)
@@ -103,6 +126,11 @@ class Emu:
         E.emu_lj_create.argtypes = [C.c_int, _dp, C.c_int]
         E.emu_lj_destroy.argtypes = [C.c_void_p]
         E.emu_lj_compute.argtypes = [C.c_void_p, C.c_int, _dp, _ip, _ip, _dp, _dp, _dp, _dp]
+        E.emu_tersoff_create.restype = C.c_void_p
+        E.emu_tersoff_create.argtypes = [C.c_int, _dp, C.c_int]
+        E.emu_tersoff_destroy.argtypes = [C.c_void_p]
+        E.emu_tersoff_compute.argtypes = [C.c_void_p, C.c_int, _dp, _ip, _ip, _dp, _dp, _dp, _dp]
+        E.emu_compute_heat.argtypes = [C.c_int, _dp, _dp, _dp]
         E.emu_apply_pbc.argtypes = [C.c_int, _dp, _ip, _dp]
         E.emu_velocity_verlet.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp]
         E.emu_find_thermo.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp]
@@ -113,6 +141,16 @@ class Emu:
 
     def lj(self, para, n):
         return EmuLj(self.E, para, n)
+
+    def tersoff(self, nt, para, n):
+        return EmuTersoff(self.E, nt, para, n)
+
+    def compute_heat(self, virial, vel):
+        n = vel.shape[1]
+        heat = np.zeros(5 * n)
+        self.E.emu_compute_heat(n, _d(np.ascontiguousarray(virial, np.float64).reshape(-1)),
+                                _d(np.ascontiguousarray(vel, np.float64).reshape(-1)), _d(heat))
+        return heat.reshape(5, n)
 
     def apply_pbc(self, h, pbc, pos):
         n = pos.shape[1]

@@ -236,6 +236,54 @@ def test_integrator_kernels(oracle, eng):
     assert np.array_equal(a, thermo.cpu().numpy())  # deterministic reduction order
 
 
+@pytest.mark.parametrize("two_types", [False, True])
+def test_tersoff_matches_oracle(oracle, eng, two_types, tmp_path):
+    import torch
+    from gpumd_b200.structures import diamond
+    _, p0 = oracle.tersoff_parameters(GOLDEN / "tersoff_Si_1989.txt")
+    s = diamond(6, a=5.431, rattle=0.08, seed=12)  # 1728 atoms
+    n = s["type"].shape[0]
+    if two_types:
+        p1 = p0 * np.array([1.05, 0.97, 1.02, 0.98, 1.0, 1.0, 1.0, 1.0, 1.0, 0.98, 0.99])
+        nt, para = 2, np.concatenate([p0, p1, [0.9776]])
+        types = (np.arange(n) % 2).astype(np.int32)
+        f = tmp_path / "t2.txt"
+        f.write_text("tersoff_1989 2 Si Ge\n" + " ".join(f"{v:.17g}" for v in p0) + "\n" +
+                     " ".join(f"{v:.17g}" for v in p1) + "\n0.9776\n")
+    else:
+        nt, para, types, f = 1, p0, s["type"], GOLDEN / "tersoff_Si_1989.txt"
+    r = oracle.tersoff_compute(nt, para, types, s["h"], s["pbc"], s["pos"])
+    pot = eng.Tersoff1989(f, n)
+    atom = eng.Atom(types, s["pos"], s["mass"], np.random.default_rng(3).normal(size=(3, n)))
+    pot.compute(eng.Box(s["h"], s["pbc"]), atom.type, atom.position_per_atom,
+                atom.potential_per_atom, atom.force_per_atom, atom.virial_per_atom)
+    pot.check()
+    assert_close(atom.potential_per_atom.cpu().numpy(), r["pe"], rtol=1e-10, atol=1e-11, what="pe")
+    assert_close(atom.force_per_atom.cpu().numpy().reshape(3, n), r["force"], rtol=1e-9, atol=1e-10,
+                 what="force")
+    vir = atom.virial_per_atom.cpu().numpy().reshape(9, n)
+    assert_close(vir, r["virial"], rtol=1e-9, atol=1e-10, what="virial")
+    heat = eng.compute_heat(atom).cpu().numpy().reshape(5, n)
+    assert np.allclose(heat, oracle.compute_heat(vir, atom.velocity_per_atom.cpu().numpy().reshape(3, n)),
+                       rtol=1e-13, atol=0)
+
+
+def test_tersoff_matches_reference_gpu_single_point(eng):
+    path = GOLDEN / "refgpu_sp_si.npz"
+    if not path.exists():
+        pytest.skip("reference-GPU Si fixture not generated yet")
+    d = np.load(path)
+    n = d["type"].shape[0]
+    pot = eng.Tersoff1989(GOLDEN / "tersoff_Si_1989.txt", n)
+    atom = eng.Atom(d["type"], d["pos"], np.full(n, 28.085))
+    pot.compute(eng.Box(d["h"], d["pbc"]), atom.type, atom.position_per_atom,
+                atom.potential_per_atom, atom.force_per_atom, atom.virial_per_atom)
+    pot.check()
+    assert abs(atom.potential_per_atom.sum().item() - float(d["energy"])) < 1e-9 * abs(float(d["energy"]))
+    assert_close(atom.force_per_atom.cpu().numpy().reshape(3, n), d["force"], rtol=1e-9, atol=1e-9,
+                 what="force")
+
+
 def test_thermostat_factors(oracle, eng):
     """Berendsen and Nose-Hoover-chain velocity scaling: device-side factors vs the host maths of
     the reference (oracle.berendsen_factor / oracle.nhc_chain), several consecutive half steps."""
