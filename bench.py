@@ -46,9 +46,11 @@ def stage_algorithmic_bytes(nn, model):
     return {
         "k_split": 36 + 4 * (Ng + Nr + Na),
         "descriptor+MLP": 52 + 4 * (Nr + Na) + 4 * D + 4 * S,
-        "k_force_radial": 32 + 4 * Nr + 4 * Dr + 192,
+        # fused radial force + angular pair reduction + scatter: the radial-force stage
+        # (32+4Nr+4Dr+192) plus the list and f12 reads of the pair reduction (16 Na); the second
+        # 192-byte force/virial RMW and 28-byte per-atom read of the separate stage are gone
+        "k_force_final": 32 + 4 * Nr + 4 * Dr + 192 + 16 * Na,
         "k_force_angular": 32 + 4 * Na + 4 * Da + 4 * S + 12 * Na,
-        "k_reduce_angular": 28 + 16 * Na + 192,
         "VV1": 128, "PBC": 48, "zero": 104, "displacement_check": 48, "VV2": 80, "thermo": 88,
     }
 

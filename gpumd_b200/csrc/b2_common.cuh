@@ -209,6 +209,16 @@ B2_HD void b2_sincospi(float x, float& s, float& c)
 #endif
 }
 
+// 1/sqrt(x): hardware approximation (<= 2 ulp) on the device
+B2_HD float b2_rsqrt(float x)
+{
+#if defined(__CUDA_ARCH__)
+  return rsqrtf(x);
+#else
+  return 1.0f / sqrtf(x);
+#endif
+}
+
 B2_HD float b2_cospi(float x)
 {
 #if defined(__CUDA_ARCH__)

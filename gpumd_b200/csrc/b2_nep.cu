@@ -108,11 +108,12 @@ __global__ void __launch_bounds__(BLK) k_utable(B2NepView P)
 }
 
 template <int NT, int K1>
-__global__ void __launch_bounds__(BLK) k_force_radial(B2NepView P, B2Box box)
+__global__ void __launch_bounds__(BLK)
+  k_force_final(B2NepView P, B2Box box, double* pe, double* force, double* virial)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < P.n)
-    b2_body_force_radial<NT, K1>(i, P, box);
+    b2_body_force_final<NT, K1>(i, P, box, pe, force, virial);
 }
 
 template <int K1>
@@ -122,29 +123,6 @@ __global__ void __launch_bounds__(BLK) k_force_angular(B2NepView P, B2Box box)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < P.n)
     b2_body_force_angular<K1>(i, P, box, dyn_smem, blockDim.x, threadIdx.x);
-}
-
-__global__ void __launch_bounds__(BLK) k_reduce_angular(B2NepView P, B2Box box)
-{
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < P.n)
-    b2_body_reduce_angular(i, P, box);
-}
-
-__global__ void __launch_bounds__(BLK) k_zbl(B2NepView P, B2Box box)
-{
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < P.n)
-    b2_body_zbl(i, P, box);
-}
-
-__global__ void __launch_bounds__(256) k_unpack(
-  int n, const int* __restrict__ perm, const double* __restrict__ acc, double* pe, double* force,
-  double* virial)
-{
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n)
-    b2_body_unpack(i, n, perm, acc, pe, force, virial);
 }
 
 // parity hooks ---------------------------------------------------------------------------------
@@ -244,20 +222,22 @@ int dispatch_desc_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
 }
 
 template <int NT, int K1>
-int launch_force_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
+int launch_force_final(
+  const b200md_nep* p, const B2Box& box, cudaStream_t st, double* pe, double* f, double* v)
 {
-  k_force_radial<NT, K1><<<grid_for(p->n, BLK), BLK, 0, st>>>(p->view, box);
+  k_force_final<NT, K1><<<grid_for(p->n, BLK), BLK, 0, st>>>(p->view, box, pe, f, v);
   B2_LAUNCHED();
   return B200MD_OK;
 }
 
 template <int K1>
-int dispatch_force_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
+int dispatch_force_final(
+  const b200md_nep* p, const B2Box& box, cudaStream_t st, double* pe, double* f, double* v)
 {
   switch (p->model.nt) {
-    case 1: return launch_force_radial<1, K1>(p, box, st);
-    case 2: return launch_force_radial<2, K1>(p, box, st);
-    default: return launch_force_radial<0, K1>(p, box, st);
+    case 1: return launch_force_final<1, K1>(p, box, st, pe, f, v);
+    case 2: return launch_force_final<2, K1>(p, box, st, pe, f, v);
+    default: return launch_force_final<0, K1>(p, box, st, pe, f, v);
   }
 }
 
@@ -302,13 +282,13 @@ int launch_mlp(const b200md_nep* p, cudaStream_t st)
   } while (0)
 
 // stage ids reported by b200md_nep_profile_read / b200md_nep_stage_name
-enum { ST_NEIGHBOR, ST_SPLIT, ST_DESC_R, ST_DESC_A, ST_MLP, ST_FORCE_R, ST_FORCE_A, ST_REDUCE_A,
-       ST_ZBL, ST_UNPACK, ST_COUNT };
+enum { ST_NEIGHBOR, ST_SPLIT, ST_DESC_R, ST_DESC_A, ST_MLP, ST_FORCE_A, ST_FORCE_FINAL, ST_COUNT };
 const char* const STAGE_NAMES[ST_COUNT] = {
-  "neighbor_update", "k_split", "k_desc_radial", "k_desc_angular", "k_mlp", "k_force_radial",
-  "k_force_angular", "k_reduce_angular", "k_zbl", "k_unpack"};
+  "neighbor_update", "k_split", "k_desc_radial", "k_desc_angular", "k_mlp", "k_force_angular",
+  "k_force_final"};
 
-int nep_pipeline(b200md_nep* p, const B2Box& box, cudaStream_t st)
+int nep_pipeline(
+  b200md_nep* p, const B2Box& box, cudaStream_t st, double* d_pe, double* d_force, double* d_virial)
 {
   const int n = p->n;
   StageProfiler& pf = p->prof;
@@ -348,13 +328,6 @@ int nep_pipeline(b200md_nep* p, const B2Box& box, cudaStream_t st)
   }
   B2_LAUNCHED();
   pf.end(st, ST_MLP);
-  pf.begin(st, ST_FORCE_R);
-  switch (p->model.K1R) {
-    case 9: B2_TRY(dispatch_force_radial<9>(p, box, st)); break;
-    case 13: B2_TRY(dispatch_force_radial<13>(p, box, st)); break;
-    default: B2_TRY(dispatch_force_radial<17>(p, box, st)); break;
-  }
-  pf.end(st, ST_FORCE_R);
   pf.begin(st, ST_FORCE_A);
   switch (p->model.K1A) {
     case 9: B2_TRY(launch_angular<9>(p, box, st, true)); break;
@@ -362,16 +335,13 @@ int nep_pipeline(b200md_nep* p, const B2Box& box, cudaStream_t st)
     default: B2_TRY(launch_angular<17>(p, box, st, true)); break;
   }
   pf.end(st, ST_FORCE_A);
-  pf.begin(st, ST_REDUCE_A);
-  k_reduce_angular<<<grid_for(n, BLK), BLK, 0, st>>>(p->view, box);
-  B2_LAUNCHED();
-  pf.end(st, ST_REDUCE_A);
-  if (p->model.zbl_enabled) {
-    pf.begin(st, ST_ZBL);
-    k_zbl<<<grid_for(n, BLK), BLK, 0, st>>>(p->view, box);
-    B2_LAUNCHED();
-    pf.end(st, ST_ZBL);
+  pf.begin(st, ST_FORCE_FINAL);
+  switch (p->model.K1R) {
+    case 9: B2_TRY(dispatch_force_final<9>(p, box, st, d_pe, d_force, d_virial)); break;
+    case 13: B2_TRY(dispatch_force_final<13>(p, box, st, d_pe, d_force, d_virial)); break;
+    default: B2_TRY(dispatch_force_final<17>(p, box, st, d_pe, d_force, d_virial)); break;
   }
+  pf.end(st, ST_FORCE_FINAL);
   return B200MD_OK;
 }
 
@@ -414,7 +384,7 @@ int nep_setup(b200md_nep* p, int num_atoms)
   B2_CUDA(p->FpA.reserve(N * m.dim_angular));
   B2_CUDA(p->U.reserve(N * m.UST));
   B2_CUDA(p->f12.reserve(N * 3 * m.MN_angular));
-  B2_CUDA(p->acc.reserve(N * 13));
+  B2_CUDA(p->acc.reserve(N)); // site energies from the MLP pass
 
   B2NepView& P = p->view;
   std::memset(&P, 0, sizeof P);
@@ -567,12 +537,7 @@ int b200md_nep_compute(
   p->n = n; // n may be anything up to the capacity given at construction (domain decomposition)
   p->view.n = n;
   p->prof.end(st, ST_NEIGHBOR);
-  B2_TRY(nep_pipeline(p, box, st));
-  p->prof.begin(st, ST_UNPACK);
-  k_unpack<<<grid_for(n, 256), 256, 0, st>>>(
-    n, p->nb.perm.p, p->acc.p, d_potential, d_force, d_virial);
-  B2_LAUNCHED();
-  p->prof.end(st, ST_UNPACK);
+  B2_TRY(nep_pipeline(p, box, st, d_potential, d_force, d_virial));
   return B200MD_OK;
 }
 

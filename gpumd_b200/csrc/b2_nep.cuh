@@ -551,8 +551,9 @@ B2_HD void b2_body_utable(int i, const B2NepView& P)
 //   F_i   += (A + B) * r12 / d,   A = fn'(d) . U_i[t_j],  B = fn'(d) . U_j[t_i]
 //   W_i^ab += r12^a * f21^b,      f21 = -B * r12 / d
 // ---------------------------------------------------------------------------------------------
+// out[12] = fx,fy,fz, vxx,vyy,vzz,vxy,vxz,vyz,vyx,vzx,vzy (FP32 partial sums of this stage)
 template <int NT, int K1>
-B2_HD void b2_body_force_radial(int i, const B2NepView& P, const B2Box& box)
+B2_HD void b2_force_radial_sum(int i, const B2NepView& P, const B2Box& box, float* out)
 {
   constexpr int KP4 = (K1 + 3) / 4; // float4 loads per U row (KP = 4*KP4)
   const B2Geo geo = b2_geo(box);
@@ -562,12 +563,17 @@ B2_HD void b2_body_force_radial(int i, const B2NepView& P, const B2Box& box)
   const int nn = P.nn_r[i];
   const float* Ui = P.U + (size_t)i * P.UST;
   float Ur[NT > 0 ? NT : 1][K1];
+  float rcv[NT > 0 ? NT : 1], rciv[NT > 0 ? NT : 1]; // pair cutoffs of (t1, t) for the few-type path
   if (NT > 0) {
 #pragma unroll
-    for (int t = 0; t < (NT > 0 ? NT : 1); ++t)
+    for (int t = 0; t < (NT > 0 ? NT : 1); ++t) {
+      const int pr = t1 * P.nt + (t < P.nt ? t : 0);
+      rcv[t] = B2_LDG(&P.rc_r[pr]);
+      rciv[t] = B2_LDG(&P.rcinv_r[pr]);
 #pragma unroll
       for (int k = 0; k < K1; ++k)
         Ur[t][k] = (t < P.nt) ? Ui[t * P.KP + k] : 0.0f;
+    }
   }
   float fx = 0.0f, fy = 0.0f, fz = 0.0f;
   float vxx = 0.0f, vyy = 0.0f, vzz = 0.0f, vxy = 0.0f, vxz = 0.0f, vyz = 0.0f;
@@ -600,12 +606,29 @@ B2_HD void b2_body_force_radial(int i, const B2NepView& P, const B2Box& box)
 
     float x12, y12, z12;
     b2_r12(geo, box, a1, a2, x12, y12, z12);
-    const float d = sqrtf(b2_d2(x12, y12, z12));
-    const float dinv = 1.0f / d;
+    const float d2 = b2_d2(x12, y12, z12);
+    const float dinv = b2_rsqrt(d2);
+    const float d = d2 * dinv;
     const int t2 = a2.type;
-    const int pair = t1 * P.nt + t2;
+    float rc, rcinv;
+    if (NT == 1) {
+      rc = rcv[0];
+      rcinv = rciv[0];
+    } else if (NT > 1) {
+      rc = rcv[0];
+      rcinv = rciv[0];
+#pragma unroll
+      for (int t = 1; t < (NT > 0 ? NT : 1); ++t) {
+        rc = (t2 == t) ? rcv[t] : rc;
+        rcinv = (t2 == t) ? rciv[t] : rcinv;
+      }
+    } else {
+      const int pair = t1 * P.nt + t2;
+      rc = B2_LDG(&P.rc_r[pair]);
+      rcinv = B2_LDG(&P.rcinv_r[pair]);
+    }
     float fnp[K1];
-    b2_basis_d<K1, false>(d, B2_LDG(&P.rc_r[pair]), B2_LDG(&P.rcinv_r[pair]), nullptr, fnp);
+    b2_basis_d<K1, false>(d, rc, rcinv, nullptr, fnp);
     float A = 0.0f, Bv = 0.0f;
     if (NT == 1) {
 #pragma unroll
@@ -641,19 +664,18 @@ B2_HD void b2_body_force_radial(int i, const B2NepView& P, const B2Box& box)
     vxz = fmaf(x12 * z12, sB, vxz);
     vyz = fmaf(y12 * z12, sB, vyz);
   }
-  double* a = P.acc + i;
-  a[1 * N] = fx;
-  a[2 * N] = fy;
-  a[3 * N] = fz;
-  a[4 * N] = vxx;
-  a[5 * N] = vyy;
-  a[6 * N] = vzz;
-  a[7 * N] = vxy;
-  a[8 * N] = vxz;
-  a[9 * N] = vyz;
-  a[10 * N] = vxy; // yx: the radial pair virial r12 (x) f21 is symmetric
-  a[11 * N] = vxz; // zx
-  a[12 * N] = vyz; // zy
+  out[0] = fx;
+  out[1] = fy;
+  out[2] = fz;
+  out[3] = vxx;
+  out[4] = vyy;
+  out[5] = vzz;
+  out[6] = vxy;
+  out[7] = vxz;
+  out[8] = vyz;
+  out[9] = vxy; // yx: the radial pair virial r12 (x) f21 is symmetric
+  out[10] = vxz; // zx
+  out[11] = vyz; // zy
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -782,7 +804,7 @@ B2_HD void b2_body_force_angular(
 // (gpu_find_force_many_body, src/force/potential.cu:170-297; the reverse slot is found by binary
 // search in j's ascending list, potential.cu:226-247)
 // ---------------------------------------------------------------------------------------------
-B2_HD void b2_body_reduce_angular(int i, const B2NepView& P, const B2Box& box)
+B2_HD void b2_reduce_angular_sum(int i, const B2NepView& P, const B2Box& box, float* out)
 {
   const size_t N = (size_t)P.n;
   const size_t plane = (size_t)P.mn_a * N;
@@ -821,19 +843,18 @@ B2_HD void b2_body_reduce_angular(int i, const B2NepView& P, const B2Box& box)
         v[a * 3 + b] = fmaf(r[a], f21[b], v[a * 3 + b]);
     }
   }
-  double* a = P.acc + i;
-  a[1 * N] += f[0];
-  a[2 * N] += f[1];
-  a[3 * N] += f[2];
-  a[4 * N] += v[0];  // xx
-  a[5 * N] += v[4];  // yy
-  a[6 * N] += v[8];  // zz
-  a[7 * N] += v[1];  // xy
-  a[8 * N] += v[2];  // xz
-  a[9 * N] += v[5];  // yz
-  a[10 * N] += v[3]; // yx
-  a[11 * N] += v[6]; // zx
-  a[12 * N] += v[7]; // zy
+  out[0] = f[0];
+  out[1] = f[1];
+  out[2] = f[2];
+  out[3] = v[0];  // xx
+  out[4] = v[4];  // yy
+  out[5] = v[8];  // zz
+  out[6] = v[1];  // xy
+  out[7] = v[2];  // xz
+  out[8] = v[5];  // yz
+  out[9] = v[3];  // yx
+  out[10] = v[6]; // zx
+  out[11] = v[7]; // zy
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -872,7 +893,7 @@ B2_HD void b2_zbl_pair(
   f = phi * fc;
 }
 
-B2_HD void b2_body_zbl(int i, const B2NepView& P, const B2Box& box)
+B2_HD void b2_zbl_sum(int i, const B2NepView& P, const B2Box& box, float* out, float& pe_out)
 {
   const size_t N = (size_t)P.n;
   const B2Geo geo = b2_geo(box);
@@ -927,20 +948,51 @@ B2_HD void b2_body_zbl(int i, const B2NepView& P, const B2Box& box)
     vyz -= y12 * (z12 * f2);
     pe += fv * 0.5f;
   }
-  double* a = P.acc + i;
-  a[0] += pe;
-  a[1 * N] += f[0];
-  a[2 * N] += f[1];
-  a[3 * N] += f[2];
-  a[4 * N] += vxx;
-  a[5 * N] += vyy;
-  a[6 * N] += vzz;
-  a[7 * N] += vxy;
-  a[8 * N] += vxz;
-  a[9 * N] += vyz;
-  a[10 * N] += vxy;
-  a[11 * N] += vxz;
-  a[12 * N] += vyz;
+  pe_out = pe;
+  out[0] = f[0];
+  out[1] = f[1];
+  out[2] = f[2];
+  out[3] = vxx;
+  out[4] = vyy;
+  out[5] = vzz;
+  out[6] = vxy;
+  out[7] = vxz;
+  out[8] = vyz;
+  out[9] = vxy;
+  out[10] = vxz;
+  out[11] = vyz;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Final force kernel: radial pair forces + angular pair reduction (+ ZBL) for one atom, then ONE
+// scatter into the caller's FP64 arrays with += (the accumulate convention of Potential::compute,
+// nep.cu:653,755-770).  Each stage keeps its own FP32 partial sums and they are combined in FP64,
+// exactly like the reference's separate kernels adding into double arrays.
+// ---------------------------------------------------------------------------------------------
+template <int NT, int K1>
+B2_HD void b2_body_force_final(
+  int i, const B2NepView& P, const B2Box& box, double* pe, double* force, double* virial)
+{
+  float r[12], a[12], z[12];
+  float zpe = 0.0f;
+  b2_force_radial_sum<NT, K1>(i, P, box, r);
+  b2_reduce_angular_sum(i, P, box, a);
+  if (P.zbl_enabled) {
+    b2_zbl_sum(i, P, box, z, zpe);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      z[k] = 0.0f;
+  }
+  const int dst = P.perm[i];
+  const size_t N = (size_t)P.n;
+  pe[dst] += P.acc[i] + (double)zpe; // acc[i] = site energy from the MLP pass
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+    force[k * N + dst] += (double)r[k] + (double)a[k] + (double)z[k];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+    virial[k * N + dst] += (double)r[3 + k] + (double)a[3 + k] + (double)z[3 + k];
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -245,6 +245,42 @@ class Tersoff1989(Potential):
         return self._L.b200md_tersoff_info(self._h, 6)
 
 
+class EAM(Potential):
+    """Analytic EAM (eam_zhou_2004 / eam_dai_2006), src/force/eam.cu:28-580."""
+
+    def __init__(self, file_potential, num_atoms):
+        _require_cuda()
+        self._L = _lib.load()
+        h = C.c_void_p()
+        _lib.check(self._L.b200md_eam_create(str(file_potential).encode(), int(num_atoms), C.byref(h)))
+        self._h = h
+        self.N1, self.N2 = 0, int(num_atoms)
+        self.rc = self._L.b200md_eam_rc(h)
+        self.num_types = self._L.b200md_eam_info(h, 0)
+        self.symbols = [self._L.b200md_eam_symbol(h, t).decode() for t in range(self.num_types)]
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.b200md_eam_destroy(self._h)
+            self._h = None
+
+    def compute(self, box, type_, position, potential, force, virial):
+        n = type_.shape[0]
+        _lib.check(self._L.b200md_eam_compute(
+            self._h, n, box._h, box._p, _ptr(type_), _ptr(position), _ptr(potential), _ptr(force),
+            _ptr(virial), _stream()))
+
+    def check(self):
+        _lib.check(self._L.b200md_eam_check(self._h, _stream()))
+
+    def invalidate(self, n_new):
+        _lib.check(self._L.b200md_eam_invalidate(self._h, int(n_new), _stream()))
+
+    @property
+    def num_rebuilds(self):
+        return self._L.b200md_eam_info(self._h, 6)
+
+
 def compute_heat(atom, heat=None):
     """Per-atom heat current (compute_heat, src/measure/compute_heat.cu:66-90): heat[5N]."""
     n = atom.number_of_atoms
@@ -271,6 +307,8 @@ class Force:
             pot = LJ(file_potential, num_atoms)
         elif first == "tersoff_1989":
             pot = Tersoff1989(file_potential, num_atoms)
+        elif first in ("eam_zhou_2004", "eam_dai_2006"):
+            pot = EAM(file_potential, num_atoms)
         else:
             raise _lib.B200mdError(f"illegal potential model '{first}' for gpumd_b200")
         self.potentials = [pot]

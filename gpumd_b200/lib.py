@@ -47,6 +47,14 @@ SIGNATURES = {
     "b200md_tersoff_compute": (C.c_int, [_vp, C.c_int, _dp, _ip, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200md_tersoff_invalidate": (C.c_int, [_vp, C.c_int, _vp]),
     "b200md_tersoff_check": (C.c_int, [_vp, _vp]),
+    "b200md_eam_create": (C.c_int, [C.c_char_p, C.c_int, C.POINTER(_vp)]),
+    "b200md_eam_destroy": (None, [_vp]),
+    "b200md_eam_rc": (C.c_double, [_vp]),
+    "b200md_eam_info": (C.c_int, [_vp, C.c_int]),
+    "b200md_eam_symbol": (C.c_char_p, [_vp, C.c_int]),
+    "b200md_eam_compute": (C.c_int, [_vp, C.c_int, _dp, _ip, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "b200md_eam_invalidate": (C.c_int, [_vp, C.c_int, _vp]),
+    "b200md_eam_check": (C.c_int, [_vp, _vp]),
     "b200md_compute_heat": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "b200md_apply_pbc": (C.c_int, [C.c_int, _dp, _ip, _vp, _vp]),
     "b200md_zero_properties": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp]),

@@ -14,7 +14,7 @@ K_B = 8.617343e-5           # eV/K, src/utilities/common.cuh:21
 TIME_UNIT_CONVERSION = 1.018051e+1  # fs per natural time unit, common.cuh:26
 
 MASS = {  # subset of MASS_TABLE, src/model/read_xyz.cu:36-142 (amu)
-    "H": 1.008, "C": 12.011, "O": 15.999, "Al": 26.9815385, "Si": 28.085, "Ar": 39.948,
+    "H": 1.008, "C": 12.011, "Fe": 55.845, "Co": 58.933, "Ge": 72.63, "O": 15.999, "Al": 26.9815385, "Si": 28.085, "Ar": 39.948,
     "Ti": 47.867, "V": 50.9415, "Cr": 51.9961, "Ni": 58.6934, "Cu": 63.546, "Zr": 91.224,
     "Mo": 95.95, "Pd": 106.42, "Ag": 107.8682, "Te": 127.6, "Ba": 137.327, "Ta": 180.94788,
     "W": 183.84, "Pt": 195.084, "Au": 196.966569, "Pb": 207.2, "Mg": 24.305,

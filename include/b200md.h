@@ -133,6 +133,24 @@ int b200md_compute_heat(
   int heat_stride, void* stream);
 
 /* ------------------------------------------------------------------------------------------
+ * Analytic EAM potentials.  Replaces class EAM : Potential (src/force/eam.cuh:20-90, eam.cu:28-580)
+ * for `eam_zhou_2004` (1..18 types) and `eam_dai_2006` (1 type):
+ *   b200md_eam_create  <- EAM::EAM(FILE*, char* name, int num_types, int num_atoms), eam.cu:28-44
+ *   b200md_eam_compute <- EAM::compute, eam.cu:478-580 (step1 density/embedding, step2 forces)
+ * ------------------------------------------------------------------------------------------ */
+typedef struct b200md_eam b200md_eam;
+int b200md_eam_create(const char* path, int num_atoms, b200md_eam** out);
+void b200md_eam_destroy(b200md_eam* p);
+double b200md_eam_rc(const b200md_eam* p);
+int b200md_eam_info(const b200md_eam* p, int what); /* 0 num_types, 6 rebuild count */
+const char* b200md_eam_symbol(const b200md_eam* p, int t);
+int b200md_eam_compute(
+  b200md_eam* p, int n, const double h[9], const int pbc[3], const int* d_type,
+  const double* d_position, double* d_potential, double* d_force, double* d_virial, void* stream);
+int b200md_eam_invalidate(b200md_eam* p, int n_new, void* stream);
+int b200md_eam_check(b200md_eam* p, void* stream);
+
+/* ------------------------------------------------------------------------------------------
  * Force::compute pre-steps (src/force/force.cu:771-801):
  *   b200md_apply_pbc        <- gpu_apply_pbc, force.cu:424-459
  *   b200md_zero_properties  <- initialize_properties, force.cu:314-333

@@ -66,6 +66,12 @@ int oracle_tersoff_compute(
   int nt, const double* para, int N, const int* type, const double h[9], const int pbc[3],
   const double* position, double* pe, double* force, double* virial);
 
+/* Analytic EAM -- restates src/force/eam.cu:28-475.  model 0 = eam_zhou_2004 (21 numbers per
+ * type, nt <= 18), model 1 = eam_dai_2006 (9 numbers, one type). */
+int oracle_eam_compute(
+  int model, int nt, const double* para, int N, const int* type, const double h[9],
+  const int pbc[3], const double* position, double* pe, double* force, double* virial);
+
 /* per-atom heat current J_i = W_i . v_i split as in gpu_compute_heat,
  * src/measure/compute_heat.cu:32-63: heat[5N] = jx_in, jx_out, jy_in, jy_out, jz */
 void oracle_compute_heat(int N, const double* virial, const double* velocity, double* heat);

@@ -52,6 +52,7 @@ def lib():
         L.oracle_neighbor_list.argtypes = [C.c_int, _dp, _ip, _dp, C.c_double, _ip, _ip, C.c_int]
         L.oracle_lj_compute.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, _ip, _dp, _dp, _dp, _dp]
         L.oracle_tersoff_compute.argtypes = [C.c_int, _dp, C.c_int, _ip, _dp, _ip, _dp, _dp, _dp, _dp]
+        L.oracle_eam_compute.argtypes = [C.c_int, C.c_int, _dp, C.c_int, _ip, _dp, _ip, _dp, _dp, _dp, _dp]
         L.oracle_compute_heat.argtypes = [C.c_int, _dp, _dp, _dp]
         L.oracle_apply_pbc.argtypes = [C.c_int, _dp, _ip, _dp]
         L.oracle_velocity_verlet.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp]
@@ -168,6 +169,29 @@ def tersoff_compute(nt, para, type_, h, pbc, pos):
     r = L.oracle_tersoff_compute(nt, _d(para), n, _i(type_), _d(h), _i(pbc), _d(pos), _d(pe), _d(f), _d(v))
     if r != 0:
         raise RuntimeError(f"oracle_tersoff_compute failed: {r}")
+    return dict(pe=pe, force=f.reshape(3, n), virial=v.reshape(9, n))
+
+
+def eam_parameters(path):
+    """(model, nt, flat parameter array) from an eam_zhou_2004 / eam_dai_2006 potential file."""
+    toks = open(path).read().split()
+    model = {"eam_zhou_2004": 0, "eam_dai_2006": 1}[toks[0]]
+    nt = int(toks[1])
+    vals = [float(v) for v in toks[2 + nt:]]
+    return model, nt, np.array(vals[:21 * nt if model == 0 else 9], dtype=np.float64)
+
+
+def eam_compute(model, nt, para, type_, h, pbc, pos):
+    L = lib()
+    n = pos.shape[1]
+    type_ = np.ascontiguousarray(type_, dtype=np.int32)
+    pos = np.ascontiguousarray(pos, dtype=np.float64).reshape(3 * n)
+    para = np.ascontiguousarray(para, dtype=np.float64)
+    h, pbc = _box(h, pbc)
+    pe, f, v = np.zeros(n), np.zeros(3 * n), np.zeros(9 * n)
+    r = L.oracle_eam_compute(model, nt, _d(para), n, _i(type_), _d(h), _i(pbc), _d(pos), _d(pe), _d(f), _d(v))
+    if r != 0:
+        raise RuntimeError(f"oracle_eam_compute failed: {r}")
     return dict(pe=pe, force=f.reshape(3, n), virial=v.reshape(9, n))
 
 

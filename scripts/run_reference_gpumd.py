@@ -90,6 +90,10 @@ def main():
     d, i = run_case("sp_si", s, ["Si"], GOLDEN / "tersoff_Si_1989.txt", sp)
     collect_single_point(d, s, ["Si"]); infos.append(i)
 
+    s = fcc(10, 3.615, rattle=0.08, seed=25, num_types=3, symbols=["Cu", "Fe", "Ni"])  # 4000 atoms
+    d, i = run_case("sp_eam", s, ["Cu", "Fe", "Ni"], GOLDEN / "eam_zhou_2004_CuFeNi.txt", sp)
+    collect_single_point(d, s, ["Cu", "Fe", "Ni"]); infos.append(i)
+
     # ---- (2) NVE trajectories from given velocities: thermo.out every 10 steps ----
     md = "ensemble nve\ntime_step {dt}\ndump_thermo 10\nrun {steps}\n"
     s = rocksalt_pbte(20, rattle=0.02, seed=1)  # 64 000 atoms

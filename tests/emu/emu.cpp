@@ -8,6 +8,7 @@
 // (scan, shared-memory tile sort, atomics, warp reductions) are replaced by serial loops here
 // and are therefore covered only by the `-m gpu` tests.
 #include "../../gpumd_b200/csrc/b2_common.cuh"
+#include "../../gpumd_b200/csrc/b2_eam.cuh"
 #include "../../gpumd_b200/csrc/b2_integrate.cuh"
 #include "../../gpumd_b200/csrc/b2_lj.cuh"
 #include "../../gpumd_b200/csrc/b2_neighbor.cuh"
@@ -179,15 +180,15 @@ static void run_desc_radial(emu_nep* p, const B2Box& box)
   }
 }
 template <int K1>
-static void run_force_radial(emu_nep* p, const B2Box& box)
+static void run_force_final(emu_nep* p, const B2Box& box, double* pe, double* f, double* v)
 {
   for (int i = 0; i < p->n; ++i) {
     if (p->m.nt == 1)
-      b2_body_force_radial<1, K1>(i, p->P, box);
+      b2_body_force_final<1, K1>(i, p->P, box, pe, f, v);
     else if (p->m.nt == 2)
-      b2_body_force_radial<2, K1>(i, p->P, box);
+      b2_body_force_final<2, K1>(i, p->P, box, pe, f, v);
     else
-      b2_body_force_radial<0, K1>(i, p->P, box);
+      b2_body_force_final<0, K1>(i, p->P, box, pe, f, v);
   }
 }
 template <int K1>
@@ -311,23 +312,16 @@ int emu_nep_compute(
     else
       b2_body_utable<17>(i, P);
   }
-  switch (p->m.K1R) {
-    case 9: run_force_radial<9>(p, box); break;
-    case 13: run_force_radial<13>(p, box); break;
-    default: run_force_radial<17>(p, box); break;
-  }
   switch (p->m.K1A) {
     case 9: run_angular<9>(p, box, true); break;
     case 13: run_angular<13>(p, box, true); break;
     default: run_angular<17>(p, box, true); break;
   }
-  for (int i = 0; i < n; ++i)
-    b2_body_reduce_angular(i, P, box);
-  if (p->m.zbl_enabled)
-    for (int i = 0; i < n; ++i)
-      b2_body_zbl(i, P, box);
-  for (int i = 0; i < n; ++i)
-    b2_body_unpack(i, n, P.perm, P.acc, pe, force, virial);
+  switch (p->m.K1R) {
+    case 9: run_force_final<9>(p, box, pe, force, virial); break;
+    case 13: run_force_final<13>(p, box, pe, force, virial); break;
+    default: run_force_final<17>(p, box, pe, force, virial); break;
+  }
   return p->nb.flags[1] ? 5 : 0;
 }
 
@@ -508,6 +502,81 @@ void emu_compute_heat(int n, const double* w, const double* v, double* heat)
 {
   for (int i = 0; i < n; ++i)
     b2_body_heat(i, n, w, v, heat, n);
+}
+
+// ---- EAM ------------------------------------------------------------------------------------
+struct emu_eam {
+  int n;
+  B2EamView P;
+  std::vector<float> zp, Fp;
+  std::vector<double> acc;
+  EmuNeighbor nb;
+};
+
+emu_eam* emu_eam_create(int model, int nt, const double* para, int n)
+{
+  emu_eam* p = new emu_eam;
+  p->n = n;
+  B2EamView& P = p->P;
+  std::memset(&P, 0, sizeof P);
+  p->zp.assign((size_t)(nt > 0 ? nt : 1) * EZ_COUNT, 0.0f);
+  float rc = 0.0f;
+  if (model == 0) {
+    for (int t = 0; t < nt; ++t) {
+      float x[21];
+      for (int k = 0; k < 21; ++k)
+        x[k] = (float)para[t * 21 + k];
+      float* e = &p->zp[(size_t)t * EZ_COUNT];
+      e[EZ_RE_INV] = 1.0f / x[0]; e[EZ_FE] = x[1]; e[EZ_RHO_E_INV] = 1.0f / x[2];
+      e[EZ_RHO_S_INV] = 1.0f / x[3]; e[EZ_ALPHA] = x[4]; e[EZ_BETA] = x[5]; e[EZ_A] = x[6];
+      e[EZ_B] = x[7]; e[EZ_KAPPA] = x[8]; e[EZ_LAMBDA] = x[9]; e[EZ_FN0] = x[10]; e[EZ_FN1] = x[11];
+      e[EZ_FN2] = x[12]; e[EZ_FN3] = x[13]; e[EZ_F0] = x[14]; e[EZ_F1] = x[15]; e[EZ_F2] = x[16];
+      e[EZ_F3] = x[17]; e[EZ_ETA] = x[18]; e[EZ_FE_EMBED] = x[19]; e[EZ_RC] = x[20];
+      e[EZ_RHO_N] = x[2] * 0.85; e[EZ_RHO_0] = x[2] * 1.15; e[EZ_RHO_N_INV] = 1.0f / e[EZ_RHO_N];
+      if (rc < x[20])
+        rc = x[20];
+    }
+  } else {
+    float x[9];
+    for (int k = 0; k < 9; ++k)
+      x[k] = (float)para[k];
+    P.dA = x[0]; P.dd = x[1]; P.dc = x[2]; P.dc0 = x[3]; P.dc1 = x[4]; P.dc2 = x[5]; P.dc3 = x[6];
+    P.dc4 = x[7]; P.dB = x[8];
+    rc = P.dc > P.dd ? P.dc : P.dd;
+  }
+  P.model = model;
+  P.nt = nt;
+  P.rc = rc;
+  const double rs = rc + 1.0;
+  p->nb.init(n, rc, (int)(4.19 * rs * rs * rs * 0.2) + 32);
+  p->Fp.resize(n);
+  p->acc.resize((size_t)13 * n);
+  return p;
+}
+void emu_eam_destroy(emu_eam* p) { delete p; }
+int emu_eam_compute(
+  emu_eam* p, int n, const double h[9], const int pbc[3], const int* type, const double* pos,
+  double* pe, double* force, double* virial)
+{
+  const B2Box box = make_box(h, pbc);
+  const int rc = p->nb.update(box, type, pos);
+  if (rc)
+    return rc;
+  B2EamView& P = p->P;
+  P.zp = p->zp.data();
+  P.n = n;
+  P.atoms = p->nb.atoms.data();
+  P.nn_skin = p->nb.nn_skin.data();
+  P.nl_skin = p->nb.nl_skin.data();
+  P.Fp = p->Fp.data();
+  P.acc = p->acc.data();
+  for (int i = 0; i < n; ++i)
+    b2_body_eam_density(i, P, box);
+  for (int i = 0; i < n; ++i)
+    b2_body_eam_force(i, P, box);
+  for (int i = 0; i < n; ++i)
+    b2_body_unpack(i, n, p->nb.perm.data(), p->acc.data(), pe, force, virial);
+  return p->nb.flags[1] ? 5 : 0;
 }
 
 // ---- integrate ------------------------------------------------------------------------------

@@ -110,6 +110,29 @@ class EmuTersoff:
         return rc, dict(pe=pe, force=f.reshape(3, n), virial=v.reshape(9, n))
 
 
+class EmuEam:
+    def __init__(self, E, model, nt, para, n):
+        self.E = E
+        self.n = n
+        para = np.ascontiguousarray(para, np.float64)
+        self.h = E.emu_eam_create(model, nt, _d(para), n)
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            self.E.emu_eam_destroy(self.h)
+            self.h = None
+
+    def compute(self, type_, h, pbc, pos):
+        n = self.n
+        pe, f, v = np.zeros(n), np.zeros(3 * n), np.zeros(9 * n)
+        ty = np.ascontiguousarray(type_, np.int32)
+        p = np.ascontiguousarray(pos, np.float64).reshape(-1)
+        hh = np.ascontiguousarray(h, np.float64).reshape(9)
+        pb = np.ascontiguousarray(pbc, np.int32)
+        rc = self.E.emu_eam_compute(self.h, n, _d(hh), _i(pb), _i(ty), _d(p), _d(pe), _d(f), _d(v))
+        return rc, dict(pe=pe, force=f.reshape(3, n), virial=v.reshape(9, n))
+
+
 class Emu:
     def __init__(self, path):
         E = C.CDLL(path)
@@ -130,6 +153,10 @@ class Emu:
         E.emu_tersoff_create.argtypes = [C.c_int, _dp, C.c_int]
         E.emu_tersoff_destroy.argtypes = [C.c_void_p]
         E.emu_tersoff_compute.argtypes = [C.c_void_p, C.c_int, _dp, _ip, _ip, _dp, _dp, _dp, _dp]
+        E.emu_eam_create.restype = C.c_void_p
+        E.emu_eam_create.argtypes = [C.c_int, C.c_int, _dp, C.c_int]
+        E.emu_eam_destroy.argtypes = [C.c_void_p]
+        E.emu_eam_compute.argtypes = [C.c_void_p, C.c_int, _dp, _ip, _ip, _dp, _dp, _dp, _dp]
         E.emu_compute_heat.argtypes = [C.c_int, _dp, _dp, _dp]
         E.emu_apply_pbc.argtypes = [C.c_int, _dp, _ip, _dp]
         E.emu_velocity_verlet.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp]
@@ -144,6 +171,9 @@ class Emu:
 
     def tersoff(self, nt, para, n):
         return EmuTersoff(self.E, nt, para, n)
+
+    def eam(self, model, nt, para, n):
+        return EmuEam(self.E, model, nt, para, n)
 
     def compute_heat(self, virial, vel):
         n = vel.shape[1]

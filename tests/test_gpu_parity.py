@@ -284,6 +284,39 @@ def test_tersoff_matches_reference_gpu_single_point(eng):
                  what="force")
 
 
+@pytest.mark.parametrize("potfile", ["eam_Cu_Zhou_2004.txt", "eam_zhou_2004_CuFeNi.txt",
+                                     "eam_Cu_Dai_2006.txt"])
+def test_eam_matches_oracle(oracle, eng, potfile):
+    model, nt, para = oracle.eam_parameters(GOLDEN / potfile)
+    s = fcc(8, 3.615, rattle=0.08, seed=31, num_types=nt, symbols=["Cu", "Fe", "Ni"][:nt])
+    n = s["type"].shape[0]  # 2048 atoms
+    r = oracle.eam_compute(model, nt, para, s["type"], s["h"], s["pbc"], s["pos"])
+    pot = eng.EAM(GOLDEN / potfile, n)
+    atom = eng.Atom(s["type"], s["pos"], s["mass"])
+    pot.compute(eng.Box(s["h"], s["pbc"]), atom.type, atom.position_per_atom,
+                atom.potential_per_atom, atom.force_per_atom, atom.virial_per_atom)
+    pot.check()
+    assert_close(atom.potential_per_atom.cpu().numpy(), r["pe"], rtol=2e-6, atol=1e-6, what="pe")
+    check_fv(dict(force=atom.force_per_atom.cpu().numpy().reshape(3, n),
+                  virial=atom.virial_per_atom.cpu().numpy().reshape(9, n)), r)
+
+
+def test_eam_matches_reference_gpu_single_point(eng):
+    path = GOLDEN / "refgpu_sp_eam.npz"
+    if not path.exists():
+        pytest.skip("reference-GPU EAM fixture not generated yet")
+    d = np.load(path)
+    n = d["type"].shape[0]
+    pot = eng.EAM(GOLDEN / "eam_zhou_2004_CuFeNi.txt", n)
+    atom = eng.Atom(d["type"], d["pos"], np.full(n, 60.0))
+    pot.compute(eng.Box(d["h"], d["pbc"]), atom.type, atom.position_per_atom,
+                atom.potential_per_atom, atom.force_per_atom, atom.virial_per_atom)
+    pot.check()
+    assert abs(atom.potential_per_atom.sum().item() - float(d["energy"])) / n < 1e-6
+    assert_close(atom.force_per_atom.cpu().numpy().reshape(3, n), d["force"], rtol=1e-4, atol=1e-5,
+                 what="force")
+
+
 def test_thermostat_factors(oracle, eng):
     """Berendsen and Nose-Hoover-chain velocity scaling: device-side factors vs the host maths of
     the reference (oracle.berendsen_factor / oracle.nhc_chain), several consecutive half steps."""

@@ -204,3 +204,28 @@ def test_tersoff_energy_is_physical(oracle):
     r = oracle.tersoff_compute(nt, para, s["type"], s["h"], s["pbc"], s["pos"])
     assert abs(r["pe"].mean() + 4.6297) < 2e-3
     assert np.abs(r["force"]).max() < 1e-9
+
+
+@pytest.mark.parametrize("potfile,ntypes", [("eam_Cu_Zhou_2004.txt", 1), ("eam_zhou_2004_CuFeNi.txt", 3),
+                                            ("eam_Cu_Dai_2006.txt", 1)])
+def test_eam_bodies_match_oracle(oracle, emu, potfile, ntypes):
+    model, nt, para = oracle.eam_parameters(GOLDEN / potfile)
+    assert nt == ntypes
+    s = fcc(6, 3.615, rattle=0.08, seed=31, num_types=nt, symbols=["Cu", "Fe", "Ni"][:nt])
+    n = s["type"].shape[0]  # 864 atoms, 21.7 A box (rc 6.5 / 4.3 A)
+    r = oracle.eam_compute(model, nt, para, s["type"], s["h"], s["pbc"], s["pos"])
+    rc, out = emu.eam(model, nt, para, n).compute(s["type"], s["h"], s["pbc"], s["pos"])
+    assert rc == 0
+    assert_close(out["pe"], r["pe"], rtol=2e-6, atol=1e-6, what="pe")
+    check_fv(out, r)
+    assert np.abs(out["force"].sum(axis=1)).max() < 1e-3
+
+
+def test_eam_cohesive_energy_is_physical(oracle):
+    """Pin of the restatement: Zhou-2004 Cu gives Ec = -3.54 eV/atom at a0 = 3.615 A (the value the
+    parametrisation was fitted to)."""
+    model, nt, para = oracle.eam_parameters(GOLDEN / "eam_Cu_Zhou_2004.txt")
+    s = fcc(6, 3.615, rattle=0.0)
+    r = oracle.eam_compute(model, nt, para, s["type"], s["h"], s["pbc"], s["pos"])
+    assert abs(r["pe"].mean() + 3.54) < 0.01
+    assert np.abs(r["force"]).max() < 1e-5
