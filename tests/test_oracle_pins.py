@@ -100,6 +100,19 @@ def test_lj_oracle_matches_reference_gpu(oracle):
     assert_close(v33, d["virial"], rtol=1e-6, atol=1e-4, what="virial")
 
 
+def test_tersoff_oracle_matches_reference_gpu(oracle):
+    """Tersoff-1989 Si single point of the reference gpumd on B200 (8000 atoms, FP64 code): the
+    restatement agrees to round-off."""
+    d = np.load(GOLDEN / "refgpu_sp_si.npz")
+    nt, para = oracle.tersoff_parameters(GOLDEN / "tersoff_Si_1989.txt")
+    r = oracle.tersoff_compute(nt, para, d["type"], d["h"], d["pbc"], d["pos"])
+    assert abs(r["pe"].sum() - float(d["energy"])) < 1e-9 * abs(float(d["energy"]))
+    assert_close(r["force"], d["force"], rtol=1e-10, atol=1e-10, what="force")
+    v = r["virial"].sum(axis=1)
+    v33 = np.array([v[0], v[3], v[4], v[6], v[1], v[5], v[7], v[8], v[2]])
+    assert_close(v33, d["virial"], rtol=1e-10, atol=1e-8, what="virial")
+
+
 def test_oracle_f32_vs_f64(oracle):
     s = rocksalt_pbte(4, rattle=0.05, seed=1)
     m = oracle.NepOracle(GOLDEN / "nep_PbTe.txt")
