@@ -187,49 +187,127 @@ def cpu_baseline(seconds=15.0):
                       f"{dt:.1f} s"}
 
 
-def lj_side_bench(args, engine, torch):
-    """--workload lj: config C2 (1M-atom LJ argon NVE, dt 5 fs) -- a secondary line, not the
-    BASELINE metric; same step definition and timing rules."""
+SIDE = {
+    # name: (description, potential file, ensemble, dt fs, T K, heat-current interval)
+    "lj": ("C2: fcc Ar, LJ rc 10 A", "lj_Ar_10A.txt", "nve", 5.0, 80.0, 0),
+    "unep": ("C4: fcc 16-metal random alloy a=3.9 A, UNEP-v1 (16 types, ZBL), nvt_ber 300 300 100",
+             "nep_UNEP_v1.txt", "nvt_ber", 1.0, 300.0, 0),
+    "si": ("C5: diamond Si a=5.431 A, Tersoff-1989 (FP64), NVE + heat current every 20 steps",
+           "tersoff_Si_1989.txt", "nve", 1.0, 300.0, 20),
+}
+
+
+def side_structure(workload, world, cells):
+    from gpumd_b200.structures import diamond, fcc, init_velocities, nep_type_order
+    if workload == "lj":
+        c = 63 if cells == 50 else cells
+        s = fcc((c * world, c, c), 5.30, rattle=0.0, seed=1)
+    elif workload == "unep":  # 16 x 126 x 126 cells per GPU = 1 016 064 atoms; 8 GPUs ~ C4's 8 M
+        c = (16, 126, 126) if cells == 50 else (cells, cells, cells)
+        s = fcc((c[0] * world, c[1], c[2]), 3.9, rattle=0.0, seed=7, num_types=16,
+                symbols=nep_type_order(GOLDEN / "nep_UNEP_v1.txt"))
+    else:  # si: 16 x 63 x 63 cells per GPU = 508 032 atoms; 4 GPUs ~ C5's 2 M
+        c = (16, 63, 63) if cells == 50 else (cells, cells, cells)
+        s = diamond((c[0] * world, c[1], c[2]), a=5.431, rattle=0.0, seed=1)
+    s["vel"] = init_velocities(s["mass"], SIDE[workload][4], seed=42)
+    return s
+
+
+def side_bench(args, rank, world, local, torch, dist, engine):
+    """--workload lj|unep|si: the other BASELINE configs (C2, C4, C5) as secondary lines -- same
+    step definition and timing rules as the headline, single GPU or slab domains."""
     from gpumd_b200.structures import TIME_UNIT_CONVERSION
-    cells = 63 if args.cells == 50 else args.cells
-    s = crystal(cells, "lj")
-    n = s["type"].shape[0]
-    atom = engine.Atom(s["type"], s["pos"], s["mass"], s["vel"])
-    box = engine.Box(s["h"], s["pbc"])
-    force = engine.Force()
-    pot = force.parse_potential(GOLDEN / "lj_Ar_10A.txt", n)
-    ens = engine.Ensemble_NVE(n)
-    thermo = torch.zeros(8, dtype=torch.float64, device="cuda")
-    dt = 5.0 / TIME_UNIT_CONVERSION
-    fargs = (box, atom.position_per_atom, atom.type, atom.potential_per_atom, atom.force_per_atom,
-             atom.virial_per_atom)
+    desc, potfile, ensemble, dt_fs, T0, heat_every = SIDE[args.workload]
+    s = side_structure(args.workload, world, args.cells)
+    n_global = s["type"].shape[0]
+    dt = dt_fs / TIME_UNIT_CONVERSION
+    heat = [None]
+    if world == 1:
+        atom = engine.Atom(s["type"], s["pos"], s["mass"], s["vel"])
+        box = engine.Box(s["h"], s["pbc"])
+        force = engine.Force()
+        pot = force.parse_potential(GOLDEN / potfile, n_global)
+        ens = engine.Ensemble_BER(n_global, T0, 100.0) if ensemble == "nvt_ber" else engine.Ensemble_NVE(n_global)
+        thermo = torch.zeros(8, dtype=torch.float64, device="cuda")
+        fargs = (box, atom.position_per_atom, atom.type, atom.potential_per_atom, atom.force_per_atom,
+                 atom.virial_per_atom)
+        count = [0]
 
-    def step():
-        ens.compute1(dt, box, atom, thermo)
+        def step():
+            ens.compute1(dt, box, atom, thermo)
+            force.compute(*fargs)
+            ens.compute2(dt, box, atom, thermo)
+            count[0] += 1
+            if heat_every and count[0] % heat_every == 0:
+                heat[0] = engine.compute_heat(atom).view(5, n_global).sum(dim=1)
+
         force.compute(*fargs)
-        ens.compute2(dt, box, atom, thermo)
+        get_thermo = lambda: thermo.cpu().numpy()
+        check = pot.check
+        rebuilds = lambda: pot.num_rebuilds
+    else:
+        from gpumd_b200.domain import DomainMD, SlabDomain
+        pot_rc = {"lj": 10.0, "unep": 6.0, "si": 3.0}[args.workload]
+        dom = SlabDomain(s["h"], s["pbc"], pot_rc, rank, world, "cuda")
+        dom.distribute(s["type"], s["pos"], s["mass"], s["vel"])
+        md = DomainMD(dom, GOLDEN / potfile, ensemble=ensemble, temperature=T0, temperature_coupling=100.0,
+                      time_step=dt)
+        count = [0]
 
-    force.compute(*fargs)
+        def step():
+            md.maybe_exchange(5)
+            md.step(dt)
+            count[0] += 1
+            if heat_every and count[0] % heat_every == 0:
+                heat[0] = md.heat_current()
+
+        md.compute_force()
+        get_thermo = lambda: md.thermo.cpu().numpy()
+        check = md.pot.check
+        rebuilds = lambda: md.pot.num_rebuilds
+    del s
+    check()
     for _ in range(max(args.warmup, 3)):
         step()
-    pot.check()
+    check()
     torch.cuda.synchronize()
-    r0 = pot.num_rebuilds
+    if world > 1:
+        dist.barrier()
+        torch.cuda.synchronize()
+    r0 = rebuilds()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         step()
     e1.record()
     torch.cuda.synchronize()
-    pot.check()
-    ms = e0.elapsed_time(e1)
-    print(json.dumps({
-        "metric": "atom-steps/sec (1M-atom LJ argon NVE, config C2)", "value": n * args.steps / (ms * 1e-3),
-        "unit": "atom-steps/s", "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
-        "ms_per_step": ms / args.steps, "higher_is_better": True, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"C2: fcc Ar {cells}^3 cells = {n} atoms, LJ rc 10 A, NVE dt 5 fs, 80 K",
-                   "list_rebuilds_in_timed_region": pot.num_rebuilds - r0,
-                   "final_T_K": float(thermo.cpu().numpy()[0])}}))
+    ms_t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.barrier()
+        dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+    ms = float(ms_t.item())
+    check()
+    th = get_thermo()
+    stage_ms = None
+    if world == 1 and hasattr(pot, "profile"):
+        pot.profile(True)
+        for _ in range(10):
+            step()
+        stage_ms = {k: round(v[0] / max(v[1], 1), 4) for k, v in pot.profile_read().items()}
+        pot.profile(False)
+    if rank == 0:
+        print(json.dumps({
+            "metric": f"atom-steps/sec ({args.workload}, secondary config)", "value": n_global * args.steps / (ms * 1e-3),
+            "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "dtype": "f64" if args.workload == "si" else "f32", "data": "synthetic",
+            "config": {"workload": f"{desc}; {n_global} atoms on {world} GPU(s), dt {dt_fs} fs, {ensemble}",
+                       "atoms_per_gpu": n_global // world,
+                       "list_rebuilds_in_timed_region_rank0": rebuilds() - r0,
+                       "final_T_K": float(th[0]), "nep_stage_ms": stage_ms,
+                       "heat_current": None if heat[0] is None else [float(v) for v in heat[0].cpu().numpy()]}}))
+    if world > 1:
+        dist.barrier()
 
 
 def ours_multi(args, rank, world, local, torch, dist, engine):
@@ -349,8 +427,8 @@ def ours(args, rank, world):
     if world > 1:
         dist.barrier()
 
-    if args.workload == "lj":
-        return lj_side_bench(args, engine, torch)
+    if args.workload != "pbte":
+        return side_bench(args, rank, world, local, torch, dist, engine)
     if world > 1:
         return ours_multi(args, rank, world, local, torch, dist, engine)
     s = crystal(args.cells)
@@ -513,8 +591,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=50, help="conventional cells per edge (50 -> 1M atoms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="pbte", choices=["pbte", "lj"],
-                    help="pbte = the BASELINE metric (C3); lj = secondary C2 line")
+    ap.add_argument("--workload", default="pbte", choices=["pbte", "lj", "unep", "si"],
+                    help="pbte = the BASELINE metric (C3); lj / unep / si = secondary lines for C2 / C4 / C5")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))

@@ -229,7 +229,10 @@ class SlabDomain:
 class DomainMD:
     """NVE driver over a SlabDomain with the libb200md kernels (one instance per rank)."""
 
-    def __init__(self, dom, potential_file, capacity_factor=1.35):
+    def __init__(self, dom, potential_file, capacity_factor=1.35, ensemble="nve", temperature=300.0,
+                 temperature_coupling=100.0, time_step=None):
+        """ensemble: "nve", "nvt_ber" (Ensemble_BER, ensemble_ber.cu:178-233) or "nvt_nhc"
+        (Ensemble_NHC, ensemble_nhc.cu:173-237); thermostats act on the GLOBAL temperature."""
         from . import engine, lib as _lib
         self.dom = dom
         self.eng = engine
@@ -243,6 +246,22 @@ class DomainMD:
         nbytes = self.L.b200md_thermo_scratch_bytes(cap)
         self._scratch = torch.zeros(nbytes, dtype=torch.uint8, device=dom.device)
         self.steps_since_exchange = 0
+        self.ensemble = ensemble
+        self.temperature = float(temperature)
+        self.temperature_coupling = float(temperature_coupling)
+        self._nhc = None
+        if ensemble == "nvt_nhc":
+            h = C.c_void_p()
+            self._lib.check(self.L.b200md_nhc_create(
+                int(dom.n_global), self.temperature, self.temperature_coupling, float(time_step), C.byref(h)))
+            self._nhc = h
+        elif ensemble not in ("nve", "nvt_ber"):
+            raise ValueError(f"unsupported ensemble {ensemble}")
+
+    def __del__(self):
+        if getattr(self, "_nhc", None):
+            self.L.b200md_nhc_destroy(self._nhc)
+            self._nhc = None
 
     def _st(self):
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -259,9 +278,30 @@ class DomainMD:
             d.n_loc, self._p(d.pe), self._p(d.force), self._p(d.virial), self._st()))
         self.pot.compute(self.box, d.type, d.pos, d.pe, d.force, d.virial)
 
+    def _nhc_half(self, dt):
+        d = self.dom
+        self.find_thermo(True)
+        self._lib.check(self.L.b200md_nhc_half_step(
+            self._nhc, d.n_own, d.n_loc, float(dt), self._p(self.thermo), self._p(d.vel), self._st()))
+
+    def heat_current(self):
+        """Global heat current (5 components: jx_in, jx_out, jy_in, jy_out, jz) from the per-atom
+        virial and velocity of the owned atoms (compute_heat.cu:32-90 + the 5-way sum of
+        hac.cu:51,106), all-reduced over ranks."""
+        d = self.dom
+        if getattr(self, "_heat", None) is None or self._heat.numel() != 5 * d.n_own:
+            self._heat = torch.zeros(5 * d.n_own, dtype=torch.float64, device=d.device)
+        self._lib.check(self.L.b200md_compute_heat(
+            d.n_own, d.n_loc, self._p(d.virial), self._p(d.vel), self._p(self._heat), d.n_own, self._st()))
+        j = self._heat.view(5, d.n_own).sum(dim=1)
+        dist.all_reduce(j, op=dist.ReduceOp.SUM)
+        return j
+
     def step(self, dt, reduce_thermo=True):
         d = self.dom
         L, st = self.L, self._st()
+        if self._nhc is not None:
+            self._nhc_half(dt)
         self._lib.check(L.b200md_velocity_verlet_strided(
             1, d.n_own, d.n_loc, float(dt), self._p(d.mass), self._p(d.pos), self._p(d.vel),
             self._p(d.force), st))
@@ -272,7 +312,14 @@ class DomainMD:
         self._lib.check(L.b200md_velocity_verlet_strided(
             0, d.n_own, d.n_loc, float(dt), self._p(d.mass), self._p(d.pos), self._p(d.vel),
             self._p(d.force), st))
-        self.find_thermo(reduce_thermo)
+        if self._nhc is not None:
+            self._nhc_half(dt)
+        else:
+            self.find_thermo(reduce_thermo or self.ensemble == "nvt_ber")
+            if self.ensemble == "nvt_ber":
+                self._lib.check(L.b200md_berendsen_temperature(
+                    d.n_own, d.n_loc, self.temperature, self.temperature_coupling, self._p(self.thermo),
+                    self._p(d.vel), st))
         self.steps_since_exchange += 1
 
     def find_thermo(self, reduce=True):

@@ -8,7 +8,9 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --fo
 echo "== smoke"; timeout 300 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -5
 echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -q ${PYTEST_ARGS:-} 2>&1 | tail -40 | tee gpurun_out/pytest_gpu.txt
 echo "== bench"; timeout 600 python bench.py --steps ${BENCH_STEPS:-100} --warmup 5 > gpurun_out/bench.json 2> gpurun_out/bench.err; tail -c 3000 gpurun_out/bench.json; tail -5 gpurun_out/bench.err
-echo "== bench lj"; timeout 300 python bench.py --workload lj --steps 100 --warmup 5 > gpurun_out/bench_lj.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_lj.json
+for w in ${SIDE_WORKLOADS:-lj}; do
+echo "== bench $w"; timeout 400 python bench.py --workload $w --steps ${SIDE_STEPS:-100} --warmup 5 > gpurun_out/bench_$w.json 2>> gpurun_out/bench.err; cat gpurun_out/bench_$w.json
+done
 if [ "${RUN_REF:-0}" = "1" ]; then
 echo "== reference gpumd"; timeout 1500 python scripts/run_reference_gpumd.py ${REF_ARGS:-} 2>&1 | tail -60
 fi

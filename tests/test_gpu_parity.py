@@ -296,7 +296,12 @@ def test_eam_matches_oracle(oracle, eng, potfile):
     pot.compute(eng.Box(s["h"], s["pbc"]), atom.type, atom.position_per_atom,
                 atom.potential_per_atom, atom.force_per_atom, atom.virial_per_atom)
     pot.check()
-    assert_close(atom.potential_per_atom.cpu().numpy(), r["pe"], rtol=2e-6, atol=1e-6, what="pe")
+    # per-atom pair energies are FP32 sums of large cancelling terms (Dai-2006 especially) taken in a
+    # different neighbour order than the oracle's: allow that reordering noise per atom, and ask
+    # the total to agree much more tightly
+    pe = atom.potential_per_atom.cpu().numpy()
+    assert_close(pe, r["pe"], rtol=1e-5, atol=1e-5, what="pe")
+    assert abs(pe.sum() - r["pe"].sum()) / n < 2e-6
     check_fv(dict(force=atom.force_per_atom.cpu().numpy().reshape(3, n),
                   virial=atom.virial_per_atom.cpu().numpy().reshape(9, n)), r)
 

@@ -113,6 +113,16 @@ def test_tersoff_oracle_matches_reference_gpu(oracle):
     assert_close(v33, d["virial"], rtol=1e-10, atol=1e-8, what="virial")
 
 
+def test_eam_oracle_matches_reference_gpu(oracle):
+    """Zhou-2004 Cu-Fe-Ni alloy single point of the reference gpumd on B200 (4000 atoms)."""
+    d = np.load(GOLDEN / "refgpu_sp_eam.npz")
+    n = d["type"].shape[0]
+    model, nt, para = oracle.eam_parameters(GOLDEN / "eam_zhou_2004_CuFeNi.txt")
+    r = oracle.eam_compute(model, nt, para, d["type"], d["h"], d["pbc"], d["pos"])
+    assert abs(r["pe"].sum() - float(d["energy"])) / n < 1e-6
+    assert_close(r["force"], d["force"], rtol=1e-5, atol=1e-5, what="force")
+
+
 def test_oracle_f32_vs_f64(oracle):
     s = rocksalt_pbte(4, rattle=0.05, seed=1)
     m = oracle.NepOracle(GOLDEN / "nep_PbTe.txt")
