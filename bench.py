@@ -44,8 +44,9 @@ def stage_algorithmic_bytes(nn, model):
     D, Dr, S = model["D"], model["Dr"], model["S"]
     Da = D - Dr
     return {
-        "k_split": 36 + 4 * (Ng + Nr + Na),
-        "descriptor+MLP": 52 + 4 * (Nr + Na) + 4 * D + 4 * S,
+        # the neighbour-set split (36 + 4(Ng+Nr+Na)) is fused into the radial descriptor pass,
+        # which therefore reads the skin list instead of re-reading the radial list
+        "descriptor+MLP": 36 + 4 * (Ng + Nr + Na) + 52 + 4 * Na + 4 * D + 4 * S,
         # fused radial force + angular pair reduction + scatter: the radial-force stage
         # (32+4Nr+4Dr+192) plus the list and f12 reads of the pair reduction (16 Na); the second
         # 192-byte force/virial RMW and 28-byte per-atom read of the separate stage are gone

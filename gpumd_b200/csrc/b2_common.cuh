@@ -30,6 +30,8 @@ struct float4 {
 #endif
 
 // Box passed by value to kernels: GPUMD's Box::cpu_h / float_h (src/model/box.cuh:18-35).
+constexpr int B2_MAX_TYPES = 94; // NUM_ELEMENTS, src/utilities/common.cuh:18
+
 struct B2Box {
   double h[18]; // h[0..8] row-major (lattice vectors are columns), h[9..17] inverse
   float hf[18];

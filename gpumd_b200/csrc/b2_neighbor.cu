@@ -164,6 +164,112 @@ __global__ void __launch_bounds__(128)
     b2_body_skin_list(i, v, box, g, cutoff2);
 }
 
+// ---- type tiles: stable counting sort of the sorted atoms by type, buckets padded to 128 ------
+// rank of this thread's atom among the same-type atoms of its block (ascending thread order);
+// leaves the per-warp counts in wcnt[warp][type]
+__device__ __forceinline__ int block_rank_by_type(
+  int t, bool valid, int nt, int (*wcnt)[B2_MAX_TYPES + 2], int& before_warp)
+{
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  for (int k = tid; k < (BLK / 32) * (B2_MAX_TYPES + 2); k += BLK)
+    (&wcnt[0][0])[k] = 0;
+  __syncthreads();
+  const unsigned act = __ballot_sync(0xffffffffu, valid);
+  int rank = 0;
+  if (valid) {
+    const unsigned peers = __match_any_sync(act, t);
+    rank = __popc(peers & ((1u << lane) - 1u));
+    if (rank == 0)
+      wcnt[w][t] = __popc(peers);
+  }
+  __syncthreads();
+  before_warp = 0;
+  if (valid)
+    for (int k = 0; k < w; ++k)
+      before_warp += wcnt[k][t];
+  return rank;
+}
+
+__global__ void __launch_bounds__(BLK) k_tile_count(B2NeighborView v)
+{
+  if (!v.flags[0])
+    return;
+  __shared__ int wcnt[BLK / 32][B2_MAX_TYPES + 2];
+  const int i = blockIdx.x * BLK + threadIdx.x;
+  for (int s = i; s < v.tile_nslot; s += gridDim.x * BLK)
+    v.tile_atom[s] = -1;
+  const bool valid = i < v.n;
+  int before;
+  block_rank_by_type(valid ? v.atoms[i].type : 0, valid, v.tile_nt, wcnt, before);
+  if (threadIdx.x < v.tile_nt) {
+    int c = 0;
+    for (int k = 0; k < BLK / 32; ++k)
+      c += wcnt[k][threadIdx.x];
+    v.tile_blk[(size_t)threadIdx.x * v.tile_nblk + blockIdx.x] = c;
+  }
+}
+
+// one warp per type: exclusive scan of the block counts; then bucket bases and tile types
+__global__ void __launch_bounds__(1024) k_tile_scan(B2NeighborView v)
+{
+  if (!v.flags[0])
+    return;
+  __shared__ int count[B2_MAX_TYPES + 2], base[B2_MAX_TYPES + 2];
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  for (int t = w; t < v.tile_nt; t += 32) {
+    int* c = v.tile_blk + (size_t)t * v.tile_nblk;
+    int run = 0;
+    for (int b0 = 0; b0 < v.tile_nblk; b0 += 32) {
+      const int b = b0 + lane;
+      const int mine = b < v.tile_nblk ? c[b] : 0;
+      int inc = mine;
+      for (int o = 1; o < 32; o <<= 1) {
+        const int up = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o)
+          inc += up;
+      }
+      if (b < v.tile_nblk)
+        c[b] = run + inc - mine;
+      run += __shfl_sync(0xffffffffu, inc, 31);
+    }
+    if (lane == 0)
+      count[t] = run;
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int slot = 0;
+    for (int t = 0; t < v.tile_nt; ++t) {
+      base[t] = slot;
+      v.tile_meta[1 + t] = slot;
+      slot += (count[t] + 127) / 128 * 128;
+    }
+    base[v.tile_nt] = slot;
+    v.tile_meta[0] = slot / 128;
+  }
+  __syncthreads();
+  const int ntile = base[v.tile_nt] / 128;
+  for (int k = tid; k < ntile; k += 1024) {
+    int t = 0;
+    while (t + 1 < v.tile_nt && base[t + 1] <= k * 128)
+      ++t;
+    v.tile_type[k] = t;
+  }
+}
+
+__global__ void __launch_bounds__(BLK) k_tile_fill(B2NeighborView v)
+{
+  if (!v.flags[0])
+    return;
+  __shared__ int wcnt[BLK / 32][B2_MAX_TYPES + 2];
+  const int i = blockIdx.x * BLK + threadIdx.x;
+  const bool valid = i < v.n;
+  const int t = valid ? v.atoms[i].type : 0;
+  int before;
+  const int rank = block_rank_by_type(t, valid, v.tile_nt, wcnt, before);
+  if (valid)
+    v.tile_atom[v.tile_meta[1 + t] + v.tile_blk[(size_t)t * v.tile_nblk + blockIdx.x] + before + rank] = i;
+}
+
 __global__ void k_rebuild_done(int* flags)
 {
   if (flags[0]) {
@@ -229,6 +335,13 @@ B2NeighborView Neighbor::view() const
   v.nn_skin = nn_skin.p;
   v.nl_skin = nl_skin.p;
   v.flags = flags.p;
+  v.tile_nt = tile_nt;
+  v.tile_nblk = grid_for(n, BLK);
+  v.tile_nslot = n + 128 * tile_nt;
+  v.tile_atom = tile_atom.p;
+  v.tile_type = tile_type.p;
+  v.tile_blk = tile_blk.p;
+  v.tile_meta = tile_meta.p;
   return v;
 }
 
@@ -298,8 +411,30 @@ int Neighbor::update(
   B2_LAUNCHED();
   k_skin_list<<<grid_for(n, 128), 128, 0, st>>>(v, box, g, cutoff);
   B2_LAUNCHED();
+  if (tile_nt > 0) {
+    k_tile_count<<<gn, BLK, 0, st>>>(v);
+    B2_LAUNCHED();
+    k_tile_scan<<<1, 1024, 0, st>>>(v);
+    B2_LAUNCHED();
+    k_tile_fill<<<gn, BLK, 0, st>>>(v);
+    B2_LAUNCHED();
+  }
   k_rebuild_done<<<1, 1, 0, st>>>(flags.p);
   B2_LAUNCHED();
+  return B200MD_OK;
+}
+
+int Neighbor::enable_type_tiles(int num_types)
+{
+  if (num_types < 1 || num_types > B2_MAX_TYPES) {
+    set_error("enable_type_tiles: bad number of types");
+    return B200MD_ERR_ARG;
+  }
+  tile_nt = num_types;
+  B2_CUDA(tile_atom.reserve((size_t)capacity + 128 * (size_t)num_types));
+  B2_CUDA(tile_type.reserve((size_t)capacity / 128 + num_types + 2));
+  B2_CUDA(tile_blk.reserve((size_t)num_types * grid_for(capacity, BLK)));
+  B2_CUDA(tile_meta.reserve(num_types + 2));
   return B200MD_OK;
 }
 

@@ -40,6 +40,15 @@ struct B2NeighborView {
   int* nn_skin;      // [n]
   int* nl_skin;      // [mn_skin * n]  column-major nl[k*n + i]
   int* flags;        // [0] rebuild requested, [1] error bits, [2] rebuild counter
+  // optional type tiles (Neighbor::enable_type_tiles): the sorted atoms bucketed by type, every
+  // bucket padded to a multiple of 128 slots -- row blocks of the tensor-core hidden layer
+  int tile_nt = 0;          // 0 = feature off
+  int tile_nblk = 0;        // blocks of BLK atoms
+  int tile_nslot = 0;       // n + 128 * tile_nt
+  int* tile_atom = nullptr; // [tile_nslot] sorted atom index or -1 (padding)
+  int* tile_type = nullptr; // [tile_nslot / 128] type of each 128-slot tile
+  int* tile_blk = nullptr;  // [tile_nt * tile_nblk] per-block counts, then offsets inside the bucket
+  int* tile_meta = nullptr; // [0] number of tiles, [1 + t] first slot of type t
 };
 
 // ---- pack: caller SoA -> sorted B2Atom records, and displacement trigger -------------------

@@ -22,9 +22,14 @@ public:
   DevBuf<double> snap;
   DevBuf<int> perm, perm_tmp, cell_of, order_tmp, cell_count, cell_fill, cell_start, nn_skin,
     nl_skin, flags;
+  int tile_nt = 0; // type tiles (see B2NeighborView) are maintained when > 0
+  DevBuf<int> tile_atom, tile_type, tile_blk, tile_meta;
 
   // Neighbor::initialize, src/force/neighbor.cu:824-833
   int init(int num_atoms, double rc, int mn_skin);
+  // also keep the type-bucketed tile order up to date at every rebuild (num_types <= 94)
+  int enable_type_tiles(int num_types);
+  int max_tiles() const { return (n + 127) / 128 + tile_nt; }
   // Neighbor::find_neighbor_global, src/force/neighbor.cu:756-800 (fully asynchronous here)
   int update(const B2Box& box, const int* d_type, const double* d_pos, int n, cudaStream_t st);
   int check(cudaStream_t st, int* err_bits, int* rebuilds);

@@ -4,7 +4,9 @@
 #include "b2_host.h"
 #include "b2_neighbor_host.h"
 #include "b2_nep.cuh"
+#include "b2_nep_tc.cuh"
 #include "b2_nep_model.h"
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -15,13 +17,6 @@ namespace {
 
 constexpr int BLK = 128;
 constexpr int MLP_BLK = 256;
-
-__global__ void __launch_bounds__(BLK) k_split(B2NepView P, B2Box box)
-{
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < P.n)
-    b2_body_split(i, P, box);
-}
 
 template <int NT, int K1>
 __global__ void __launch_bounds__(BLK) k_desc_radial(B2NepView P, B2Box box)
@@ -188,6 +183,8 @@ struct b200md_nep {
   DevBuf<int> nn_r, nl_r, nn_a, nl_a;
   DevBuf<float> q, sfx, FpR, FpA, U, f12;
   DevBuf<double> acc;
+  DevBuf<float> tc_img;
+  bool use_tc = false; // hidden layer on the tensor cores (k_mlp_tc) instead of k_mlp
   // staging for the host-buffer entry point
   DevBuf<int> h_type;
   DevBuf<double> h_pos, h_out;
@@ -282,9 +279,9 @@ int launch_mlp(const b200md_nep* p, cudaStream_t st)
   } while (0)
 
 // stage ids reported by b200md_nep_profile_read / b200md_nep_stage_name
-enum { ST_NEIGHBOR, ST_SPLIT, ST_DESC_R, ST_DESC_A, ST_MLP, ST_FORCE_A, ST_FORCE_FINAL, ST_COUNT };
+enum { ST_NEIGHBOR, ST_DESC_R, ST_DESC_A, ST_MLP, ST_FORCE_A, ST_FORCE_FINAL, ST_COUNT };
 const char* const STAGE_NAMES[ST_COUNT] = {
-  "neighbor_update", "k_split", "k_desc_radial", "k_desc_angular", "k_mlp", "k_force_angular",
+  "neighbor_update", "k_desc_radial", "k_desc_angular", "k_mlp", "k_force_angular",
   "k_force_final"};
 
 int nep_pipeline(
@@ -292,10 +289,6 @@ int nep_pipeline(
 {
   const int n = p->n;
   StageProfiler& pf = p->prof;
-  pf.begin(st, ST_SPLIT);
-  k_split<<<grid_for(n, BLK), BLK, 0, st>>>(p->view, box);
-  B2_LAUNCHED();
-  pf.end(st, ST_SPLIT);
   pf.begin(st, ST_DESC_R);
   switch (p->model.K1R) {
     case 9: B2_TRY(dispatch_desc_radial<9>(p, box, st)); break;
@@ -311,6 +304,14 @@ int nep_pipeline(
   }
   pf.end(st, ST_DESC_A);
   pf.begin(st, ST_MLP);
+  if (p->use_tc) {
+    const size_t bytes = b2_tc_smem_bytes(p->model.tc_img_floats, p->model.HN, p->model.DK);
+    if (bytes > 48 * 1024)
+      B2_CUDA(cudaFuncSetAttribute(
+        k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    k_mlp_tc<<<p->nb.max_tiles(), 128, bytes, st>>>(p->view);
+    B2_LAUNCHED();
+  } else
   switch (p->model.DIMP) {
     case 16: B2_TRY(launch_mlp<16>(p, st)); break;
     case 32: B2_TRY(launch_mlp<32>(p, st)); break;
@@ -445,6 +446,22 @@ int nep_setup(b200md_nep* p, int num_atoms)
   P.f12 = p->f12.p;
   P.acc = p->acc.p;
   P.flags = p->nb.flags.p;
+  // hidden layer: tensor cores unless the shapes do not fit or B200MD_NEP_MLP=simt asks for the
+  // SIMT kernel (kept for A/B measurements and for exotic layer sizes)
+  const char* mlp_env = std::getenv("B200MD_NEP_MLP");
+  p->use_tc = m.tc_ok && !(mlp_env && std::strcmp(mlp_env, "simt") == 0);
+  if (p->use_tc) {
+    B2_TRY(p->nb.enable_type_tiles(m.nt));
+    B2_TRY(upload(p->tc_img, m.tc_img));
+    P.tc_img = p->tc_img.p;
+    P.tc_img_floats = m.tc_img_floats;
+    P.HN = m.HN;
+    P.DK = m.DK;
+    P.DN = m.DN;
+    P.tile_atom = p->nb.tile_atom.p;
+    P.tile_type = p->nb.tile_type.p;
+    P.tile_meta = p->nb.tile_meta.p;
+  }
 
   // shared-memory budgets
   p->ang_block = BLK;

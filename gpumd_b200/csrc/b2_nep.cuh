@@ -42,7 +42,6 @@
 #define B2_C5B2 (0.026596810706114f)
 
 constexpr int B2_NABC = 24;      // (L_max+1)^2 - 1 for L_max = 4
-constexpr int B2_MAX_TYPES = 94; // NUM_ELEMENTS, src/utilities/common.cuh:18
 
 struct B2NepView {
   // ---- model (device tables) ----
@@ -91,56 +90,13 @@ struct B2NepView {
   float* f12; // [3 * mn_a * n]
   double* acc; // [13 * n]: pe, fx,fy,fz, virial xx,yy,zz,xy,xz,yz,yx,zx,zy (sorted order)
   int* flags;
+  // ---- tensor-core hidden layer (k_mlp_tc; null / 0 when the SIMT k_mlp is used) ----
+  const float* tc_img;  // [nt][tc_img_floats] shared-memory images, see NepModel::tc_img
+  int tc_img_floats, HN, DK, DN;
+  const int* tile_atom; // B2NeighborView::tile_atom / tile_type / tile_meta
+  const int* tile_type;
+  const int* tile_meta;
 };
-
-// ---------------------------------------------------------------------------------------------
-// neighbour-set split: find_neighbor_list_large_box, nep.cu:436-486
-// ---------------------------------------------------------------------------------------------
-B2_HD void b2_body_split(int i, const B2NepView& P, const B2Box& box)
-{
-  const B2Geo geo = b2_geo(box);
-  const size_t N = (size_t)P.n;
-  const B2Atom a1 = P.atoms[i];
-  const int nn = P.nn_skin[i];
-  const int row = a1.type * P.nt;
-  int cr = 0, ca = 0;
-  // software pipeline: the record of candidate k+1 and the index of candidate k+2 are in flight
-  // while candidate k is tested (the loads are dependent: index -> record)
-  int jn = nn > 0 ? P.nl_skin[i] : i;
-  B2Atom an = b2_load_atom(&P.atoms[jn]);
-  int j2 = nn > 1 ? P.nl_skin[N + i] : i;
-  for (int k = 0; k < nn; ++k) {
-    const int j = jn;
-    const B2Atom a2 = an;
-    jn = j2;
-    an = b2_load_atom(&P.atoms[jn]);
-    j2 = (k + 2 < nn) ? P.nl_skin[(size_t)(k + 2) * N + i] : i;
-    float x12, y12, z12;
-    b2_r12(geo, box, a1, a2, x12, y12, z12);
-    const float d2 = b2_d2(x12, y12, z12);
-    const int pair = row + a2.type;
-    if (d2 >= B2_LDG(&P.rc2_r[pair]))
-      continue;
-    if (cr < P.mn_r)
-      P.nl_r[(size_t)cr * N + i] = j;
-    ++cr;
-    if (d2 < B2_LDG(&P.rc2_a[pair])) {
-      if (ca < P.mn_a)
-        P.nl_a[(size_t)ca * N + i] = j;
-      ++ca;
-    }
-  }
-  if (cr > P.mn_r) {
-    B2_ATOMIC_OR(&P.flags[1], (int)B2_ERR_RADIAL_OVERFLOW);
-    cr = P.mn_r;
-  }
-  if (ca > P.mn_a) {
-    B2_ATOMIC_OR(&P.flags[1], (int)B2_ERR_ANGULAR_OVERFLOW);
-    ca = P.mn_a;
-  }
-  P.nn_r[i] = cr;
-  P.nn_a[i] = ca;
-}
 
 // ---------------------------------------------------------------------------------------------
 // radial basis.  fc, fc' : nep_utilities.cuh:409-431;  fn, fn' : nep_utilities.cuh:572-623
@@ -209,6 +165,9 @@ B2_HD void b2_basis_d(float d, float rc, float rcinv, float* fn, float* fnp)
 // NT > 0: per-type accumulators in registers (models with <= NT types); NT == 0: accumulators in
 // the caller-provided scratch `acc` laid out [(t2*K1+k)*stride + lane].
 // ---------------------------------------------------------------------------------------------
+// The neighbour-set split (find_neighbor_list_large_box, nep.cu:436-486) is fused into this pass:
+// the loop walks the skin list, applies the reference's two FP32 membership tests and emits the
+// radial / angular lists (ascending, like the reference's) for the later kernels on the way.
 template <int NT, int K1>
 B2_HD void b2_body_desc_radial(
   int i, const B2NepView& P, const B2Box& box, float* acc, int stride, int lane)
@@ -216,7 +175,9 @@ B2_HD void b2_body_desc_radial(
   const B2Geo geo = b2_geo(box);
   const B2Atom a1 = P.atoms[i];
   const int t1 = a1.type;
-  const int nn = P.nn_r[i];
+  const int nn = P.nn_skin[i];
+  const int* list = P.nl_skin;
+  int cr = 0, ca = 0;
   float S[NT > 0 ? NT : 1][K1];
   if (NT > 0) {
 #pragma unroll
@@ -228,18 +189,31 @@ B2_HD void b2_body_desc_radial(
     for (int m = 0; m < P.nt * K1; ++m)
       acc[(size_t)m * stride + lane] = 0.0f;
   }
-  int jn = nn > 0 ? P.nl_r[i] : i;
+  int jn = nn > 0 ? list[i] : i;
   B2Atom an = b2_load_atom(&P.atoms[jn]);
-  int j2 = nn > 1 ? P.nl_r[(size_t)P.n + i] : i;
+  int j2 = nn > 1 ? list[(size_t)P.n + i] : i;
   for (int s = 0; s < nn; ++s) {
+    const int j = jn;
     const B2Atom a2 = an;
+    jn = j2;
     an = b2_load_atom(&P.atoms[j2]);
-    j2 = (s + 2 < nn) ? P.nl_r[(size_t)(s + 2) * P.n + i] : i;
+    j2 = (s + 2 < nn) ? list[(size_t)(s + 2) * P.n + i] : i;
     float x12, y12, z12;
     b2_r12(geo, box, a1, a2, x12, y12, z12);
-    const float d = sqrtf(b2_d2(x12, y12, z12));
+    const float d2 = b2_d2(x12, y12, z12);
     const int t2 = a2.type;
     const int pair = t1 * P.nt + t2;
+    if (d2 >= B2_LDG(&P.rc2_r[pair]))
+      continue;
+    if (cr < P.mn_r)
+      P.nl_r[(size_t)cr * P.n + i] = j;
+    ++cr;
+    if (d2 < B2_LDG(&P.rc2_a[pair])) {
+      if (ca < P.mn_a)
+        P.nl_a[(size_t)ca * P.n + i] = j;
+      ++ca;
+    }
+    const float d = sqrtf(d2);
     float fn[K1];
     b2_basis<K1>(d, B2_LDG(&P.rc_r[pair]), B2_LDG(&P.rcinv_r[pair]), fn);
     if (NT == 1) {
@@ -261,6 +235,16 @@ B2_HD void b2_body_desc_radial(
         a[(size_t)k * stride] += fn[k];
     }
   }
+  if (cr > P.mn_r) {
+    B2_ATOMIC_OR(&P.flags[1], (int)B2_ERR_RADIAL_OVERFLOW);
+    cr = P.mn_r;
+  }
+  if (ca > P.mn_a) {
+    B2_ATOMIC_OR(&P.flags[1], (int)B2_ERR_ANGULAR_OVERFLOW);
+    ca = P.mn_a;
+  }
+  P.nn_r[i] = cr;
+  P.nn_a[i] = ca;
   // contraction with the expansion coefficients
   for (int n = 0; n < P.nr1; ++n) {
     float q = 0.0f;

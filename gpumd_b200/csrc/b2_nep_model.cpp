@@ -1,11 +1,31 @@
 // b2_nep_model.cpp -- nep.txt parser (format: src/force/nep.cu:100-395 of the reference).
 #include "b2_nep_model.h"
+#include <cstdint>
+#include <cstring>
 #include <cmath>
 #include <cstdlib>
 #include <fstream>
 #include <sstream>
 
 namespace b2 {
+
+// x = hi + lo with hi = x rounded to TF32 (10 explicit mantissa bits, nearest, ties away from
+// zero -- what cvt.rna.tf32.f32 does) and lo = tf32(x - hi); same split as b2tc::split_tf32
+static void split_tf32(float x, float& hi, float& lo)
+{
+  auto rna = [](float v) {
+    uint32_t u;
+    std::memcpy(&u, &v, 4);
+    if ((u & 0x7F800000u) != 0x7F800000u)
+      u = (u + 0x1000u) & 0xFFFFE000u;
+    float r;
+    std::memcpy(&r, &u, 4);
+    return r;
+  };
+  hi = rna(x);
+  lo = rna(x - hi);
+}
+
 
 // covalent radii used by the typewise ZBL cutoff (values: nep_utilities.cuh:143-154)
 const float COVALENT_RADIUS[94] = {
@@ -209,6 +229,43 @@ std::string NepModel::load(const char* path)
   const float b1 = para[p++];
   for (int t = 0; t < nt; ++t)
     bias[t] = (version == 5) ? bias[t] + b1 : b1; // nep_utilities.cuh:193, 309
+  // ---- tensor-core images of the hidden layer (layout documented in b2_nep_model.h) ----
+  HN = (nneu + 15) / 16 * 16;
+  DK = (dim + 7) / 8 * 8;
+  DN = (dim + 15) / 16 * 16;
+  tc_img_floats = 2 * HN * DK + 2 * DN * HN + 2 * HN;
+  {
+    int cols = 32;
+    while (cols < HN + DN)
+      cols <<= 1;
+    const size_t smem = (size_t)tc_img_floats * 4 + 2 * 128 * (size_t)(DK > HN ? DK : HN) * 4 + 64;
+    tc_ok = HN <= 256 && DN <= 256 && cols <= 512 && smem <= 200 * 1024;
+  }
+  if (tc_ok) {
+    tc_img.assign((size_t)nt * tc_img_floats, 0.0f);
+    for (int t = 0; t < nt; ++t) {
+      float* b1_hi = tc_img.data() + (size_t)t * tc_img_floats;
+      float* b1_lo = b1_hi + HN * DK;
+      float* b2_hi = b1_lo + HN * DK;
+      float* b2_lo = b2_hi + DN * HN;
+      float* ib0 = b2_lo + DN * HN;
+      float* iw1 = ib0 + HN;
+      for (int n = 0; n < nneu; ++n) {
+        for (int d = 0; d < dim; ++d) {
+          float hi, lo;
+          split_tf32(w0p[((size_t)t * nneu + n) * DIMP + d], hi, lo);
+          const size_t o1 = (size_t)n * 4 + (size_t)(d / 4) * (HN * 4) + (d % 4); // row n, column d
+          const size_t o2 = (size_t)d * 4 + (size_t)(n / 4) * (DN * 4) + (n % 4); // row d, column n
+          b1_hi[o1] = hi;
+          b1_lo[o1] = lo;
+          b2_hi[o2] = hi;
+          b2_lo[o2] = lo;
+        }
+        ib0[n] = b0[(size_t)t * nneu + n];
+        iw1[n] = w1[(size_t)t * nneu + n];
+      }
+    }
+  }
   // ---- expansion coefficients: file order [(n*(K+1)+k)*nt^2 + t1*nt + t2] ----
   c_r.assign((size_t)ntsq * nr1 * K1R, 0.0f);
   c_a.assign((size_t)ntsq * na1 * K1A, 0.0f);

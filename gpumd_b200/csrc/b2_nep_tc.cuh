@@ -1,0 +1,172 @@
+// b2_nep_tc.cuh -- the NEP hidden layer on the 5th-generation tensor cores (device only).
+//
+// apply_ann_one_layer (src/utilities/nep_utilities.cuh:166-193 of the reference) for 128 atoms of
+// ONE type at a time, as two GEMMs with a pointwise stage between them:
+//     Z  [128 x HN] = Q [128 x DK] . W0^T              (tcgen05.mma kind::tf32, 3xTF32 split)
+//     x  = tanh(Z - b0),  E = sum_j w1_j x_j - bias,   C_j = w1_j (1 - x_j^2)
+//     Fp [128 x DN] = C [128 x HN] . W0
+// Rows come from the type tiles the neighbour rebuild maintains (B2NeighborView::tile_*), so
+// every row of a tile shares W0.  The weights arrive as a ready-made shared-memory image
+// (NepModel::tc_img) by one TMA bulk copy; accumulators live in TMEM (HN + DN columns); thread r
+// of the 128-thread CTA owns row r = TMEM lane r in both epilogues.
+#pragma once
+#include "b2_nep.cuh"
+#include "b2_tc.cuh"
+
+namespace b2 {
+
+__host__ __device__ inline int b2_tc_tmem_cols(int HN, int DN)
+{
+  int c = 32;
+  while (c < HN + DN)
+    c <<= 1;
+  return c;
+}
+__host__ __device__ inline size_t b2_tc_img_bytes(int img_floats)
+{
+  return ((size_t)img_floats * 4 + 127) / 128 * 128;
+}
+__host__ __device__ inline size_t b2_tc_smem_bytes(int img_floats, int HN, int DK)
+{
+  return b2_tc_img_bytes(img_floats) + 2 * 128 * (size_t)(DK > HN ? DK : HN) * 4;
+}
+
+__global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
+{
+  extern __shared__ __align__(128) unsigned char tc_smem[];
+  __shared__ __align__(8) uint64_t bar_w, bar_mma;
+  __shared__ uint32_t tmem_slot;
+  const int tile = blockIdx.x;
+  if (tile >= P.tile_meta[0])
+    return;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int t = P.tile_type[tile];
+  const int i = P.tile_atom[tile * 128 + tid]; // -1 = padding row
+  const size_t N = (size_t)P.n;
+  const int HN = P.HN, DK = P.DK, DN = P.DN;
+  const int KA = DK > HN ? DK : HN;
+  float* img = reinterpret_cast<float*>(tc_smem);
+  const float* sb0 = img + 2 * HN * DK + 2 * DN * HN;
+  const float* sw1 = sb0 + HN;
+  unsigned char* a_hi = tc_smem + b2_tc_img_bytes(P.tc_img_floats);
+  unsigned char* a_lo = a_hi + (size_t)128 * KA * 4;
+  const uint32_t ncols = (uint32_t)b2_tc_tmem_cols(HN, DN);
+
+  if (warp == 0)
+    b2tc::tmem_alloc(&tmem_slot, ncols);
+  if (tid == 0) {
+    b2tc::mbar_init(&bar_w, 1);
+    b2tc::mbar_init(&bar_mma, 1);
+    const uint32_t bytes = (uint32_t)P.tc_img_floats * 4u;
+    b2tc::mbar_expect_tx(&bar_w, bytes);
+    b2tc::bulk_g2s(img, P.tc_img + (size_t)t * P.tc_img_floats, bytes, &bar_w);
+  }
+  // ---- stage Q (scaled descriptors) as the A operand: row tid, four columns per store ----
+  for (int k4 = 0; k4 < DK / 4; ++k4) {
+    float hi[4], lo[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const int d = 4 * k4 + c;
+      const float v = (i >= 0 && d < P.dim) ? P.q[(size_t)d * N + i] * __ldg(&P.q_scaler[d]) : 0.0f;
+      b2tc::split_tf32(v, hi[c], lo[c]);
+    }
+    const uint32_t off = (uint32_t)tid * 16u + (uint32_t)k4 * 2048u;
+    *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  }
+  b2tc::fence_async_smem();
+  b2tc::fence_before_sync();
+  __syncthreads();
+  b2tc::fence_after_sync();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t ah = b2tc::smem_u32(a_hi), al = b2tc::smem_u32(a_lo);
+  b2tc::mbar_wait(&bar_w, 0); // weights, b0, w1 have landed
+  if (tid == 0) {
+    // GEMM 1: Z = Q . W0^T   (B1: [HN rows x DK], K chunks HN*16 bytes apart)
+    const uint32_t idesc = b2tc::make_idesc_tf32(128, HN);
+    const uint32_t bh = b2tc::smem_u32(img), bl = bh + (uint32_t)HN * DK * 4u;
+    const uint32_t lbo_b = (uint32_t)HN * 16u;
+    for (int ks = 0; ks < DK / 8; ++ks) {
+      const uint64_t dah = b2tc::make_desc(ah + ks * 4096u, 2048u, 128u);
+      const uint64_t dal = b2tc::make_desc(al + ks * 4096u, 2048u, 128u);
+      const uint64_t dbh = b2tc::make_desc(bh + ks * 2u * lbo_b, lbo_b, 128u);
+      const uint64_t dbl = b2tc::make_desc(bl + ks * 2u * lbo_b, lbo_b, 128u);
+      b2tc::mma_tf32(tmem, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+      b2tc::mma_tf32(tmem, dah, dbl, idesc, 1u);
+      b2tc::mma_tf32(tmem, dah, dbh, idesc, 1u);
+    }
+    b2tc::mma_commit(&bar_mma);
+  }
+  b2tc::mbar_wait(&bar_mma, 0);
+  b2tc::fence_after_sync();
+  // ---- epilogue 1: activation, site energy, and C as the A operand of GEMM 2 ----
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
+  float F = 0.0f;
+  for (int c0 = 0; c0 < HN; c0 += 16) {
+    uint32_t v[16];
+    b2tc::tmem_ld16(tmem + lane_base + (uint32_t)c0, v);
+#pragma unroll
+    for (int g = 0; g < 4; ++g) {
+      float hi[4], lo[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const int j = c0 + 4 * g + c;
+        const float x1 = tanhf(__uint_as_float(v[4 * g + c]) - sb0[j]);
+        const float w1j = sw1[j];
+        F = fmaf(w1j, x1, F);
+        b2tc::split_tf32(w1j * (1.0f - x1 * x1), hi[c], lo[c]);
+      }
+      const uint32_t off = (uint32_t)tid * 16u + (uint32_t)(c0 / 4 + g) * 2048u;
+      *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+    }
+  }
+  b2tc::fence_async_smem();
+  b2tc::fence_before_sync();
+  __syncthreads();
+  b2tc::fence_after_sync();
+  if (tid == 0) {
+    // GEMM 2: Fp = C . W0   (B2: [DN rows x HN], K chunks DN*16 bytes apart), D at column HN
+    const uint32_t idesc = b2tc::make_idesc_tf32(128, DN);
+    const uint32_t bh = b2tc::smem_u32(img) + 2u * HN * DK * 4u, bl = bh + (uint32_t)DN * HN * 4u;
+    const uint32_t lbo_b = (uint32_t)DN * 16u;
+    for (int ks = 0; ks < HN / 8; ++ks) {
+      const uint64_t dah = b2tc::make_desc(ah + ks * 4096u, 2048u, 128u);
+      const uint64_t dal = b2tc::make_desc(al + ks * 4096u, 2048u, 128u);
+      const uint64_t dbh = b2tc::make_desc(bh + ks * 2u * lbo_b, lbo_b, 128u);
+      const uint64_t dbl = b2tc::make_desc(bl + ks * 2u * lbo_b, lbo_b, 128u);
+      b2tc::mma_tf32(tmem + (uint32_t)HN, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+      b2tc::mma_tf32(tmem + (uint32_t)HN, dah, dbl, idesc, 1u);
+      b2tc::mma_tf32(tmem + (uint32_t)HN, dah, dbh, idesc, 1u);
+    }
+    b2tc::mma_commit(&bar_mma);
+  }
+  b2tc::mbar_wait(&bar_mma, 1);
+  b2tc::fence_after_sync();
+  // ---- epilogue 2: dU/dq (times q_scaler), radial part for k_utable, angular part for the rest ----
+  for (int c0 = 0; c0 < DN; c0 += 16) {
+    uint32_t v[16];
+    b2tc::tmem_ld16(tmem + lane_base + (uint32_t)(HN + c0), v);
+    if (i >= 0) {
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const int d = c0 + c;
+        if (d < P.dim) {
+          const float f = __uint_as_float(v[c]) * __ldg(&P.q_scaler[d]);
+          if (d < P.nr1)
+            P.FpR[(size_t)d * N + i] = f;
+          else
+            P.FpA[(size_t)(d - P.nr1) * N + i] = f;
+        }
+      }
+    }
+  }
+  if (i >= 0)
+    P.acc[i] = (double)(F - __ldg(&P.bias[t]));
+  b2tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0)
+    b2tc::tmem_dealloc(tmem, ncols);
+}
+
+} // namespace b2

@@ -225,6 +225,17 @@ int b200md_halo_pack(
   double* d_out, void* stream);
 int b200md_nep_invalidate(b200md_nep* p, int n_new, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Tensor-core self-test (no reference counterpart): one CTA computes D[128 x N] = A[128 x K] .
+ * B[N x K]^T on the 5th-generation tensor cores (tcgen05.mma kind::tf32, 3xTF32 split, FP32
+ * accumulators in TMEM) exactly as the NEP hidden-layer kernel issues it.  Row-major device
+ * arrays; 16 <= N <= 256, N % 16 == 0, K % 8 == 0; layout 0 / 1 = the two shared-memory operand
+ * arrangements of b2_tc.cuh (1 is the hidden layer's).  Used by tests/ to validate the descriptor
+ * and TMEM plumbing against a host GEMM.
+ * ------------------------------------------------------------------------------------------- */
+int b200md_tc_selftest(
+  int layout, int N, int K, const float* d_A, const float* d_B, float* d_D, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

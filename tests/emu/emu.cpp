@@ -282,8 +282,6 @@ int emu_nep_compute(
   P.nn_skin = p->nb.nn_skin.data();
   P.nl_skin = p->nb.nl_skin.data();
   P.flags = p->nb.flags.data();
-  for (int i = 0; i < n; ++i)
-    b2_body_split(i, P, box);
   switch (p->m.K1R) {
     case 9: run_desc_radial<9>(p, box); break;
     case 13: run_desc_radial<13>(p, box); break;

@@ -58,9 +58,12 @@ class GpuNep:
         return self.pot.num_rebuilds
 
 
+@pytest.mark.parametrize("mlp", ["tc", "simt"])
 @pytest.mark.parametrize("case", list(NEP_CASES))
-def test_nep_matches_oracle(oracle, eng, case):
+def test_nep_matches_oracle(oracle, eng, case, mlp, monkeypatch):
+    """mlp: hidden layer on the tensor cores (k_mlp_tc, the default) or the SIMT kernel (k_mlp)."""
     from test_kernel_bodies_cpu import check_nep
+    monkeypatch.setenv("B200MD_NEP_MLP", mlp)
     model, make = NEP_CASES[case]
     s = make()
     n = s["type"].shape[0]
@@ -302,8 +305,11 @@ def test_eam_matches_oracle(oracle, eng, potfile):
     pe = atom.potential_per_atom.cpu().numpy()
     assert_close(pe, r["pe"], rtol=1e-5, atol=1e-5, what="pe")
     assert abs(pe.sum() - r["pe"].sum()) / n < 2e-6
+    # Dai-2006's pair function is a degree-6 polynomial whose terms cancel to ~1e-2 of their size:
+    # FP32 summation-order noise on force/virial is ~3x that of the other models
     check_fv(dict(force=atom.force_per_atom.cpu().numpy().reshape(3, n),
-                  virial=atom.virial_per_atom.cpu().numpy().reshape(9, n)), r)
+                  virial=atom.virial_per_atom.cpu().numpy().reshape(9, n)), r,
+             noise=4.0 if "Dai" in potfile else 1.0)
 
 
 def test_eam_matches_reference_gpu_single_point(eng):
