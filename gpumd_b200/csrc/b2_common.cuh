@@ -29,6 +29,34 @@ struct float4 {
 #define B2_ATOMIC_OR(p, v) (*(p) |= (v))
 #endif
 
+// ---- lane teams: kernels that spread ONE atom's neighbour loop over B2_TEAM adjacent lanes.
+// Consecutive list entries are (mostly) consecutive cell-sorted atoms, so a team's gathers fall
+// into a few 128-byte lines instead of one line per lane.  The host build (tests/emu) uses a team
+// of one, for which every primitive is the identity.
+#if defined(__CUDACC__)
+#define B2_TEAM 8
+__device__ __forceinline__ unsigned b2_team_mask() { return 0xFFu << (threadIdx.x & 24u); }
+__device__ __forceinline__ float b2_team_sum(float v)
+{
+  const unsigned m = b2_team_mask();
+  v += __shfl_xor_sync(m, v, 1);
+  v += __shfl_xor_sync(m, v, 2);
+  v += __shfl_xor_sync(m, v, 4);
+  return v;
+}
+// bit l = predicate of team lane l
+__device__ __forceinline__ unsigned b2_team_ballot(bool p)
+{
+  return (__ballot_sync(b2_team_mask(), p) >> (threadIdx.x & 24u)) & 0xFFu;
+}
+#define B2_POPC(x) __popc(x)
+#else
+#define B2_TEAM 1
+static inline float b2_team_sum(float v) { return v; }
+static inline unsigned b2_team_ballot(bool p) { return p ? 1u : 0u; }
+#define B2_POPC(x) __builtin_popcount(x)
+#endif
+
 // Box passed by value to kernels: GPUMD's Box::cpu_h / float_h (src/model/box.cuh:18-35).
 constexpr int B2_MAX_TYPES = 94; // NUM_ELEMENTS, src/utilities/common.cuh:18
 

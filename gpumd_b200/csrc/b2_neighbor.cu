@@ -308,7 +308,7 @@ int Neighbor::init(int num_atoms, double rc_, int mn_skin_)
   B2_CUDA(cell_of.reserve(n));
   B2_CUDA(order_tmp.reserve(n));
   B2_CUDA(nn_skin.reserve(n));
-  B2_CUDA(nl_skin.reserve((size_t)mn_skin * n));
+  B2_CUDA(nl_skin.reserve((size_t)skin_pitch() * n));
   B2_CUDA(flags.reserve(4));
   B2_CUDA(cudaMemset(snap.p, 0, sizeof(double) * 3 * (size_t)n));
   k_init_perm<<<grid_for(n, BLK), BLK>>>(n, perm.p, flags.p);
@@ -334,6 +334,8 @@ B2NeighborView Neighbor::view() const
   v.cell_start = cell_start.p;
   v.nn_skin = nn_skin.p;
   v.nl_skin = nl_skin.p;
+  v.skin_si = skin_row_major ? (size_t)skin_pitch() : 1;
+  v.skin_sk = skin_row_major ? 1 : (size_t)n;
   v.flags = flags.p;
   v.tile_nt = tile_nt;
   v.tile_nblk = grid_for(n, BLK);

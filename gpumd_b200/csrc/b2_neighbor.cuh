@@ -38,7 +38,10 @@ struct B2NeighborView {
   int* cell_fill;    // [ncell_cap]
   int* cell_start;   // [ncell_cap+1]
   int* nn_skin;      // [n]
-  int* nl_skin;      // [mn_skin * n]  column-major nl[k*n + i]
+  int* nl_skin;      // entry k of atom i at nl_skin[i*skin_si + k*skin_sk]: column-major
+                     // (si = 1, sk = n) for thread-per-atom kernels, row-major (si = pitch,
+                     // sk = 1) for kernels that spread one atom's neighbours over lanes
+  size_t skin_si = 1, skin_sk = 0;
   int* flags;        // [0] rebuild requested, [1] error bits, [2] rebuild counter
   // optional type tiles (Neighbor::enable_type_tiles): the sorted atoms bucketed by type, every
   // bucket padded to a multiple of 128 slots -- row blocks of the tensor-core hidden layer
@@ -191,7 +194,7 @@ B2_HD void b2_body_skin_list(
           b2_r12(geo, box, a1, v.atoms[j], x12, y12, z12);
           if (b2_d2(x12, y12, z12) < cutoff2) {
             if (count < v.mn_skin)
-              v.nl_skin[(size_t)count * v.n + i] = j;
+              v.nl_skin[(size_t)i * v.skin_si + (size_t)count * v.skin_sk] = j;
             ++count;
           }
         }

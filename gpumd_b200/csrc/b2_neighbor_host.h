@@ -13,6 +13,8 @@ public:
   int n = 0;        // atoms of the current system (<= capacity)
   int capacity = 0; // atoms the buffers were sized for
   int mn_skin = 0;
+  bool skin_row_major = false; // set before init(): rows of skin_pitch() ints instead of columns
+  int skin_pitch() const { return (mn_skin + 7) / 8 * 8; }
   double rc = 0.0;
   double skin = 1.0; // src/force/neighbor.cuh:212
   B2Grid grid;

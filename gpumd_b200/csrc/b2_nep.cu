@@ -18,13 +18,38 @@ namespace {
 constexpr int BLK = 128;
 constexpr int MLP_BLK = 256;
 
-template <int NT, int K1>
+__global__ void __launch_bounds__(BLK) k_split(B2NepView P, B2Box box)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < P.n)
+    b2_body_split(i, P, box);
+}
+
+template <int NT, int K1, bool SPLIT>
 __global__ void __launch_bounds__(BLK) k_desc_radial(B2NepView P, B2Box box)
 {
   extern __shared__ float dyn_smem[];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < P.n)
-    b2_body_desc_radial<NT, K1>(i, P, box, dyn_smem, blockDim.x, threadIdx.x);
+    b2_body_desc_radial<NT, K1, SPLIT>(i, P, box, dyn_smem, blockDim.x, threadIdx.x);
+}
+
+// lane-team kernels: B2_TEAM adjacent lanes per atom, BLK / B2_TEAM atoms per block
+template <int NT, int K1>
+__global__ void __launch_bounds__(BLK) k_team_desc_radial(B2NepView P, B2Box box)
+{
+  const int i = blockIdx.x * (BLK / B2_TEAM) + threadIdx.x / B2_TEAM;
+  if (i < P.n)
+    b2_team_desc_radial<NT, K1>(i, threadIdx.x % B2_TEAM, P, box);
+}
+
+template <int NT, int K1>
+__global__ void __launch_bounds__(BLK)
+  k_team_force_final(B2NepView P, B2Box box, double* pe, double* force, double* virial)
+{
+  const int i = blockIdx.x * (BLK / B2_TEAM) + threadIdx.x / B2_TEAM;
+  if (i < P.n)
+    b2_team_force_final<NT, K1>(i, threadIdx.x % B2_TEAM, P, box, pe, force, virial);
 }
 
 template <int K1, int NCH>
@@ -98,12 +123,17 @@ template <int K1>
 __global__ void __launch_bounds__(BLK) k_utable(B2NepView P)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < P.n)
+  if (i >= P.n)
+    return;
+  if (P.team)
+    b2_body_utable_planes<K1>(i, P);
+  else
     b2_body_utable<K1>(i, P);
 }
 
-template <int NT, int K1>
-__global__ void __launch_bounds__(BLK)
+// MINB: resident blocks per SM the register allocation is tuned for (latency hiding vs spills)
+template <int NT, int K1, int MINB>
+__global__ void __launch_bounds__(BLK, MINB)
   k_force_final(B2NepView P, B2Box box, double* pe, double* force, double* virial)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -122,8 +152,8 @@ __global__ void __launch_bounds__(BLK) k_force_angular(B2NepView P, B2Box box)
 
 // parity hooks ---------------------------------------------------------------------------------
 __global__ void k_export_list(
-  int n, const int* perm, const int* nn, const int* nl, int mn_out, int* NN_out, int* NL_out,
-  int* flags)
+  int n, const int* perm, const int* nn, const int* nl, size_t si, size_t sk, int mn_out,
+  int* NN_out, int* NL_out, int* flags)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n)
@@ -136,7 +166,7 @@ __global__ void k_export_list(
   }
   int* row = NL_out + (size_t)a * mn_out;
   for (int k = 0; k < cnt; ++k) { // insertion sort into ascending caller index
-    const int v = perm[nl[(size_t)k * n + i]];
+    const int v = perm[nl[(size_t)i * si + (size_t)k * sk]];
     int q = k - 1;
     while (q >= 0 && row[q] > v) {
       row[q + 1] = row[q];
@@ -184,6 +214,9 @@ struct b200md_nep {
   DevBuf<float> q, sfx, FpR, FpA, U, f12;
   DevBuf<double> acc;
   DevBuf<float> tc_img;
+  int num_sms = 148;
+  int variant = 0;         // B200MD_NEP_VARIANT: kernel tuning variants for A/B measurements
+  bool fuse_split = false; // many-type path: neighbour split inside the radial descriptor pass
   bool use_tc = false; // hidden layer on the tensor cores (k_mlp_tc) instead of k_mlp
   // staging for the host-buffer entry point
   DevBuf<int> h_type;
@@ -196,10 +229,11 @@ struct b200md_nep {
 
 namespace {
 
-template <int NT, int K1>
+// thread per atom; NT = 0: per-type accumulators in shared memory (many types)
+template <int NT, int K1, bool SPLIT>
 int launch_desc_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
 {
-  auto kern = k_desc_radial<NT, K1>;
+  auto kern = k_desc_radial<NT, K1, SPLIT>;
   if (NT == 0 && p->rad_smem > 48 * 1024)
     B2_CUDA(cudaFuncSetAttribute(
       kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->rad_smem));
@@ -211,18 +245,36 @@ int launch_desc_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
 template <int K1>
 int dispatch_desc_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
 {
-  switch (p->model.nt) {
-    case 1: return launch_desc_radial<1, K1>(p, box, st);
-    case 2: return launch_desc_radial<2, K1>(p, box, st);
-    default: return launch_desc_radial<0, K1>(p, box, st);
+  const int team_grid = grid_for(p->n, BLK / B2_TEAM);
+  if (p->view.team && p->model.nt == 1) {
+    k_team_desc_radial<1, K1><<<team_grid, BLK, 0, st>>>(p->view, box);
+  } else if (p->view.team) {
+    k_team_desc_radial<2, K1><<<team_grid, BLK, 0, st>>>(p->view, box);
+  } else if (p->model.nt == 1) {
+    return launch_desc_radial<1, K1, true>(p, box, st);
+  } else if (p->model.nt == 2) {
+    return launch_desc_radial<2, K1, true>(p, box, st);
+  } else if (p->fuse_split) {
+    return launch_desc_radial<0, K1, true>(p, box, st);
+  } else {
+    k_split<<<grid_for(p->n, BLK), BLK, 0, st>>>(p->view, box);
+    B2_LAUNCHED();
+    return launch_desc_radial<0, K1, false>(p, box, st);
   }
+  B2_LAUNCHED();
+  return B200MD_OK;
 }
 
 template <int NT, int K1>
 int launch_force_final(
   const b200md_nep* p, const B2Box& box, cudaStream_t st, double* pe, double* f, double* v)
 {
-  k_force_final<NT, K1><<<grid_for(p->n, BLK), BLK, 0, st>>>(p->view, box, pe, f, v);
+  const int g = grid_for(p->n, BLK);
+  switch (p->variant) {
+    case 1: k_force_final<NT, K1, 6><<<g, BLK, 0, st>>>(p->view, box, pe, f, v); break;
+    case 2: k_force_final<NT, K1, 8><<<g, BLK, 0, st>>>(p->view, box, pe, f, v); break;
+    default: k_force_final<NT, K1, 5><<<g, BLK, 0, st>>>(p->view, box, pe, f, v); break;
+  }
   B2_LAUNCHED();
   return B200MD_OK;
 }
@@ -231,11 +283,19 @@ template <int K1>
 int dispatch_force_final(
   const b200md_nep* p, const B2Box& box, cudaStream_t st, double* pe, double* f, double* v)
 {
-  switch (p->model.nt) {
-    case 1: return launch_force_final<1, K1>(p, box, st, pe, f, v);
-    case 2: return launch_force_final<2, K1>(p, box, st, pe, f, v);
-    default: return launch_force_final<0, K1>(p, box, st, pe, f, v);
-  }
+  const int team_grid = grid_for(p->n, BLK / B2_TEAM);
+  if (p->view.team && p->model.nt == 1)
+    k_team_force_final<1, K1><<<team_grid, BLK, 0, st>>>(p->view, box, pe, f, v);
+  else if (p->view.team)
+    k_team_force_final<2, K1><<<team_grid, BLK, 0, st>>>(p->view, box, pe, f, v);
+  else if (p->model.nt == 1)
+    return launch_force_final<1, K1>(p, box, st, pe, f, v);
+  else if (p->model.nt == 2)
+    return launch_force_final<2, K1>(p, box, st, pe, f, v);
+  else
+    return launch_force_final<0, K1>(p, box, st, pe, f, v);
+  B2_LAUNCHED();
+  return B200MD_OK;
 }
 
 template <int K1>
@@ -309,7 +369,14 @@ int nep_pipeline(
     if (bytes > 48 * 1024)
       B2_CUDA(cudaFuncSetAttribute(
         k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
-    k_mlp_tc<<<p->nb.max_tiles(), 128, bytes, st>>>(p->view);
+    // persistent CTAs: as many as fit per SM (shared memory, TMEM columns), each walking tiles
+    int per_sm = (int)((size_t)220 * 1024 / (bytes + 2048));
+    const int by_tmem = 512 / b2_tc_tmem_cols(p->model.HN, p->model.DN);
+    per_sm = per_sm < by_tmem ? per_sm : by_tmem;
+    per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
+    const int tiles = p->nb.max_tiles();
+    const int ctas = tiles < p->num_sms * per_sm ? tiles : p->num_sms * per_sm;
+    k_mlp_tc<<<ctas, 128, bytes, st>>>(p->view);
     B2_LAUNCHED();
   } else
   switch (p->model.DIMP) {
@@ -373,10 +440,21 @@ int nep_setup(b200md_nep* p, int num_atoms)
   const double rc = m.rc_radial_max;
   const double rs = rc + 1.0;
   const int mn_skin = (int)(m.MN_radial * rs * rs * rs / (rc * rc * rc));
+  // radial passes: thread per atom by default.  B200MD_NEP_TEAM=1 selects the lane-team kernels
+  // for one- and two-type models: they cut the L1 gather wavefronts ~3x (profiles/r01_f_*) but
+  // cost ~30% more instructions and are currently slower (1.42 vs 1.02 ms on the final kernel).
+  const char* team_env = std::getenv("B200MD_NEP_TEAM");
+  const bool team = m.nt <= 2 && team_env && std::strcmp(team_env, "1") == 0;
+  p->nb.skin_row_major = team;
+  if (const char* v = std::getenv("B200MD_NEP_VARIANT"))
+    p->variant = std::atoi(v);
+  // fused split pays when few skin candidates fail the radial test: (rc+skin)^3 / rc^3 small
+  p->fuse_split = rs * rs * rs / (rc * rc * rc) < 1.45;
   B2_TRY(p->nb.init(num_atoms, rc, mn_skin));
+  const int pitch_r = (m.MN_radial + 7) / 8 * 8;
 
   B2_CUDA(p->nn_r.reserve(N));
-  B2_CUDA(p->nl_r.reserve(N * m.MN_radial));
+  B2_CUDA(p->nl_r.reserve(N * (size_t)pitch_r));
   B2_CUDA(p->nn_a.reserve(N));
   B2_CUDA(p->nl_a.reserve(N * m.MN_angular));
   B2_CUDA(p->q.reserve(N * m.dim));
@@ -446,11 +524,21 @@ int nep_setup(b200md_nep* p, int num_atoms)
   P.f12 = p->f12.p;
   P.acc = p->acc.p;
   P.flags = p->nb.flags.p;
+  P.team = team ? 1 : 0;
+  P.pitch_r = pitch_r;
+  {
+    const B2NeighborView nv = p->nb.view();
+    P.skin_si = nv.skin_si;
+    P.skin_sk = nv.skin_sk;
+  }
   // hidden layer: tensor cores unless the shapes do not fit or B200MD_NEP_MLP=simt asks for the
   // SIMT kernel (kept for A/B measurements and for exotic layer sizes)
   const char* mlp_env = std::getenv("B200MD_NEP_MLP");
   p->use_tc = m.tc_ok && !(mlp_env && std::strcmp(mlp_env, "simt") == 0);
   if (p->use_tc) {
+    int dev = 0;
+    B2_CUDA(cudaGetDevice(&dev));
+    B2_CUDA(cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev));
     B2_TRY(p->nb.enable_type_tiles(m.nt));
     B2_TRY(upload(p->tc_img, m.tc_img));
     P.tc_img = p->tc_img.p;
@@ -553,6 +641,8 @@ int b200md_nep_compute(
   B2_TRY(p->nb.update(box, d_type, d_position, n, st));
   p->n = n; // n may be anything up to the capacity given at construction (domain decomposition)
   p->view.n = n;
+  if (!p->view.team)
+    p->view.skin_sk = (size_t)n; // column-major skin list: entry stride = current atom count
   p->prof.end(st, ST_NEIGHBOR);
   B2_TRY(nep_pipeline(p, box, st, d_potential, d_force, d_virial));
   return B200MD_OK;
@@ -589,12 +679,13 @@ int b200md_nep_export_neighbors(
   const int n = p->n;
   if (d_NN_r && d_NL_r) {
     k_export_list<<<grid_for(n, 128), 128, 0, st>>>(
-      n, p->nb.perm.p, p->nn_r.p, p->nl_r.p, mn_r, d_NN_r, d_NL_r, p->nb.flags.p);
+      n, p->nb.perm.p, p->nn_r.p, p->nl_r.p, p->view.team ? (size_t)p->view.pitch_r : 1,
+      p->view.team ? 1 : (size_t)n, mn_r, d_NN_r, d_NL_r, p->nb.flags.p);
     B2_LAUNCHED();
   }
   if (d_NN_a && d_NL_a) {
     k_export_list<<<grid_for(n, 128), 128, 0, st>>>(
-      n, p->nb.perm.p, p->nn_a.p, p->nl_a.p, mn_a, d_NN_a, d_NL_a, p->nb.flags.p);
+      n, p->nb.perm.p, p->nn_a.p, p->nl_a.p, 1, (size_t)n, mn_a, d_NN_a, d_NL_a, p->nb.flags.p);
     B2_LAUNCHED();
   }
   return B200MD_OK;

@@ -90,6 +90,10 @@ struct B2NepView {
   float* f12; // [3 * mn_a * n]
   double* acc; // [13 * n]: pe, fx,fy,fz, virial xx,yy,zz,xy,xz,yz,yx,zx,zy (sorted order)
   int* flags;
+  // ---- lane-team path (<= 2 types): row-major skin / radial lists, U table as float4 planes ----
+  size_t skin_si, skin_sk; // B2NeighborView::skin_si / skin_sk
+  int pitch_r;             // row pitch of nl_r when team != 0 (else nl_r is column-major)
+  int team;                // 1: k_team_* kernels own the radial passes
   // ---- tensor-core hidden layer (k_mlp_tc; null / 0 when the SIMT k_mlp is used) ----
   const float* tc_img;  // [nt][tc_img_floats] shared-memory images, see NepModel::tc_img
   int tc_img_floats, HN, DK, DN;
@@ -97,6 +101,55 @@ struct B2NepView {
   const int* tile_type;
   const int* tile_meta;
 };
+
+// ---------------------------------------------------------------------------------------------
+// neighbour-set split: find_neighbor_list_large_box, nep.cu:436-486
+// ---------------------------------------------------------------------------------------------
+B2_HD void b2_body_split(int i, const B2NepView& P, const B2Box& box)
+{
+  const B2Geo geo = b2_geo(box);
+  const size_t N = (size_t)P.n;
+  const B2Atom a1 = P.atoms[i];
+  const int nn = P.nn_skin[i];
+  const int row = a1.type * P.nt;
+  int cr = 0, ca = 0;
+  // software pipeline: the record of candidate k+1 and the index of candidate k+2 are in flight
+  // while candidate k is tested (the loads are dependent: index -> record)
+  int jn = nn > 0 ? P.nl_skin[i] : i;
+  B2Atom an = b2_load_atom(&P.atoms[jn]);
+  int j2 = nn > 1 ? P.nl_skin[N + i] : i;
+  for (int k = 0; k < nn; ++k) {
+    const int j = jn;
+    const B2Atom a2 = an;
+    jn = j2;
+    an = b2_load_atom(&P.atoms[jn]);
+    j2 = (k + 2 < nn) ? P.nl_skin[(size_t)(k + 2) * N + i] : i;
+    float x12, y12, z12;
+    b2_r12(geo, box, a1, a2, x12, y12, z12);
+    const float d2 = b2_d2(x12, y12, z12);
+    const int pair = row + a2.type;
+    if (d2 >= B2_LDG(&P.rc2_r[pair]))
+      continue;
+    if (cr < P.mn_r)
+      P.nl_r[(size_t)cr * N + i] = j;
+    ++cr;
+    if (d2 < B2_LDG(&P.rc2_a[pair])) {
+      if (ca < P.mn_a)
+        P.nl_a[(size_t)ca * N + i] = j;
+      ++ca;
+    }
+  }
+  if (cr > P.mn_r) {
+    B2_ATOMIC_OR(&P.flags[1], (int)B2_ERR_RADIAL_OVERFLOW);
+    cr = P.mn_r;
+  }
+  if (ca > P.mn_a) {
+    B2_ATOMIC_OR(&P.flags[1], (int)B2_ERR_ANGULAR_OVERFLOW);
+    ca = P.mn_a;
+  }
+  P.nn_r[i] = cr;
+  P.nn_a[i] = ca;
+}
 
 // ---------------------------------------------------------------------------------------------
 // radial basis.  fc, fc' : nep_utilities.cuh:409-431;  fn, fn' : nep_utilities.cuh:572-623
@@ -165,18 +218,19 @@ B2_HD void b2_basis_d(float d, float rc, float rcinv, float* fn, float* fnp)
 // NT > 0: per-type accumulators in registers (models with <= NT types); NT == 0: accumulators in
 // the caller-provided scratch `acc` laid out [(t2*K1+k)*stride + lane].
 // ---------------------------------------------------------------------------------------------
-// The neighbour-set split (find_neighbor_list_large_box, nep.cu:436-486) is fused into this pass:
-// the loop walks the skin list, applies the reference's two FP32 membership tests and emits the
-// radial / angular lists (ascending, like the reference's) for the later kernels on the way.
-template <int NT, int K1>
+// SPLIT = true fuses the neighbour-set split (b2_body_split) into this pass: the loop then walks
+// the skin list, applies the reference's two FP32 membership tests and emits the radial /
+// angular lists on the way.  That pays when few skin candidates fail the test (large rc); with a
+// small rc the idle lanes cost more than the separate cheap kernel.
+template <int NT, int K1, bool SPLIT>
 B2_HD void b2_body_desc_radial(
   int i, const B2NepView& P, const B2Box& box, float* acc, int stride, int lane)
 {
   const B2Geo geo = b2_geo(box);
   const B2Atom a1 = P.atoms[i];
   const int t1 = a1.type;
-  const int nn = P.nn_skin[i];
-  const int* list = P.nl_skin;
+  const int nn = SPLIT ? P.nn_skin[i] : P.nn_r[i];
+  const int* list = SPLIT ? P.nl_skin : P.nl_r;
   int cr = 0, ca = 0;
   float S[NT > 0 ? NT : 1][K1];
   if (NT > 0) {
@@ -203,15 +257,17 @@ B2_HD void b2_body_desc_radial(
     const float d2 = b2_d2(x12, y12, z12);
     const int t2 = a2.type;
     const int pair = t1 * P.nt + t2;
-    if (d2 >= B2_LDG(&P.rc2_r[pair]))
-      continue;
-    if (cr < P.mn_r)
-      P.nl_r[(size_t)cr * P.n + i] = j;
-    ++cr;
-    if (d2 < B2_LDG(&P.rc2_a[pair])) {
-      if (ca < P.mn_a)
-        P.nl_a[(size_t)ca * P.n + i] = j;
-      ++ca;
+    if (SPLIT) {
+      if (d2 >= B2_LDG(&P.rc2_r[pair]))
+        continue;
+      if (cr < P.mn_r)
+        P.nl_r[(size_t)cr * P.n + i] = j;
+      ++cr;
+      if (d2 < B2_LDG(&P.rc2_a[pair])) {
+        if (ca < P.mn_a)
+          P.nl_a[(size_t)ca * P.n + i] = j;
+        ++ca;
+      }
     }
     const float d = sqrtf(d2);
     float fn[K1];
@@ -235,16 +291,18 @@ B2_HD void b2_body_desc_radial(
         a[(size_t)k * stride] += fn[k];
     }
   }
-  if (cr > P.mn_r) {
-    B2_ATOMIC_OR(&P.flags[1], (int)B2_ERR_RADIAL_OVERFLOW);
-    cr = P.mn_r;
+  if (SPLIT) {
+    if (cr > P.mn_r) {
+      B2_ATOMIC_OR(&P.flags[1], (int)B2_ERR_RADIAL_OVERFLOW);
+      cr = P.mn_r;
+    }
+    if (ca > P.mn_a) {
+      B2_ATOMIC_OR(&P.flags[1], (int)B2_ERR_ANGULAR_OVERFLOW);
+      ca = P.mn_a;
+    }
+    P.nn_r[i] = cr;
+    P.nn_a[i] = ca;
   }
-  if (ca > P.mn_a) {
-    B2_ATOMIC_OR(&P.flags[1], (int)B2_ERR_ANGULAR_OVERFLOW);
-    ca = P.mn_a;
-  }
-  P.nn_r[i] = cr;
-  P.nn_a[i] = ca;
   // contraction with the expansion coefficients
   for (int n = 0; n < P.nr1; ++n) {
     float q = 0.0f;
@@ -530,6 +588,37 @@ B2_HD void b2_body_utable(int i, const B2NepView& P)
   }
 }
 
+// same contraction, written as float4 planes U4[(t2*KP/4 + q)*n + i] for the lane-team radial force
+template <int K1>
+B2_HD void b2_body_utable_planes(int i, const B2NepView& P)
+{
+  constexpr int KP4 = (K1 + 3) / 4;
+  const int t = P.atoms[i].type;
+  float4* U4 = reinterpret_cast<float4*>(P.U);
+  for (int t2 = 0; t2 < P.nt; ++t2) {
+    const float* c = P.c_r + (size_t)(t * P.nt + t2) * P.nr1 * K1;
+    float u[KP4 * 4];
+#pragma unroll
+    for (int k = 0; k < KP4 * 4; ++k)
+      u[k] = 0.0f;
+    for (int n = 0; n < P.nr1; ++n) {
+      const float f = P.FpR[(size_t)n * P.n + i];
+#pragma unroll
+      for (int k = 0; k < K1; ++k)
+        u[k] = fmaf(f, B2_LDG(&c[n * K1 + k]), u[k]);
+    }
+#pragma unroll
+    for (int q = 0; q < KP4; ++q) {
+      float4 v;
+      v.x = u[4 * q];
+      v.y = u[4 * q + 1];
+      v.z = u[4 * q + 2];
+      v.w = u[4 * q + 3];
+      U4[(size_t)(t2 * KP4 + q) * P.n + i] = v;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // radial force (find_force_radial, nep.cu:661-772) in the pre-contracted form:
 //   F_i   += (A + B) * r12 / d,   A = fn'(d) . U_i[t_j],  B = fn'(d) . U_j[t_i]
@@ -788,7 +877,9 @@ B2_HD void b2_body_force_angular(
 // (gpu_find_force_many_body, src/force/potential.cu:170-297; the reverse slot is found by binary
 // search in j's ascending list, potential.cu:226-247)
 // ---------------------------------------------------------------------------------------------
-B2_HD void b2_reduce_angular_sum(int i, const B2NepView& P, const B2Box& box, float* out)
+// m0 / mstep: the neighbours m0, m0+mstep, ... are summed (0, 1 = all; a lane team passes lane, B2_TEAM)
+B2_HD void b2_reduce_angular_sum(
+  int i, const B2NepView& P, const B2Box& box, float* out, int m0 = 0, int mstep = 1)
 {
   const size_t N = (size_t)P.n;
   const size_t plane = (size_t)P.mn_a * N;
@@ -796,7 +887,7 @@ B2_HD void b2_reduce_angular_sum(int i, const B2NepView& P, const B2Box& box, fl
   const int nn = P.nn_a[i];
   float f[3] = {0.0f, 0.0f, 0.0f};
   float v[9] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f}; // row-major r (x) f21
-  for (int m = 0; m < nn; ++m) {
+  for (int m = m0; m < nn; m += mstep) {
     const size_t slot = (size_t)m * N + i;
     const int j = P.nl_a[slot];
     const B2Atom a2 = P.atoms[j];
@@ -877,7 +968,8 @@ B2_HD void b2_zbl_pair(
   f = phi * fc;
 }
 
-B2_HD void b2_zbl_sum(int i, const B2NepView& P, const B2Box& box, float* out, float& pe_out)
+B2_HD void b2_zbl_sum(
+  int i, const B2NepView& P, const B2Box& box, float* out, float& pe_out, int m0 = 0, int mstep = 1)
 {
   const size_t N = (size_t)P.n;
   const B2Geo geo = b2_geo(box);
@@ -888,7 +980,7 @@ B2_HD void b2_zbl_sum(int i, const B2NepView& P, const B2Box& box, float* out, f
   const int nn = P.nn_a[i];
   float pe = 0.0f, f[3] = {0.0f, 0.0f, 0.0f};
   float vxx = 0.0f, vyy = 0.0f, vzz = 0.0f, vxy = 0.0f, vxz = 0.0f, vyz = 0.0f;
-  for (int m = 0; m < nn; ++m) {
+  for (int m = m0; m < nn; m += mstep) {
     const int j = P.nl_a[(size_t)m * N + i];
     const B2Atom a2 = b2_load_atom(&P.atoms[j]);
     float x12, y12, z12;
@@ -977,6 +1069,271 @@ B2_HD void b2_body_force_final(
 #pragma unroll
   for (int k = 0; k < 9; ++k)
     virial[k * N + dst] += (double)r[3 + k] + (double)a[3 + k] + (double)z[3 + k];
+}
+
+// =============================================================================================
+// Lane-team variants of the two radial passes (models with <= 2 types, NT = number of types).
+// Team lane l of atom i handles list entries l, l+B2_TEAM, ...; partial sums are combined with
+// b2_team_sum.  Lists: skin and radial row-major (see B2NepView::skin_si / pitch_r), angular
+// column-major (its consumers are thread-per-atom).  Same arithmetic per pair as the
+// thread-per-atom bodies; only the summation order over neighbours differs.
+// =============================================================================================
+template <int NT, int K1>
+B2_HD void b2_team_desc_radial(int i, int l, const B2NepView& P, const B2Box& box)
+{
+  constexpr int G = B2_TEAM;
+  const B2Geo geo = b2_geo(box);
+  const size_t N = (size_t)P.n;
+  const B2Atom a1 = P.atoms[i];
+  const int t1 = a1.type;
+  const int nn = P.nn_skin[i];
+  const int* row = P.nl_skin + (size_t)i * P.skin_si;
+  int* out_r = P.nl_r + (size_t)i * P.pitch_r;
+  float S[NT][K1];
+  float rcv[NT], rciv[NT], rc2r[NT], rc2a[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int pr = t1 * P.nt + (t < P.nt ? t : 0);
+    rcv[t] = B2_LDG(&P.rc_r[pr]);
+    rciv[t] = B2_LDG(&P.rcinv_r[pr]);
+    rc2r[t] = B2_LDG(&P.rc2_r[pr]);
+    rc2a[t] = B2_LDG(&P.rc2_a[pr]);
+#pragma unroll
+    for (int k = 0; k < K1; ++k)
+      S[t][k] = 0.0f;
+  }
+  int cr = 0, ca = 0;
+  const unsigned below = (1u << l) - 1u;
+  // software pipeline as in the thread-per-atom bodies: record one entry ahead, index two ahead
+  int jn = l < nn ? row[l] : i;
+  B2Atom an = b2_load_atom(&P.atoms[jn]);
+  int j2 = l + G < nn ? row[l + G] : i;
+  for (int k0 = 0; k0 < nn; k0 += G) {
+    const bool valid = k0 + l < nn;
+    const int j = jn;
+    const B2Atom a2 = an;
+    jn = j2;
+    an = b2_load_atom(&P.atoms[j2]);
+    j2 = (k0 + l + 2 * G < nn) ? row[k0 + l + 2 * G] : i;
+    float x12, y12, z12;
+    b2_r12(geo, box, a1, a2, x12, y12, z12);
+    const float d2 = b2_d2(x12, y12, z12);
+    const int t2 = a2.type;
+    float rc = rcv[0], rcinv = rciv[0], r2r = rc2r[0], r2a = rc2a[0];
+#pragma unroll
+    for (int t = 1; t < NT; ++t) {
+      rc = (t2 == t) ? rcv[t] : rc;
+      rcinv = (t2 == t) ? rciv[t] : rcinv;
+      r2r = (t2 == t) ? rc2r[t] : r2r;
+      r2a = (t2 == t) ? rc2a[t] : r2a;
+    }
+    // the reference's membership tests (nep.cu:473-484), list order = ascending sorted index
+    const bool inr = valid && d2 < r2r;
+    const bool ina = inr && d2 < r2a;
+    const unsigned mr = b2_team_ballot(inr), ma = b2_team_ballot(ina);
+    if (inr) {
+      const int pos = cr + B2_POPC(mr & below);
+      if (pos < P.mn_r)
+        out_r[pos] = j;
+    }
+    if (ina) {
+      const int pos = ca + B2_POPC(ma & below);
+      if (pos < P.mn_a)
+        P.nl_a[(size_t)pos * N + i] = j;
+    }
+    cr += B2_POPC(mr);
+    ca += B2_POPC(ma);
+    if (inr) {
+      float fn[K1];
+      b2_basis<K1>(sqrtf(d2), rc, rcinv, fn);
+      if (NT == 1) {
+#pragma unroll
+        for (int k = 0; k < K1; ++k)
+          S[0][k] += fn[k];
+      } else {
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+          const float m = (t2 == t) ? 1.0f : 0.0f;
+#pragma unroll
+          for (int k = 0; k < K1; ++k)
+            S[t][k] = fmaf(m, fn[k], S[t][k]);
+        }
+      }
+    }
+  }
+  if (l == 0) {
+    if (cr > P.mn_r) {
+      B2_ATOMIC_OR(&P.flags[1], (int)B2_ERR_RADIAL_OVERFLOW);
+      cr = P.mn_r;
+    }
+    if (ca > P.mn_a) {
+      B2_ATOMIC_OR(&P.flags[1], (int)B2_ERR_ANGULAR_OVERFLOW);
+      ca = P.mn_a;
+    }
+    P.nn_r[i] = cr;
+    P.nn_a[i] = ca;
+  }
+#pragma unroll
+  for (int t = 0; t < NT; ++t)
+#pragma unroll
+    for (int k = 0; k < K1; ++k)
+      S[t][k] = b2_team_sum(S[t][k]);
+  // contraction with the expansion coefficients, one n per lane
+  for (int n = l; n < P.nr1; n += G) {
+    float q = 0.0f;
+#pragma unroll
+    for (int t = 0; t < NT; ++t) {
+      if (t < P.nt) {
+        const float* c = P.c_r + ((size_t)(t1 * P.nt + t) * P.nr1 + n) * K1;
+#pragma unroll
+        for (int k = 0; k < K1; ++k)
+          q = fmaf(B2_LDG(&c[k]), S[t][k], q);
+      }
+    }
+    P.q[(size_t)n * N + i] = q;
+  }
+}
+
+// radial pair forces + angular pair reduction (+ ZBL) + the scatter into the caller's arrays;
+// the lane-team counterpart of b2_body_force_final
+template <int NT, int K1>
+B2_HD void b2_team_force_final(
+  int i, int l, const B2NepView& P, const B2Box& box, double* pe, double* force, double* virial)
+{
+  constexpr int G = B2_TEAM;
+  constexpr int KP4 = (K1 + 3) / 4;
+  const B2Geo geo = b2_geo(box);
+  const size_t N = (size_t)P.n;
+  const B2Atom a1 = P.atoms[i];
+  const int t1 = a1.type;
+  const int nn = P.nn_r[i];
+  const int* row = P.nl_r + (size_t)i * P.pitch_r;
+  const float4* U4 = reinterpret_cast<const float4*>(P.U);
+  float Ur[NT][K1];
+  float rcv[NT], rciv[NT];
+#pragma unroll
+  for (int t = 0; t < NT; ++t) {
+    const int tt = t < P.nt ? t : 0;
+    const int pr = t1 * P.nt + tt;
+    rcv[t] = B2_LDG(&P.rc_r[pr]);
+    rciv[t] = B2_LDG(&P.rcinv_r[pr]);
+    float u[KP4 * 4];
+#pragma unroll
+    for (int q = 0; q < KP4; ++q) {
+      const float4 v = B2_LDG(&U4[(size_t)(tt * KP4 + q) * N + i]);
+      u[4 * q] = v.x;
+      u[4 * q + 1] = v.y;
+      u[4 * q + 2] = v.z;
+      u[4 * q + 3] = v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < K1; ++k)
+      Ur[t][k] = u[k];
+  }
+  float fx = 0.0f, fy = 0.0f, fz = 0.0f;
+  float vxx = 0.0f, vyy = 0.0f, vzz = 0.0f, vxy = 0.0f, vxz = 0.0f, vyz = 0.0f;
+  const float4* Ub = U4 + (size_t)t1 * KP4 * N; // plane q of the neighbour's row for MY type
+  int jn = l < nn ? row[l] : i;
+  B2Atom an = b2_load_atom(&P.atoms[jn]);
+  float4 un[KP4];
+#pragma unroll
+  for (int q = 0; q < KP4; ++q)
+    un[q] = B2_LDG(&Ub[(size_t)q * N + jn]);
+  int j2 = l + G < nn ? row[l + G] : i;
+  for (int k0 = 0; k0 < nn; k0 += G) {
+    const bool valid = k0 + l < nn;
+    const B2Atom a2 = an;
+    float Uj[KP4 * 4];
+#pragma unroll
+    for (int q = 0; q < KP4; ++q) {
+      Uj[4 * q] = un[q].x;
+      Uj[4 * q + 1] = un[q].y;
+      Uj[4 * q + 2] = un[q].z;
+      Uj[4 * q + 3] = un[q].w;
+    }
+    an = b2_load_atom(&P.atoms[j2]);
+#pragma unroll
+    for (int q = 0; q < KP4; ++q)
+      un[q] = B2_LDG(&Ub[(size_t)q * N + j2]);
+    j2 = (k0 + l + 2 * G < nn) ? row[k0 + l + 2 * G] : i;
+    if (!valid)
+      continue;
+    float x12, y12, z12;
+    b2_r12(geo, box, a1, a2, x12, y12, z12);
+    const float d2 = b2_d2(x12, y12, z12);
+    const float dinv = b2_rsqrt(d2);
+    const float d = d2 * dinv;
+    const int t2 = a2.type;
+    float rc = rcv[0], rcinv = rciv[0];
+#pragma unroll
+    for (int t = 1; t < NT; ++t) {
+      rc = (t2 == t) ? rcv[t] : rc;
+      rcinv = (t2 == t) ? rciv[t] : rcinv;
+    }
+    float fnp[K1];
+    b2_basis_d<K1, false>(d, rc, rcinv, nullptr, fnp);
+    float A = 0.0f, Bv = 0.0f;
+#pragma unroll
+    for (int k = 0; k < K1; ++k) {
+      float u = Ur[0][k];
+#pragma unroll
+      for (int t = 1; t < NT; ++t)
+        u = (t2 == t) ? Ur[t][k] : u;
+      A = fmaf(fnp[k], u, A);
+      Bv = fmaf(fnp[k], Uj[k], Bv);
+    }
+    const float sA = (A + Bv) * dinv;
+    const float sB = -Bv * dinv; // f21 = sB * r12
+    fx = fmaf(sA, x12, fx);
+    fy = fmaf(sA, y12, fy);
+    fz = fmaf(sA, z12, fz);
+    vxx = fmaf(x12 * x12, sB, vxx);
+    vyy = fmaf(y12 * y12, sB, vyy);
+    vzz = fmaf(z12 * z12, sB, vzz);
+    vxy = fmaf(x12 * y12, sB, vxy);
+    vxz = fmaf(x12 * z12, sB, vxz);
+    vyz = fmaf(y12 * z12, sB, vyz);
+  }
+  // this lane's share of the angular pair reduction and of the ZBL pairs
+  float a[12], z[12], zpe = 0.0f;
+  b2_reduce_angular_sum(i, P, box, a, l, G);
+  if (P.zbl_enabled) {
+    b2_zbl_sum(i, P, box, z, zpe, l, G);
+  } else {
+#pragma unroll
+    for (int k = 0; k < 12; ++k)
+      z[k] = 0.0f;
+  }
+  float tot[13];
+  tot[0] = zpe;
+  tot[1] = fx + a[0] + z[0];
+  tot[2] = fy + a[1] + z[1];
+  tot[3] = fz + a[2] + z[2];
+  tot[4] = vxx + a[3] + z[3];
+  tot[5] = vyy + a[4] + z[4];
+  tot[6] = vzz + a[5] + z[5];
+  tot[7] = vxy + a[6] + z[6];
+  tot[8] = vxz + a[7] + z[7];
+  tot[9] = vyz + a[8] + z[8];
+  tot[10] = vxy + a[9] + z[9];   // yx (the radial pair virial is symmetric)
+  tot[11] = vxz + a[10] + z[10]; // zx
+  tot[12] = vyz + a[11] + z[11]; // zy
+#pragma unroll
+  for (int k = 0; k < 13; ++k)
+    tot[k] = b2_team_sum(tot[k]);
+  // scatter (+=, the accumulate convention of Potential::compute): component c by lane c % G
+  const int dst = P.perm[i];
+#pragma unroll
+  for (int c = 0; c < 13; ++c) {
+    if (c % G == l) {
+      if (c == 0)
+        pe[dst] += P.acc[i] + (double)tot[0]; // acc[i] = site energy from the MLP pass
+      else if (c < 4)
+        force[(size_t)(c - 1) * N + dst] += (double)tot[c];
+      else
+        virial[(size_t)(c - 4) * N + dst] += (double)tot[c];
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------

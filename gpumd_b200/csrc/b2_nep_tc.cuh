@@ -31,17 +31,18 @@ __host__ __device__ inline size_t b2_tc_smem_bytes(int img_floats, int HN, int D
   return b2_tc_img_bytes(img_floats) + 2 * 128 * (size_t)(DK > HN ? DK : HN) * 4;
 }
 
+// Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... so that the TMEM
+// allocation, barrier set-up and (tiles being ordered by type) almost every weight fetch are paid
+// once per CTA instead of once per tile.
 __global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
 {
   extern __shared__ __align__(128) unsigned char tc_smem[];
   __shared__ __align__(8) uint64_t bar_w, bar_mma;
   __shared__ uint32_t tmem_slot;
-  const int tile = blockIdx.x;
-  if (tile >= P.tile_meta[0])
+  const int ntile = P.tile_meta[0];
+  if ((int)blockIdx.x >= ntile)
     return;
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int t = P.tile_type[tile];
-  const int i = P.tile_atom[tile * 128 + tid]; // -1 = padding row
   const size_t N = (size_t)P.n;
   const int HN = P.HN, DK = P.DK, DN = P.DN;
   const int KA = DK > HN ? DK : HN;
@@ -57,112 +58,147 @@ __global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
   if (tid == 0) {
     b2tc::mbar_init(&bar_w, 1);
     b2tc::mbar_init(&bar_mma, 1);
-    const uint32_t bytes = (uint32_t)P.tc_img_floats * 4u;
-    b2tc::mbar_expect_tx(&bar_w, bytes);
-    b2tc::bulk_g2s(img, P.tc_img + (size_t)t * P.tc_img_floats, bytes, &bar_w);
   }
-  // ---- stage Q (scaled descriptors) as the A operand: row tid, four columns per store ----
-  for (int k4 = 0; k4 < DK / 4; ++k4) {
-    float hi[4], lo[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      const int d = 4 * k4 + c;
-      const float v = (i >= 0 && d < P.dim) ? P.q[(size_t)d * N + i] * __ldg(&P.q_scaler[d]) : 0.0f;
-      b2tc::split_tf32(v, hi[c], lo[c]);
-    }
-    const uint32_t off = (uint32_t)tid * 16u + (uint32_t)k4 * 2048u;
-    *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-    *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-  }
-  b2tc::fence_async_smem();
   b2tc::fence_before_sync();
   __syncthreads();
   b2tc::fence_after_sync();
   const uint32_t tmem = tmem_slot;
   const uint32_t ah = b2tc::smem_u32(a_hi), al = b2tc::smem_u32(a_lo);
-  b2tc::mbar_wait(&bar_w, 0); // weights, b0, w1 have landed
-  if (tid == 0) {
-    // GEMM 1: Z = Q . W0^T   (B1: [HN rows x DK], K chunks HN*16 bytes apart)
-    const uint32_t idesc = b2tc::make_idesc_tf32(128, HN);
-    const uint32_t bh = b2tc::smem_u32(img), bl = bh + (uint32_t)HN * DK * 4u;
-    const uint32_t lbo_b = (uint32_t)HN * 16u;
-    for (int ks = 0; ks < DK / 8; ++ks) {
-      const uint64_t dah = b2tc::make_desc(ah + ks * 4096u, 2048u, 128u);
-      const uint64_t dal = b2tc::make_desc(al + ks * 4096u, 2048u, 128u);
-      const uint64_t dbh = b2tc::make_desc(bh + ks * 2u * lbo_b, lbo_b, 128u);
-      const uint64_t dbl = b2tc::make_desc(bl + ks * 2u * lbo_b, lbo_b, 128u);
-      b2tc::mma_tf32(tmem, dal, dbh, idesc, ks > 0 ? 1u : 0u);
-      b2tc::mma_tf32(tmem, dah, dbl, idesc, 1u);
-      b2tc::mma_tf32(tmem, dah, dbh, idesc, 1u);
-    }
-    b2tc::mma_commit(&bar_mma);
-  }
-  b2tc::mbar_wait(&bar_mma, 0);
-  b2tc::fence_after_sync();
-  // ---- epilogue 1: activation, site energy, and C as the A operand of GEMM 2 ----
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-  float F = 0.0f;
-  for (int c0 = 0; c0 < HN; c0 += 16) {
-    uint32_t v[16];
-    b2tc::tmem_ld16(tmem + lane_base + (uint32_t)c0, v);
-#pragma unroll
-    for (int g = 0; g < 4; ++g) {
-      float hi[4], lo[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const int j = c0 + 4 * g + c;
-        const float x1 = tanhf(__uint_as_float(v[4 * g + c]) - sb0[j]);
-        const float w1j = sw1[j];
-        F = fmaf(w1j, x1, F);
-        b2tc::split_tf32(w1j * (1.0f - x1 * x1), hi[c], lo[c]);
-      }
-      const uint32_t off = (uint32_t)tid * 16u + (uint32_t)(c0 / 4 + g) * 2048u;
-      *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-      *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+  uint32_t w_phase = 0, mma_phase = 0;
+  int cur_type = -1;
+
+  int i_next = P.tile_atom[blockIdx.x * 128 + tid];
+  for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
+    const int t = P.tile_type[tile];
+    const int i = i_next; // -1 = padding row
+    if (tile + (int)gridDim.x < ntile)
+      i_next = P.tile_atom[(tile + gridDim.x) * 128 + tid];
+    const bool new_weights = t != cur_type;      // uniform over the CTA
+    if (new_weights && tid == 0) {
+      // every thread is past the previous tile's last read of the image (the barrier after
+      // epilogue 1) and its MMAs have completed (bar_mma), so the image may be replaced
+      const uint32_t bytes = (uint32_t)P.tc_img_floats * 4u;
+      b2tc::mbar_expect_tx(&bar_w, bytes);
+      b2tc::bulk_g2s(img, P.tc_img + (size_t)t * P.tc_img_floats, bytes, &bar_w);
     }
-  }
-  b2tc::fence_async_smem();
-  b2tc::fence_before_sync();
-  __syncthreads();
-  b2tc::fence_after_sync();
-  if (tid == 0) {
-    // GEMM 2: Fp = C . W0   (B2: [DN rows x HN], K chunks DN*16 bytes apart), D at column HN
-    const uint32_t idesc = b2tc::make_idesc_tf32(128, DN);
-    const uint32_t bh = b2tc::smem_u32(img) + 2u * HN * DK * 4u, bl = bh + (uint32_t)DN * HN * 4u;
-    const uint32_t lbo_b = (uint32_t)DN * 16u;
-    for (int ks = 0; ks < HN / 8; ++ks) {
-      const uint64_t dah = b2tc::make_desc(ah + ks * 4096u, 2048u, 128u);
-      const uint64_t dal = b2tc::make_desc(al + ks * 4096u, 2048u, 128u);
-      const uint64_t dbh = b2tc::make_desc(bh + ks * 2u * lbo_b, lbo_b, 128u);
-      const uint64_t dbl = b2tc::make_desc(bl + ks * 2u * lbo_b, lbo_b, 128u);
-      b2tc::mma_tf32(tmem + (uint32_t)HN, dal, dbh, idesc, ks > 0 ? 1u : 0u);
-      b2tc::mma_tf32(tmem + (uint32_t)HN, dah, dbl, idesc, 1u);
-      b2tc::mma_tf32(tmem + (uint32_t)HN, dah, dbh, idesc, 1u);
-    }
-    b2tc::mma_commit(&bar_mma);
-  }
-  b2tc::mbar_wait(&bar_mma, 1);
-  b2tc::fence_after_sync();
-  // ---- epilogue 2: dU/dq (times q_scaler), radial part for k_utable, angular part for the rest ----
-  for (int c0 = 0; c0 < DN; c0 += 16) {
-    uint32_t v[16];
-    b2tc::tmem_ld16(tmem + lane_base + (uint32_t)(HN + c0), v);
-    if (i >= 0) {
+    cur_type = t;
+    // ---- stage Q (scaled descriptors) as the A operand: row tid, four columns per store.
+    //      16 columns are fetched at a time so that their (strided) loads are all in flight ----
+    for (int c0 = 0; c0 < DK; c0 += 16) {
+      float v[16];
 #pragma unroll
       for (int c = 0; c < 16; ++c) {
         const int d = c0 + c;
-        if (d < P.dim) {
-          const float f = __uint_as_float(v[c]) * __ldg(&P.q_scaler[d]);
-          if (d < P.nr1)
-            P.FpR[(size_t)d * N + i] = f;
-          else
-            P.FpA[(size_t)(d - P.nr1) * N + i] = f;
+        v[c] = (i >= 0 && d < P.dim) ? P.q[(size_t)d * N + i] * __ldg(&P.q_scaler[d]) : 0.0f;
+      }
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (c0 + 4 * g < DK) {
+          float hi[4], lo[4];
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+            b2tc::split_tf32(v[4 * g + c], hi[c], lo[c]);
+          const uint32_t off = (uint32_t)tid * 16u + (uint32_t)(c0 / 4 + g) * 2048u;
+          *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
       }
     }
+    b2tc::fence_async_smem();
+    b2tc::fence_before_sync();
+    __syncthreads();
+    b2tc::fence_after_sync();
+    if (new_weights) {
+      b2tc::mbar_wait(&bar_w, w_phase); // weights, b0, w1 have landed
+      w_phase ^= 1u;
+    }
+    if (tid == 0) {
+      // GEMM 1: Z = Q . W0^T   (B1: [HN rows x DK], K chunks HN*16 bytes apart)
+      const uint32_t idesc = b2tc::make_idesc_tf32(128, HN);
+      const uint32_t bh = b2tc::smem_u32(img), bl = bh + (uint32_t)HN * DK * 4u;
+      const uint32_t lbo_b = (uint32_t)HN * 16u;
+      for (int ks = 0; ks < DK / 8; ++ks) {
+        const uint64_t dah = b2tc::make_desc(ah + ks * 4096u, 2048u, 128u);
+        const uint64_t dal = b2tc::make_desc(al + ks * 4096u, 2048u, 128u);
+        const uint64_t dbh = b2tc::make_desc(bh + ks * 2u * lbo_b, lbo_b, 128u);
+        const uint64_t dbl = b2tc::make_desc(bl + ks * 2u * lbo_b, lbo_b, 128u);
+        b2tc::mma_tf32(tmem, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+        b2tc::mma_tf32(tmem, dah, dbl, idesc, 1u);
+        b2tc::mma_tf32(tmem, dah, dbh, idesc, 1u);
+      }
+      b2tc::mma_commit(&bar_mma);
+    }
+    b2tc::mbar_wait(&bar_mma, mma_phase);
+    mma_phase ^= 1u;
+    b2tc::fence_after_sync();
+    // ---- epilogue 1: activation, site energy, and C as the A operand of GEMM 2 ----
+    float F = 0.0f;
+    for (int c0 = 0; c0 < HN; c0 += 16) {
+      uint32_t v[16];
+      b2tc::tmem_ld16(tmem + lane_base + (uint32_t)c0, v);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float hi[4], lo[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const int j = c0 + 4 * g + c;
+          const float x1 = tanhf(__uint_as_float(v[4 * g + c]) - sb0[j]);
+          const float w1j = sw1[j];
+          F = fmaf(w1j, x1, F);
+          b2tc::split_tf32(w1j * (1.0f - x1 * x1), hi[c], lo[c]);
+        }
+        const uint32_t off = (uint32_t)tid * 16u + (uint32_t)(c0 / 4 + g) * 2048u;
+        *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+      }
+    }
+    b2tc::fence_async_smem();
+    b2tc::fence_before_sync();
+    __syncthreads();
+    b2tc::fence_after_sync();
+    if (tid == 0) {
+      // GEMM 2: Fp = C . W0   (B2: [DN rows x HN], K chunks DN*16 bytes apart), D at column HN
+      const uint32_t idesc = b2tc::make_idesc_tf32(128, DN);
+      const uint32_t bh = b2tc::smem_u32(img) + 2u * HN * DK * 4u, bl = bh + (uint32_t)DN * HN * 4u;
+      const uint32_t lbo_b = (uint32_t)DN * 16u;
+      for (int ks = 0; ks < HN / 8; ++ks) {
+        const uint64_t dah = b2tc::make_desc(ah + ks * 4096u, 2048u, 128u);
+        const uint64_t dal = b2tc::make_desc(al + ks * 4096u, 2048u, 128u);
+        const uint64_t dbh = b2tc::make_desc(bh + ks * 2u * lbo_b, lbo_b, 128u);
+        const uint64_t dbl = b2tc::make_desc(bl + ks * 2u * lbo_b, lbo_b, 128u);
+        b2tc::mma_tf32(tmem + (uint32_t)HN, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+        b2tc::mma_tf32(tmem + (uint32_t)HN, dah, dbl, idesc, 1u);
+        b2tc::mma_tf32(tmem + (uint32_t)HN, dah, dbh, idesc, 1u);
+      }
+      b2tc::mma_commit(&bar_mma);
+    }
+    b2tc::mbar_wait(&bar_mma, mma_phase);
+    mma_phase ^= 1u;
+    b2tc::fence_after_sync();
+    // ---- epilogue 2: dU/dq (times q_scaler): radial part for k_utable, angular part for the rest
+    for (int c0 = 0; c0 < DN; c0 += 16) {
+      uint32_t v[16];
+      b2tc::tmem_ld16(tmem + lane_base + (uint32_t)(HN + c0), v);
+      if (i >= 0) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          const int d = c0 + c;
+          if (d < P.dim) {
+            const float f = __uint_as_float(v[c]) * __ldg(&P.q_scaler[d]);
+            if (d < P.nr1)
+              P.FpR[(size_t)d * N + i] = f;
+            else
+              P.FpA[(size_t)(d - P.nr1) * N + i] = f;
+          }
+        }
+      }
+    }
+    if (i >= 0)
+      P.acc[i] = (double)(F - __ldg(&P.bias[t]));
+    // the next tile's GEMM 1 overwrites Z (columns [0, HN)) only after the barrier in its staging
+    // phase, i.e. after every thread's epilogue-1 loads above; its GEMM 2 after the next barrier
   }
-  if (i >= 0)
-    P.acc[i] = (double)(F - __ldg(&P.bias[t]));
   b2tc::fence_before_sync();
   __syncthreads();
   if (warp == 0)

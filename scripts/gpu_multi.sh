@@ -4,7 +4,7 @@ set -u
 N=${NGPUS:-2}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name,clocks.sm --format=csv > gpurun_out/gpus.txt 2>&1
-echo "== pytest gpu (all)"; timeout 1200 python -m pytest tests -m gpu -q 2>&1 | tail -15 | tee gpurun_out/pytest_gpu_multi.txt
+echo "== pytest gpu (all)"; timeout 1200 python -m pytest ${PYTEST_TARGET:-tests} -m gpu -q 2>&1 | tail -15 | tee gpurun_out/pytest_gpu_multi.txt
 for g in ${BENCH_GPUS:-1 2}; do
   echo "== bench N=$g"
   if [ "$g" = "1" ]; then

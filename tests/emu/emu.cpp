@@ -66,6 +66,8 @@ struct EmuNeighbor {
     nl_skin, flags;
   B2NeighborView v;
   int rebuilds = 0;
+  bool row_major = false; // mirrors Neighbor::skin_row_major
+  int pitch() const { return (mn_skin + 7) / 8 * 8; }
 
   void init(int n_, double rc_, int mn)
   {
@@ -82,7 +84,7 @@ struct EmuNeighbor {
     cell_of.resize(n);
     order_tmp.resize(n);
     nn_skin.resize(n);
-    nl_skin.resize((size_t)mn * n);
+    nl_skin.resize((size_t)pitch() * n);
     flags.assign(4, 0);
     flags[0] = 1;
   }
@@ -115,6 +117,8 @@ struct EmuNeighbor {
     v.cell_start = cell_start.data();
     v.nn_skin = nn_skin.data();
     v.nl_skin = nl_skin.data();
+    v.skin_si = row_major ? (size_t)pitch() : 1;
+    v.skin_sk = row_major ? 1 : (size_t)n;
     v.flags = flags.data();
     const float trigger = (float)(skin * skin * 0.25);
     const float cutoff = (float)((rc + skin) * (rc + skin));
@@ -164,26 +168,40 @@ struct emu_nep {
   std::vector<int> zbl_z;
   std::vector<float> cov;
   B2NepView P;
+  bool team = false, fuse_split = false; // same choices as nep_setup() in b2_nep.cu
 };
 
 template <int K1>
 static void run_desc_radial(emu_nep* p, const B2Box& box)
 {
   std::vector<float> scratch((size_t)p->m.nt * K1 + 1);
+  if (!p->team && p->m.nt > 2 && !p->fuse_split)
+    for (int i = 0; i < p->n; ++i)
+      b2_body_split(i, p->P, box);
   for (int i = 0; i < p->n; ++i) {
-    if (p->m.nt == 1)
-      b2_body_desc_radial<1, K1>(i, p->P, box, scratch.data(), 1, 0);
+    if (p->team && p->m.nt == 1)
+      b2_team_desc_radial<1, K1>(i, 0, p->P, box);
+    else if (p->team)
+      b2_team_desc_radial<2, K1>(i, 0, p->P, box);
+    else if (p->m.nt == 1)
+      b2_body_desc_radial<1, K1, true>(i, p->P, box, scratch.data(), 1, 0);
     else if (p->m.nt == 2)
-      b2_body_desc_radial<2, K1>(i, p->P, box, scratch.data(), 1, 0);
+      b2_body_desc_radial<2, K1, true>(i, p->P, box, scratch.data(), 1, 0);
+    else if (p->fuse_split)
+      b2_body_desc_radial<0, K1, true>(i, p->P, box, scratch.data(), 1, 0);
     else
-      b2_body_desc_radial<0, K1>(i, p->P, box, scratch.data(), 1, 0);
+      b2_body_desc_radial<0, K1, false>(i, p->P, box, scratch.data(), 1, 0);
   }
 }
 template <int K1>
 static void run_force_final(emu_nep* p, const B2Box& box, double* pe, double* f, double* v)
 {
   for (int i = 0; i < p->n; ++i) {
-    if (p->m.nt == 1)
+    if (p->team && p->m.nt == 1)
+      b2_team_force_final<1, K1>(i, 0, p->P, box, pe, f, v);
+    else if (p->team)
+      b2_team_force_final<2, K1>(i, 0, p->P, box, pe, f, v);
+    else if (p->m.nt == 1)
       b2_body_force_final<1, K1>(i, p->P, box, pe, f, v);
     else if (p->m.nt == 2)
       b2_body_force_final<2, K1>(i, p->P, box, pe, f, v);
@@ -225,9 +243,14 @@ emu_nep* emu_nep_create(const char* path, int n)
   p->n = n;
   const size_t N = n;
   const double rc = m.rc_radial_max, rs = rc + 1.0;
+  const char* team_env = std::getenv("B200MD_NEP_TEAM");
+  p->team = m.nt <= 2 && team_env && std::strcmp(team_env, "1") == 0;
+  p->fuse_split = rs * rs * rs / (rc * rc * rc) < 1.45;
+  p->nb.row_major = p->team;
   p->nb.init(n, rc, (int)(m.MN_radial * rs * rs * rs / (rc * rc * rc)));
+  const int pitch_r = (m.MN_radial + 7) / 8 * 8;
   p->nn_r.resize(N);
-  p->nl_r.resize(N * m.MN_radial);
+  p->nl_r.resize(N * pitch_r);
   p->nn_a.resize(N);
   p->nl_a.resize(N * m.MN_angular);
   p->q.resize(N * m.dim);
@@ -259,6 +282,8 @@ emu_nep* emu_nep_create(const char* path, int n)
   P.nn_r = p->nn_r.data(); P.nl_r = p->nl_r.data(); P.nn_a = p->nn_a.data(); P.nl_a = p->nl_a.data();
   P.q = p->q.data(); P.sfx = p->sfx.data(); P.FpR = p->FpR.data(); P.FpA = p->FpA.data(); P.U = p->U.data();
   P.f12 = p->f12.data(); P.acc = p->acc.data();
+  P.team = p->team ? 1 : 0;
+  P.pitch_r = pitch_r;
   return p;
 }
 
@@ -281,6 +306,8 @@ int emu_nep_compute(
   P.perm = p->nb.perm.data();
   P.nn_skin = p->nb.nn_skin.data();
   P.nl_skin = p->nb.nl_skin.data();
+  P.skin_si = p->nb.v.skin_si;
+  P.skin_sk = p->nb.v.skin_sk;
   P.flags = p->nb.flags.data();
   switch (p->m.K1R) {
     case 9: run_desc_radial<9>(p, box); break;
@@ -304,11 +331,11 @@ int emu_nep_compute(
   }
   for (int i = 0; i < n; ++i) {
     if (p->m.K1R == 9)
-      b2_body_utable<9>(i, P);
+      p->team ? b2_body_utable_planes<9>(i, P) : b2_body_utable<9>(i, P);
     else if (p->m.K1R == 13)
-      b2_body_utable<13>(i, P);
+      p->team ? b2_body_utable_planes<13>(i, P) : b2_body_utable<13>(i, P);
     else
-      b2_body_utable<17>(i, P);
+      p->team ? b2_body_utable_planes<17>(i, P) : b2_body_utable<17>(i, P);
   }
   switch (p->m.K1A) {
     case 9: run_angular<9>(p, box, true); break;
@@ -324,14 +351,15 @@ int emu_nep_compute(
 }
 
 static void export_list(
-  int n, const int* perm, const int* nn, const int* nl, int mn, int* NN, int* NL)
+  int n, const int* perm, const int* nn, const int* nl, size_t si, size_t sk, int mn, int* NN,
+  int* NL)
 {
   for (int i = 0; i < n; ++i) {
     const int a = perm[i];
     const int cnt = nn[i] < mn ? nn[i] : mn;
     int* row = NL + (size_t)a * mn;
     for (int k = 0; k < cnt; ++k) {
-      const int v = perm[nl[(size_t)k * n + i]];
+      const int v = perm[nl[(size_t)i * si + (size_t)k * sk]];
       int q = k - 1;
       while (q >= 0 && row[q] > v) {
         row[q + 1] = row[q];
@@ -346,8 +374,10 @@ static void export_list(
 void emu_nep_export_neighbors(
   emu_nep* p, int mn_r, int* NN_r, int* NL_r, int mn_a, int* NN_a, int* NL_a)
 {
-  export_list(p->n, p->P.perm, p->nn_r.data(), p->nl_r.data(), mn_r, NN_r, NL_r);
-  export_list(p->n, p->P.perm, p->nn_a.data(), p->nl_a.data(), mn_a, NN_a, NL_a);
+  export_list(
+    p->n, p->P.perm, p->nn_r.data(), p->nl_r.data(), p->team ? (size_t)p->P.pitch_r : 1,
+    p->team ? 1 : (size_t)p->n, mn_r, NN_r, NL_r);
+  export_list(p->n, p->P.perm, p->nn_a.data(), p->nl_a.data(), 1, (size_t)p->n, mn_a, NN_a, NL_a);
 }
 
 void emu_nep_export_descriptors(emu_nep* p, float* q)
@@ -360,7 +390,9 @@ void emu_nep_export_descriptors(emu_nep* p, float* q)
 // skin list of the last rebuild, in caller indices (row-major, ascending) -- neighbour tests
 void emu_nep_export_skin(emu_nep* p, int mn, int* NN, int* NL)
 {
-  export_list(p->n, p->P.perm, p->nb.nn_skin.data(), p->nb.nl_skin.data(), mn, NN, NL);
+  export_list(
+    p->n, p->P.perm, p->nb.nn_skin.data(), p->nb.nl_skin.data(), p->nb.v.skin_si, p->nb.v.skin_sk,
+    mn, NN, NL);
 }
 
 // ---- LJ -------------------------------------------------------------------------------------

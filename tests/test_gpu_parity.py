@@ -58,12 +58,14 @@ class GpuNep:
         return self.pot.num_rebuilds
 
 
-@pytest.mark.parametrize("mlp", ["tc", "simt"])
+@pytest.mark.parametrize("mlp,team", [("tc", "0"), ("simt", "0"), ("tc", "1")])
 @pytest.mark.parametrize("case", list(NEP_CASES))
-def test_nep_matches_oracle(oracle, eng, case, mlp, monkeypatch):
-    """mlp: hidden layer on the tensor cores (k_mlp_tc, the default) or the SIMT kernel (k_mlp)."""
+def test_nep_matches_oracle(oracle, eng, case, mlp, team, monkeypatch):
+    """mlp: hidden layer on the tensor cores (k_mlp_tc, the default) or the SIMT kernel (k_mlp);
+    team: thread-per-atom radial passes (default) or the lane-team kernels (<= 2 types)."""
     from test_kernel_bodies_cpu import check_nep
     monkeypatch.setenv("B200MD_NEP_MLP", mlp)
+    monkeypatch.setenv("B200MD_NEP_TEAM", team)
     model, make = NEP_CASES[case]
     s = make()
     n = s["type"].shape[0]

@@ -46,8 +46,12 @@ def check_nep(oracle, dev, model, s, n):
     return out
 
 
+@pytest.mark.parametrize("team", ["0", "1"])
 @pytest.mark.parametrize("case", list(NEP_CASES))
-def test_nep_bodies_match_oracle(oracle, emu, case):
+def test_nep_bodies_match_oracle(oracle, emu, case, team, monkeypatch):
+    """team: thread-per-atom radial passes (default) or the lane-team bodies (<= 2 types; the host
+    build runs them with a team of one lane)."""
+    monkeypatch.setenv("B200MD_NEP_TEAM", team)
     model, make = NEP_CASES[case]
     s = make()
     n = s["type"].shape[0]
