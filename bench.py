@@ -35,6 +35,7 @@ sys.path.insert(0, str(ROOT))
 GOLDEN = ROOT / "tests" / "golden"
 MODEL = GOLDEN / "nep_PbTe.txt"
 METRIC = "atom-steps/sec (1M-atom PbTe NEP NVE per GPU)"
+DOMAIN_SKIN = 3.0  # A, multi-GPU ghost-list skin (gpumd_b200/domain.py)
 
 
 def stage_algorithmic_bytes(nn, model):
@@ -249,7 +250,7 @@ def side_bench(args, rank, world, local, torch, dist, engine):
     else:
         from gpumd_b200.domain import DomainMD, SlabDomain
         pot_rc = {"lj": 10.0, "unep": 6.0, "si": 3.0}[args.workload]
-        dom = SlabDomain(s["h"], s["pbc"], pot_rc, rank, world, "cuda")
+        dom = SlabDomain(s["h"], s["pbc"], pot_rc, rank, world, "cuda", skin=DOMAIN_SKIN)
         dom.distribute(s["type"], s["pos"], s["mass"], s["vel"])
         md = DomainMD(dom, GOLDEN / potfile, ensemble=ensemble, temperature=T0, temperature_coupling=100.0,
                       time_step=dt)
@@ -263,13 +264,18 @@ def side_bench(args, rank, world, local, torch, dist, engine):
                 heat[0] = md.heat_current()
 
         md.compute_force()
-        get_thermo = lambda: md.thermo.cpu().numpy()
+        get_thermo = lambda: md.read_thermo()
         check = md.pot.check
         rebuilds = lambda: md.pot.num_rebuilds
     del s
     check()
     for _ in range(max(args.warmup, 3)):
         step()
+    if world > 1:
+        for _ in range(2):  # warm the displacement check (torch ops + all-reduce MAX) as well
+            dom.needs_exchange()
+        if heat_every:
+            md.heat_current()
     check()
     torch.cuda.synchronize()
     if world > 1:
@@ -320,7 +326,9 @@ def ours_multi(args, rank, world, local, torch, dist, engine):
     s = rocksalt_pbte((args.cells * world, args.cells, args.cells), rattle=0.02, seed=1)
     vel = init_velocities(s["mass"], 300.0, seed=42)
     n_global = s["type"].shape[0]
-    dom = SlabDomain(s["h"], s["pbc"], 8.0, rank, world, "cuda")
+    # domain skin 3 A: ghost lists stay valid until some atom has moved 1.05 A (0.7 * skin / 2), which a
+    # solid at 300 K never does -- migrations are for diffusing systems; costs ~1 % more ghosts than 1 A
+    dom = SlabDomain(s["h"], s["pbc"], 8.0, rank, world, "cuda", skin=DOMAIN_SKIN)
     dom.distribute(s["type"], s["pos"], s["mass"], vel)
     del s, vel
     md = DomainMD(dom, MODEL)
@@ -328,17 +336,24 @@ def ours_multi(args, rank, world, local, torch, dist, engine):
     cadence = 5  # displacement check (all-reduce MAX + host read) every 5 steps
     exchanges = [0]
 
+    exchange_s = [0.0]
+
     def step():
+        t0 = time.time()
         if md.maybe_exchange(cadence):
+            torch.cuda.synchronize()
             exchanges[0] += 1
+            exchange_s[0] += time.time() - t0
         md.step(dt)
 
     md.compute_force()
     md.pot.check()
     for _ in range(max(args.warmup, 3)):
         step()
+    for _ in range(2):  # the displacement check (torch ops + all-reduce MAX) is part of the loop: warm it too
+        dom.needs_exchange()
     md.pot.check()
-    sampler = ClockSampler(local) if rank == 0 else None
+    sampler = ClockSampler(local) if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER") else None
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
@@ -346,20 +361,38 @@ def ours_multi(args, rank, world, local, torch, dist, engine):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     w0 = time.time()
     e0.record()
-    for _ in range(args.steps):
+    marks = []
+    for k in range(args.steps):
         step()
+        if os.environ.get("BENCH_MARKS") and k % 10 == 9:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
     e1.record()
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
     w1 = time.time()
+    # phase breakdown (untimed extra steps with CUDA events between the phases of DomainMD.step)
+    md.enable_profile(True)
+    h0 = time.time()
+    for _ in range(10):
+        md.step(dt)
+    host_issue_ms = (time.time() - h0) * 100.0  # host time to ISSUE one step (no sync inside)
+    phase_ms = md.profile_read()
+    phase_ms["host_issue"] = host_issue_ms
+    md.enable_profile(False)
     ms_t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if marks:
+        seq = [e0] + marks
+        print(f"rank {rank}: ms per 10 steps:", [round(a.elapsed_time(b), 2) for a, b in zip(seq[:-1], seq[1:])],
+              file=sys.stderr, flush=True)
     dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms = float(ms_t.item())
     launches = engine.launch_count() - launches0
     md.pot.check()
     clocks = sampler.stop(w0, w1) if sampler else None
-    th = md.thermo.cpu().numpy()
+    th = md.read_thermo()
     loc = torch.tensor([dom.n_own, dom.n_loc], dtype=torch.float64, device="cuda")
     loc_max = loc.clone()
     dist.all_reduce(loc_max, op=dist.ReduceOp.MAX)
@@ -395,10 +428,12 @@ def ours_multi(args, rank, world, local, torch, dist, engine):
                             f"{n_global} atoms, NEP (nep_PbTe.txt), NVE dt 1 fs, 300 K",
                 "atoms_per_gpu": n_global // world,
                 "parallelism": f"{world} slab domains along x, owned-atom integration, NCCL halo of "
-                               f"FP64 ghost positions (2*rc+skin = 17 A) per force call, thermo all-reduce "
-                               f"per step, displacement-triggered migration (checked every {cadence} steps; "
-                               f"{exchanges[0]} exchanges so far)",
+                               f"FP64 ghost positions (2*rc+skin = {16 + DOMAIN_SKIN:g} A) per force call, thermo "
+                               f"all-reduce per step, displacement-triggered migration (checked every "
+                               f"{cadence} steps; {exchanges[0]} exchanges taking {exchange_s[0] * 1e3:.1f} ms "
+                               f"in warm-up + timed region)",
                 "max_owned": int(loc_max[0].item()), "max_local_with_ghosts": int(loc_max[1].item()),
+                "phase_ms_rank0": {k: round(v, 4) for k, v in (phase_ms or {}).items()},
                 "cache": "inputs larger than L2; no flush needed",
                 "final_T_K": float(th[0]), "final_U_eV_per_atom": float(th[1]) / n_global},
             "clocks": clocks,

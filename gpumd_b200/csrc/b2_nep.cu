@@ -119,16 +119,57 @@ __global__ void __launch_bounds__(MLP_BLK) k_mlp(B2NepView P)
     b2_body_mlp<DIMP, !STAGE>(mine, P, w0, b0, w1);
 }
 
+// AoS rows (thread-per-atom consumers gather one row per neighbour): each thread contracts its
+// own row, the block transposes it through shared memory so that the global stores are runs of
+// consecutive floats instead of one 4-byte store per thread per element (same arithmetic as
+// b2_body_utable, which tests/emu runs).
 template <int K1>
 __global__ void __launch_bounds__(BLK) k_utable(B2NepView P)
 {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.n)
+  constexpr int KP = (K1 + 3) / 4 * 4;
+  __shared__ float tile[BLK][KP + 1];
+  const int base = blockIdx.x * BLK;
+  const int i = base + threadIdx.x;
+  if (P.team) {
+    if (i < P.n)
+      b2_body_utable_planes<K1>(i, P);
     return;
-  if (P.team)
-    b2_body_utable_planes<K1>(i, P);
-  else
-    b2_body_utable<K1>(i, P);
+  }
+  const int t = i < P.n ? P.atoms[i].type : 0;
+  float fp[8]; // nr1 <= n_max_radial + 1; larger models take the loop below in two halves
+  const int nr1 = P.nr1;
+  for (int t2 = 0; t2 < P.nt; ++t2) {
+    float u[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+      u[k] = 0.0f;
+    if (i < P.n) {
+      const float* c = P.c_r + (size_t)(t * P.nt + t2) * nr1 * K1;
+      for (int n0 = 0; n0 < nr1; n0 += 8) {
+#pragma unroll
+        for (int m = 0; m < 8; ++m)
+          fp[m] = (n0 + m < nr1) ? P.FpR[(size_t)(n0 + m) * P.n + i] : 0.0f;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) {
+          if (n0 + m < nr1) {
+#pragma unroll
+            for (int k = 0; k < K1; ++k)
+              u[k] = fmaf(fp[m], __ldg(&c[(n0 + m) * K1 + k]), u[k]);
+          }
+        }
+      }
+    }
+    __syncthreads(); // previous t2's tile has been written out
+#pragma unroll
+    for (int k = 0; k < KP; ++k)
+      tile[threadIdx.x][k] = u[k];
+    __syncthreads();
+    for (int e = threadIdx.x; e < BLK * KP; e += BLK) {
+      const int r = e / KP, k = e - r * KP;
+      if (base + r < P.n)
+        P.U[(size_t)(base + r) * P.UST + t2 * KP + k] = tile[r][k];
+    }
+  }
 }
 
 // MINB: resident blocks per SM the register allocation is tuned for (latency hiding vs spills)

@@ -221,9 +221,8 @@ class SlabDomain:
         p[:, n:n + self.n_ghost_right] = self.recv_right.view(3, self.n_ghost_right)
         p[:, n + self.n_ghost_right:] = self.recv_left.view(3, self.n_ghost_left)
 
-    def allreduce_thermo(self, thermo):
-        dist.all_reduce(thermo, op=dist.ReduceOp.SUM)
-        return thermo
+    def allreduce_thermo(self, thermo, async_op=False):
+        return dist.all_reduce(thermo, op=dist.ReduceOp.SUM, async_op=async_op)
 
 
 class DomainMD:
@@ -250,6 +249,8 @@ class DomainMD:
         self.temperature = float(temperature)
         self.temperature_coupling = float(temperature_coupling)
         self._nhc = None
+        self.profile = None  # enable_profile(): {phase: [ms_sum, count]} from CUDA events
+        self._pending = []
         if ensemble == "nvt_nhc":
             h = C.c_void_p()
             self._lib.check(self.L.b200md_nhc_create(
@@ -266,6 +267,33 @@ class DomainMD:
     def _st(self):
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
 
+    # ---- optional per-phase device timing (CUDA events on the current stream) ----
+    def enable_profile(self, on=True):
+        self.profile = {} if on else None
+        self._pending = []
+
+    def _mark(self, name):
+        """Close the phase opened by the previous _mark (if any) and open `name`."""
+        if self.profile is None:
+            return
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        self._pending.append((name, ev))
+
+    def profile_read(self):
+        """Mean milliseconds per occurrence of every phase since enable_profile()."""
+        if self.profile is None:
+            return None
+        torch.cuda.synchronize()
+        for (name, e0), (_, e1) in zip(self._pending[:-1], self._pending[1:]):
+            if name is None:
+                continue
+            acc = self.profile.setdefault(name, [0.0, 0])
+            acc[0] += e0.elapsed_time(e1)
+            acc[1] += 1
+        self._pending = []
+        return {k: v[0] / max(v[1], 1) for k, v in self.profile.items()}
+
     @staticmethod
     def _p(t):
         return C.c_void_p(t.data_ptr())
@@ -280,7 +308,7 @@ class DomainMD:
 
     def _nhc_half(self, dt):
         d = self.dom
-        self.find_thermo(True)
+        self.find_thermo(True, wait=True)
         self._lib.check(self.L.b200md_nhc_half_step(
             self._nhc, d.n_own, d.n_loc, float(dt), self._p(self.thermo), self._p(d.vel), self._st()))
 
@@ -300,6 +328,7 @@ class DomainMD:
     def step(self, dt, reduce_thermo=True):
         d = self.dom
         L, st = self.L, self._st()
+        self._mark("vv1+wrap")
         if self._nhc is not None:
             self._nhc_half(dt)
         self._lib.check(L.b200md_velocity_verlet_strided(
@@ -307,28 +336,50 @@ class DomainMD:
             self._p(d.force), st))
         self._lib.check(L.b200md_apply_pbc_strided(
             d.n_own, d.n_loc, self.box._h, self.box._p, self._p(d.pos), st))
+        self._mark("halo")
         d.halo_update()
+        self._mark("force")
         self.compute_force()
+        self._mark("vv2+thermo")
         self._lib.check(L.b200md_velocity_verlet_strided(
             0, d.n_own, d.n_loc, float(dt), self._p(d.mass), self._p(d.pos), self._p(d.vel),
             self._p(d.force), st))
         if self._nhc is not None:
             self._nhc_half(dt)
         else:
-            self.find_thermo(reduce_thermo or self.ensemble == "nvt_ber")
+            self.find_thermo(reduce_thermo or self.ensemble == "nvt_ber", wait=self.ensemble == "nvt_ber")
             if self.ensemble == "nvt_ber":
                 self._lib.check(L.b200md_berendsen_temperature(
                     d.n_own, d.n_loc, self.temperature, self.temperature_coupling, self._p(self.thermo),
                     self._p(d.vel), st))
         self.steps_since_exchange += 1
+        self._mark(None)
 
-    def find_thermo(self, reduce=True):
+    def find_thermo(self, reduce=True, wait=False):
         d = self.dom
+        self.thermo_wait()  # the previous all-reduce must be done before thermo is overwritten
         self._lib.check(self.L.b200md_find_thermo_strided(
             d.n_own, d.n_loc, d.n_global, d.volume, self._p(d.mass), self._p(d.pe), self._p(d.vel),
             self._p(d.virial), self._p(self.thermo), self._p(self._scratch), self._st()))
         if reduce:
-            d.allreduce_thermo(self.thermo)
+            # asynchronous: the 8-double all-reduce runs on the communication stream while the next
+            # step's kernels start; thermo_wait() (or the next find_thermo) joins it
+            self._thermo_work = d.allreduce_thermo(self.thermo, async_op=True)
+            if wait:
+                self.thermo_wait()
+
+    def read_thermo(self):
+        """Global thermo[0..7] = T, U, sxx, syy, szz, sxy, sxz, syz as a host array."""
+        self.thermo_wait()
+        return self.thermo.cpu().numpy().copy()
+
+    def thermo_wait(self):
+        """Make the current stream wait for the pending thermo all-reduce (call before reading
+        self.thermo)."""
+        w = getattr(self, "_thermo_work", None)
+        if w is not None:
+            w.wait()
+            self._thermo_work = None
 
     def exchange(self):
         """Migration + new ghost lists; invalidates the potential's cell order."""

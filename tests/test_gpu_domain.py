@@ -37,7 +37,7 @@ def _worker(rank, world, port, out_dir, steps):
         md = DomainMD(dom, GOLDEN / "nep_PbTe.txt")
         md.compute_force()
         md.find_thermo()
-        rows = [md.thermo.cpu().numpy().copy()]
+        rows = [md.read_thermo()]
         dt = 2.0 / TIME_UNIT_CONVERSION
         for k in range(steps):
             if k == 30:
@@ -46,7 +46,7 @@ def _worker(rank, world, port, out_dir, steps):
                 md.maybe_exchange(5)
             md.step(dt)
             if (k + 1) % 10 == 0:
-                rows.append(md.thermo.cpu().numpy().copy())
+                rows.append(md.read_thermo())
         md.pot.check()
         if rank == 0:
             np.save(os.path.join(out_dir, "multi.npy"), np.array(rows))
