@@ -173,13 +173,13 @@ __global__ void __launch_bounds__(BLK) k_utable(B2NepView P)
 }
 
 // MINB: resident blocks per SM the register allocation is tuned for (latency hiding vs spills)
-template <int NT, int K1, int MINB>
+template <int NT, int K1, int MINB, int DEPTH>
 __global__ void __launch_bounds__(BLK, MINB)
   k_force_final(B2NepView P, B2Box box, double* pe, double* force, double* virial)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < P.n)
-    b2_body_force_final<NT, K1>(i, P, box, pe, force, virial);
+    b2_body_force_final<NT, K1, DEPTH>(i, P, box, pe, force, virial);
 }
 
 template <int K1>
@@ -312,9 +312,11 @@ int launch_force_final(
 {
   const int g = grid_for(p->n, BLK);
   switch (p->variant) {
-    case 1: k_force_final<NT, K1, 6><<<g, BLK, 0, st>>>(p->view, box, pe, f, v); break;
-    case 2: k_force_final<NT, K1, 8><<<g, BLK, 0, st>>>(p->view, box, pe, f, v); break;
-    default: k_force_final<NT, K1, 5><<<g, BLK, 0, st>>>(p->view, box, pe, f, v); break;
+    // measured on 1 M-atom PbTe (profiles/r01_f_ab.md): 96 regs / depth 1 = 1.02 ms (default);
+    // 80 regs (6 blocks/SM) 1.02; 64 regs (8 blocks, spills) 1.29; depth 2 at 114 regs 1.20
+    case 1: k_force_final<NT, K1, 6, 1><<<g, BLK, 0, st>>>(p->view, box, pe, f, v); break;
+    case 2: k_force_final<NT, K1, 4, 2><<<g, BLK, 0, st>>>(p->view, box, pe, f, v); break;
+    default: k_force_final<NT, K1, 5, 1><<<g, BLK, 0, st>>>(p->view, box, pe, f, v); break;
   }
   B2_LAUNCHED();
   return B200MD_OK;

@@ -625,21 +625,92 @@ B2_HD void b2_body_utable_planes(int i, const B2NepView& P)
 //   W_i^ab += r12^a * f21^b,      f21 = -B * r12 / d
 // ---------------------------------------------------------------------------------------------
 // out[12] = fx,fy,fz, vxx,vyy,vzz,vxy,vxz,vyz,vyx,vzx,vzy (FP32 partial sums of this stage)
+// one pair of the radial force; acc = fx,fy,fz,vxx,vyy,vzz,vxy,vxz,vyz
 template <int NT, int K1>
+B2_HD void b2_radial_pair(
+  const B2NepView& P, const B2Geo& geo, const B2Box& box, const B2Atom& a1, int t1,
+  const B2Atom& a2, const float* Uj, const float (*Ur)[K1], const float* rcv, const float* rciv,
+  const float* Ui, float* acc)
+{
+  float x12, y12, z12;
+  b2_r12(geo, box, a1, a2, x12, y12, z12);
+  const float d2 = b2_d2(x12, y12, z12);
+  const float dinv = b2_rsqrt(d2);
+  const float d = d2 * dinv;
+  const int t2 = a2.type;
+  float rc, rcinv;
+  if (NT == 1) {
+    rc = rcv[0];
+    rcinv = rciv[0];
+  } else if (NT > 1) {
+    rc = rcv[0];
+    rcinv = rciv[0];
+#pragma unroll
+    for (int t = 1; t < (NT > 0 ? NT : 1); ++t) {
+      rc = (t2 == t) ? rcv[t] : rc;
+      rcinv = (t2 == t) ? rciv[t] : rcinv;
+    }
+  } else {
+    const int pair = t1 * P.nt + t2;
+    rc = B2_LDG(&P.rc_r[pair]);
+    rcinv = B2_LDG(&P.rcinv_r[pair]);
+  }
+  float fnp[K1];
+  b2_basis_d<K1, false>(d, rc, rcinv, nullptr, fnp);
+  float A = 0.0f, Bv = 0.0f;
+  if (NT == 1) {
+#pragma unroll
+    for (int k = 0; k < K1; ++k)
+      A = fmaf(fnp[k], Ur[0][k], A);
+  } else if (NT > 1) {
+#pragma unroll
+    for (int k = 0; k < K1; ++k) {
+      float u = Ur[0][k];
+#pragma unroll
+      for (int t = 1; t < (NT > 0 ? NT : 1); ++t)
+        u = (t2 == t) ? Ur[t][k] : u;
+      A = fmaf(fnp[k], u, A);
+    }
+  } else {
+    const float* Uit = Ui + t2 * P.KP;
+#pragma unroll
+    for (int k = 0; k < K1; ++k)
+      A = fmaf(fnp[k], Uit[k], A);
+  }
+#pragma unroll
+  for (int k = 0; k < K1; ++k)
+    Bv = fmaf(fnp[k], Uj[k], Bv);
+  const float sA = (A + Bv) * dinv;
+  const float sB = -Bv * dinv; // f21 = sB * r12
+  acc[0] = fmaf(sA, x12, acc[0]);
+  acc[1] = fmaf(sA, y12, acc[1]);
+  acc[2] = fmaf(sA, z12, acc[2]);
+  acc[3] = fmaf(x12 * x12, sB, acc[3]);
+  acc[4] = fmaf(y12 * y12, sB, acc[4]);
+  acc[5] = fmaf(z12 * z12, sB, acc[5]);
+  acc[6] = fmaf(x12 * y12, sB, acc[6]);
+  acc[7] = fmaf(x12 * z12, sB, acc[7]);
+  acc[8] = fmaf(y12 * z12, sB, acc[8]);
+}
+
+// DEPTH = neighbours whose record and U row are in flight while one is evaluated (1 or 2); the
+// loop is latency-bound on those dependent gathers (index -> record / U row)
+template <int NT, int K1, int DEPTH>
 B2_HD void b2_force_radial_sum(int i, const B2NepView& P, const B2Box& box, float* out)
 {
   constexpr int KP4 = (K1 + 3) / 4; // float4 loads per U row (KP = 4*KP4)
+  constexpr int NTA = NT > 0 ? NT : 1;
   const B2Geo geo = b2_geo(box);
   const size_t N = (size_t)P.n;
   const B2Atom a1 = P.atoms[i];
   const int t1 = a1.type;
   const int nn = P.nn_r[i];
   const float* Ui = P.U + (size_t)i * P.UST;
-  float Ur[NT > 0 ? NT : 1][K1];
-  float rcv[NT > 0 ? NT : 1], rciv[NT > 0 ? NT : 1]; // pair cutoffs of (t1, t) for the few-type path
+  float Ur[NTA][K1];
+  float rcv[NTA], rciv[NTA]; // pair cutoffs of (t1, t) for the few-type path
   if (NT > 0) {
 #pragma unroll
-    for (int t = 0; t < (NT > 0 ? NT : 1); ++t) {
+    for (int t = 0; t < NTA; ++t) {
       const int pr = t1 * P.nt + (t < P.nt ? t : 0);
       rcv[t] = B2_LDG(&P.rc_r[pr]);
       rciv[t] = B2_LDG(&P.rcinv_r[pr]);
@@ -648,107 +719,60 @@ B2_HD void b2_force_radial_sum(int i, const B2NepView& P, const B2Box& box, floa
         Ur[t][k] = (t < P.nt) ? Ui[t * P.KP + k] : 0.0f;
     }
   }
-  float fx = 0.0f, fy = 0.0f, fz = 0.0f;
-  float vxx = 0.0f, vyy = 0.0f, vzz = 0.0f, vxy = 0.0f, vxz = 0.0f, vyz = 0.0f;
-  // software pipeline (dependent loads index -> record / U row): neighbour s+1's record and U row
-  // and neighbour s+2's index are in flight while neighbour s is evaluated
+  float acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k)
+    acc[k] = 0.0f;
   const float4* Ubase = reinterpret_cast<const float4*>(P.U + (size_t)t1 * P.KP);
   const size_t ust4 = (size_t)P.UST / 4;
-  int jn = nn > 0 ? P.nl_r[i] : i;
-  B2Atom an = b2_load_atom(&P.atoms[jn]);
-  float4 un[KP4];
+  // software pipeline: records / U rows of the next DEPTH neighbours and the index after them
+  // are in flight while neighbour s is evaluated
+  B2Atom an[DEPTH];
+  float4 un[DEPTH][KP4];
 #pragma unroll
-  for (int q = 0; q < KP4; ++q)
-    un[q] = B2_LDG(&Ubase[(size_t)jn * ust4 + q]);
-  int j2 = nn > 1 ? P.nl_r[N + i] : i;
-  for (int s = 0; s < nn; ++s) {
-    const B2Atom a2 = an;
-    float Uj[KP4 * 4];
-#pragma unroll
-    for (int q = 0; q < KP4; ++q) {
-      Uj[4 * q] = un[q].x;
-      Uj[4 * q + 1] = un[q].y;
-      Uj[4 * q + 2] = un[q].z;
-      Uj[4 * q + 3] = un[q].w;
-    }
-    an = b2_load_atom(&P.atoms[j2]);
+  for (int p = 0; p < DEPTH; ++p) {
+    const int jp = p < nn ? P.nl_r[(size_t)p * N + i] : i;
+    an[p] = b2_load_atom(&P.atoms[jp]);
 #pragma unroll
     for (int q = 0; q < KP4; ++q)
-      un[q] = B2_LDG(&Ubase[(size_t)j2 * ust4 + q]);
-    j2 = (s + 2 < nn) ? P.nl_r[(size_t)(s + 2) * N + i] : i;
-
-    float x12, y12, z12;
-    b2_r12(geo, box, a1, a2, x12, y12, z12);
-    const float d2 = b2_d2(x12, y12, z12);
-    const float dinv = b2_rsqrt(d2);
-    const float d = d2 * dinv;
-    const int t2 = a2.type;
-    float rc, rcinv;
-    if (NT == 1) {
-      rc = rcv[0];
-      rcinv = rciv[0];
-    } else if (NT > 1) {
-      rc = rcv[0];
-      rcinv = rciv[0];
-#pragma unroll
-      for (int t = 1; t < (NT > 0 ? NT : 1); ++t) {
-        rc = (t2 == t) ? rcv[t] : rc;
-        rcinv = (t2 == t) ? rciv[t] : rcinv;
-      }
-    } else {
-      const int pair = t1 * P.nt + t2;
-      rc = B2_LDG(&P.rc_r[pair]);
-      rcinv = B2_LDG(&P.rcinv_r[pair]);
-    }
-    float fnp[K1];
-    b2_basis_d<K1, false>(d, rc, rcinv, nullptr, fnp);
-    float A = 0.0f, Bv = 0.0f;
-    if (NT == 1) {
-#pragma unroll
-      for (int k = 0; k < K1; ++k)
-        A = fmaf(fnp[k], Ur[0][k], A);
-    } else if (NT > 1) {
-#pragma unroll
-      for (int k = 0; k < K1; ++k) {
-        float u = Ur[0][k];
-#pragma unroll
-        for (int t = 1; t < (NT > 0 ? NT : 1); ++t)
-          u = (t2 == t) ? Ur[t][k] : u;
-        A = fmaf(fnp[k], u, A);
-      }
-    } else {
-      const float* Uit = Ui + t2 * P.KP;
-#pragma unroll
-      for (int k = 0; k < K1; ++k)
-        A = fmaf(fnp[k], Uit[k], A);
-    }
-#pragma unroll
-    for (int k = 0; k < K1; ++k)
-      Bv = fmaf(fnp[k], Uj[k], Bv);
-    const float sA = (A + Bv) * dinv;
-    const float sB = -Bv * dinv; // f21 = sB * r12
-    fx = fmaf(sA, x12, fx);
-    fy = fmaf(sA, y12, fy);
-    fz = fmaf(sA, z12, fz);
-    vxx = fmaf(x12 * x12, sB, vxx);
-    vyy = fmaf(y12 * y12, sB, vyy);
-    vzz = fmaf(z12 * z12, sB, vzz);
-    vxy = fmaf(x12 * y12, sB, vxy);
-    vxz = fmaf(x12 * z12, sB, vxz);
-    vyz = fmaf(y12 * z12, sB, vyz);
+      un[p][q] = B2_LDG(&Ubase[(size_t)jp * ust4 + q]);
   }
-  out[0] = fx;
-  out[1] = fy;
-  out[2] = fz;
-  out[3] = vxx;
-  out[4] = vyy;
-  out[5] = vzz;
-  out[6] = vxy;
-  out[7] = vxz;
-  out[8] = vyz;
-  out[9] = vxy; // yx: the radial pair virial r12 (x) f21 is symmetric
-  out[10] = vxz; // zx
-  out[11] = vyz; // zy
+  int jnext = DEPTH < nn ? P.nl_r[(size_t)DEPTH * N + i] : i;
+  for (int s = 0; s < nn; s += DEPTH) {
+#pragma unroll
+    for (int p = 0; p < DEPTH; ++p) {
+      const B2Atom a2 = an[p];
+      float Uj[KP4 * 4];
+#pragma unroll
+      for (int q = 0; q < KP4; ++q) {
+        Uj[4 * q] = un[p][q].x;
+        Uj[4 * q + 1] = un[p][q].y;
+        Uj[4 * q + 2] = un[p][q].z;
+        Uj[4 * q + 3] = un[p][q].w;
+      }
+      // refill slot p with neighbour s + p + DEPTH, fetch the index after it
+      const int jl = jnext;
+      an[p] = b2_load_atom(&P.atoms[jl]);
+#pragma unroll
+      for (int q = 0; q < KP4; ++q)
+        un[p][q] = B2_LDG(&Ubase[(size_t)jl * ust4 + q]);
+      jnext = (s + p + DEPTH + 1 < nn) ? P.nl_r[(size_t)(s + p + DEPTH + 1) * N + i] : i;
+      if (s + p < nn)
+        b2_radial_pair<NT, K1>(P, geo, box, a1, t1, a2, Uj, Ur, rcv, rciv, Ui, acc);
+    }
+  }
+  out[0] = acc[0];
+  out[1] = acc[1];
+  out[2] = acc[2];
+  out[3] = acc[3];
+  out[4] = acc[4];
+  out[5] = acc[5];
+  out[6] = acc[6];
+  out[7] = acc[7];
+  out[8] = acc[8];
+  out[9] = acc[6];  // yx: the radial pair virial r12 (x) f21 is symmetric
+  out[10] = acc[7]; // zx
+  out[11] = acc[8]; // zy
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1045,13 +1069,13 @@ B2_HD void b2_zbl_sum(
 // nep.cu:653,755-770).  Each stage keeps its own FP32 partial sums and they are combined in FP64,
 // exactly like the reference's separate kernels adding into double arrays.
 // ---------------------------------------------------------------------------------------------
-template <int NT, int K1>
+template <int NT, int K1, int DEPTH = 1>
 B2_HD void b2_body_force_final(
   int i, const B2NepView& P, const B2Box& box, double* pe, double* force, double* virial)
 {
   float r[12], a[12], z[12];
   float zpe = 0.0f;
-  b2_force_radial_sum<NT, K1>(i, P, box, r);
+  b2_force_radial_sum<NT, K1, DEPTH>(i, P, box, r);
   b2_reduce_angular_sum(i, P, box, a);
   if (P.zbl_enabled) {
     b2_zbl_sum(i, P, box, z, zpe);
