@@ -3,11 +3,13 @@
 // b200md_zero_properties, b200md_velocity_verlet, b200md_find_thermo, b200md_scale_velocity.
 #include "../../include/b200md.h"
 #include "b2_host.h"
+#include "b2_bdp.cuh"
 #include "b2_integrate.cuh"
 #include "b2_lj.cuh"
 #include "b2_neighbor_host.h"
 #include "b2_nep.cuh" // b2_body_unpack
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <new>
@@ -138,6 +140,22 @@ __global__ void k_nhc_chain(
     }
   }
   state[3 * M] = factor;
+}
+
+__global__ void k_bdp_seed(B2BdpState* state, unsigned seed)
+{
+  if (threadIdx.x == 0 && blockIdx.x == 0)
+    b2_mt_seed(*state, seed);
+}
+
+// BDP: one thread advances the generator and leaves the factor in the state record
+__global__ void k_bdp_factor(
+  B2BdpState* state, const double* __restrict__ thermo, int ndeg, double temperature,
+  double temperature_coupling)
+{
+  if (threadIdx.x != 0 || blockIdx.x != 0)
+    return;
+  state->factor = b2_bdp_factor(*state, thermo[0], ndeg, temperature, temperature_coupling);
 }
 
 __global__ void __launch_bounds__(BLK) k_scale_by(
@@ -545,6 +563,55 @@ int b200md_nhc_half_step(
   k_nhc_chain<<<1, 32, 0, st>>>(p->state.p, d_thermo, p->dof, p->kT, 0.5 * time_step);
   B2_LAUNCHED();
   k_scale_by<<<grid_for(n, BLK), BLK, 0, st>>>(n, stride, p->state.p + 12, d_velocity);
+  B2_LAUNCHED();
+  return B200MD_OK;
+}
+
+struct b200md_bdp {
+  DevBuf<B2BdpState> state;
+  int ndeg = 0;
+  double temperature = 0.0, coupling = 0.0;
+};
+
+int b200md_bdp_create(
+  long long n_global, double temperature, double temperature_coupling, unsigned seed,
+  b200md_bdp** out)
+{
+  if (n_global < 1 || 3 * n_global > 2147483647LL || temperature <= 0.0) {
+    set_error("b200md_bdp_create: bad atom count or temperature");
+    return B200MD_ERR_ARG;
+  }
+  b200md_bdp* p = new (std::nothrow) b200md_bdp;
+  if (!p || p->state.reserve(1) != cudaSuccess) {
+    delete p;
+    set_error("b200md_bdp_create: allocation failed");
+    return B200MD_ERR_CUDA;
+  }
+  k_bdp_seed<<<1, 32>>>(p->state.p, seed);
+  const cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) {
+    delete p;
+    set_error(cudaGetErrorString(e));
+    return B200MD_ERR_CUDA;
+  }
+  p->ndeg = (int)(3 * n_global);
+  p->temperature = temperature;
+  p->coupling = temperature_coupling;
+  *out = p;
+  return B200MD_OK;
+}
+
+void b200md_bdp_destroy(b200md_bdp* p) { delete p; }
+
+int b200md_bdp_step(
+  b200md_bdp* p, int n, int stride, const double* d_thermo, double* d_velocity, void* stream)
+{
+  cudaStream_t st = (cudaStream_t)stream;
+  k_bdp_factor<<<1, 32, 0, st>>>(p->state.p, d_thermo, p->ndeg, p->temperature, p->coupling);
+  B2_LAUNCHED();
+  const double* factor = reinterpret_cast<const double*>(
+    reinterpret_cast<const char*>(p->state.p) + offsetof(B2BdpState, factor));
+  k_scale_by<<<grid_for(n, BLK), BLK, 0, st>>>(n, stride, factor, d_velocity);
   B2_LAUNCHED();
   return B200MD_OK;
 }

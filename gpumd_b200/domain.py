@@ -249,6 +249,7 @@ class DomainMD:
         self.temperature = float(temperature)
         self.temperature_coupling = float(temperature_coupling)
         self._nhc = None
+        self._bdp = None
         self.profile = None  # enable_profile(): {phase: [ms_sum, count]} from CUDA events
         self._pending = []
         if ensemble == "nvt_nhc":
@@ -256,6 +257,11 @@ class DomainMD:
             self._lib.check(self.L.b200md_nhc_create(
                 int(dom.n_global), self.temperature, self.temperature_coupling, float(time_step), C.byref(h)))
             self._nhc = h
+        elif ensemble == "nvt_bdp":
+            h = C.c_void_p()
+            self._lib.check(self.L.b200md_bdp_create(
+                int(dom.n_global), self.temperature, self.temperature_coupling, 12345678, C.byref(h)))
+            self._bdp = h  # every rank advances an identical generator from the all-reduced T
         elif ensemble not in ("nve", "nvt_ber"):
             raise ValueError(f"unsupported ensemble {ensemble}")
 
@@ -263,6 +269,9 @@ class DomainMD:
         if getattr(self, "_nhc", None):
             self.L.b200md_nhc_destroy(self._nhc)
             self._nhc = None
+        if getattr(self, "_bdp", None):
+            self.L.b200md_bdp_destroy(self._bdp)
+            self._bdp = None
 
     def _st(self):
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -347,7 +356,11 @@ class DomainMD:
         if self._nhc is not None:
             self._nhc_half(dt)
         else:
-            self.find_thermo(reduce_thermo or self.ensemble == "nvt_ber", wait=self.ensemble == "nvt_ber")
+            scaled = self.ensemble in ("nvt_ber", "nvt_bdp")
+            self.find_thermo(reduce_thermo or scaled, wait=scaled)
+            if self.ensemble == "nvt_bdp":
+                self._lib.check(L.b200md_bdp_step(
+                    self._bdp, d.n_own, d.n_loc, self._p(self.thermo), self._p(d.vel), st))
             if self.ensemble == "nvt_ber":
                 self._lib.check(L.b200md_berendsen_temperature(
                     d.n_own, d.n_loc, self.temperature, self.temperature_coupling, self._p(self.thermo),

@@ -370,6 +370,30 @@ class Ensemble_BER(Ensemble_NVE):
             _ptr(atom.velocity_per_atom), _stream()))
 
 
+class Ensemble_BDP(Ensemble_NVE):
+    """nvt_bdp, src/integrate/ensemble_bdp.cu:69-101: velocity-Verlet, thermo, then the stochastic
+    rescaling of Bussi et al.; generator and factor live on the device (seed 12345678 = the
+    reference's -DDEBUG stream)."""
+
+    def __init__(self, num_atoms, temperature, temperature_coupling, seed=12345678):
+        super().__init__(num_atoms)
+        h = C.c_void_p()
+        _lib.check(self._L.b200md_bdp_create(int(num_atoms), float(temperature),
+                                             float(temperature_coupling), int(seed), C.byref(h)))
+        self._bdp = h
+
+    def __del__(self):
+        if getattr(self, "_bdp", None):
+            self._L.b200md_bdp_destroy(self._bdp)
+            self._bdp = None
+
+    def compute2(self, time_step, box, atom, thermo):
+        super().compute2(time_step, box, atom, thermo)
+        n = atom.number_of_atoms
+        _lib.check(self._L.b200md_bdp_step(
+            self._bdp, n, n, _ptr(thermo), _ptr(atom.velocity_per_atom), _stream()))
+
+
 class Ensemble_NHC(Ensemble_NVE):
     """nvt_nhc, src/integrate/ensemble_nhc.cu:173-237 (chain integrated on the device)."""
 

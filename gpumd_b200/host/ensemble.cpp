@@ -60,6 +60,33 @@ void Ensemble_BER_B200::compute2(
     b2h_fail("Ensemble_BER_B200::compute2");
 }
 
+Ensemble_BDP_B200::Ensemble_BDP_B200(int t, int N, double T, double Tc, unsigned seed)
+{
+  type = t;
+  temperature = T;
+  if (b200md_bdp_create(N, T, Tc, seed, &bdp_) != B200MD_OK)
+    b2h_fail("Ensemble_BDP_B200");
+}
+
+Ensemble_BDP_B200::~Ensemble_BDP_B200() { b200md_bdp_destroy(bdp_); }
+
+void Ensemble_BDP_B200::compute1(
+  const double time_step, const std::vector<Group>&, Box&, Atom& atom, GPU_Vector<double>&)
+{
+  velocity_verlet(true, time_step, atom);
+}
+
+void Ensemble_BDP_B200::compute2(
+  const double time_step, const std::vector<Group>&, Box& box, Atom& atom,
+  GPU_Vector<double>& thermo)
+{
+  velocity_verlet(false, time_step, atom);
+  find_thermo(box.get_volume(), atom, thermo);
+  const int n = atom.number_of_atoms;
+  if (b200md_bdp_step(bdp_, n, n, thermo.data(), atom.velocity_per_atom.data(), nullptr) != B200MD_OK)
+    b2h_fail("Ensemble_BDP_B200::compute2");
+}
+
 Ensemble_NHC_B200::Ensemble_NHC_B200(int t, int N, double T, double Tc, double time_step)
 {
   type = t;

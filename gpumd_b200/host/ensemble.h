@@ -46,6 +46,24 @@ public:
   double temperature_coupling = 100.0;
 };
 
+// replaces Ensemble_BDP for type 4 (nvt_bdp), src/integrate/ensemble_bdp.cu:69-101,151-196; the
+// generator lives on the device and follows the reference's -DDEBUG stream (seed 12345678)
+class Ensemble_BDP_B200 : public Ensemble
+{
+public:
+  Ensemble_BDP_B200(int t, int N, double T, double Tc, unsigned seed = 12345678u);
+  ~Ensemble_BDP_B200() override;
+  void compute1(
+    const double time_step, const std::vector<Group>& group, Box& box, Atom& atom,
+    GPU_Vector<double>& thermo) override;
+  void compute2(
+    const double time_step, const std::vector<Group>& group, Box& box, Atom& atom,
+    GPU_Vector<double>& thermo) override;
+
+private:
+  b200md_bdp* bdp_ = nullptr;
+};
+
 // replaces Ensemble_NHC for type 2 (nvt_nhc), src/integrate/ensemble_nhc.cu:173-237
 class Ensemble_NHC_B200 : public Ensemble
 {

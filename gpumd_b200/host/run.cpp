@@ -8,7 +8,7 @@
 //   initialize_position (model.xyz)                 src/model/read_xyz.cu:145-425, 482-557
 //   Velocity::initialize                            src/main_gpumd/velocity.cu:55-75, 312-347
 //   Dump_Thermo                                     src/measure/dump_thermo.cu:57-129
-// Keywords: potential, velocity <T> [seed <s>], ensemble nve | nvt_ber T T tau | nvt_nhc T T tau,
+// Keywords: potential, velocity <T> [seed <s>], ensemble nve | nvt_ber|nvt_nhc|nvt_bdp T T tau,
 // time_step <fs>, dump_thermo <n>, run <n>.  Anything else is an input error (exit 1), as in the reference.
 #include "ensemble.h"
 #include "force.h"
@@ -279,7 +279,7 @@ private:
       // Integrate::parse_ensemble, integrate.cu:406-432,569-600: nvt_* take T1 T2 tau_T/dt
       if (t.size() == 2 && t[1] == "nve") {
         ensemble_.reset(new Ensemble_NVE_B200(0));
-      } else if (t.size() == 5 && (t[1] == "nvt_ber" || t[1] == "nvt_nhc")) {
+      } else if (t.size() == 5 && (t[1] == "nvt_ber" || t[1] == "nvt_nhc" || t[1] == "nvt_bdp")) {
         const double T1 = std::atof(t[2].c_str()), T2 = std::atof(t[3].c_str());
         const double Tc = std::atof(t[4].c_str());
         if (T1 <= 0.0 || T2 <= 0.0)
@@ -290,10 +290,12 @@ private:
           input_error("Temperature coupling should >= 1.");
         if (t[1] == "nvt_ber")
           ensemble_.reset(new Ensemble_BER_B200(1, T1, Tc));
+        else if (t[1] == "nvt_bdp")
+          ensemble_.reset(new Ensemble_BDP_B200(4, a.number_of_atoms, T1, Tc));
         else
           ensemble_.reset(new Ensemble_NHC_B200(2, a.number_of_atoms, T1, Tc, time_step_));
       } else {
-        input_error("only 'ensemble nve', 'nvt_ber T T tau' and 'nvt_nhc T T tau' are supported "
+        input_error("only 'ensemble nve', 'nvt_ber|nvt_nhc|nvt_bdp T T tau' are supported "
                     "by the b200md backend.");
       }
     } else if (t[0] == "time_step") {

@@ -66,6 +66,9 @@ SIGNATURES = {
     "b200md_nhc_create": (C.c_int, [C.c_longlong, C.c_double, C.c_double, C.c_double, C.POINTER(_vp)]),
     "b200md_nhc_destroy": (None, [_vp]),
     "b200md_nhc_half_step": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp]),
+    "b200md_bdp_create": (C.c_int, [C.c_longlong, C.c_double, C.c_double, C.c_uint, C.POINTER(_vp)]),
+    "b200md_bdp_destroy": (None, [_vp]),
+    "b200md_bdp_step": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp]),
     "b200md_apply_pbc_strided": (C.c_int, [C.c_int, C.c_int, _dp, _ip, _vp, _vp]),
     "b200md_velocity_verlet_strided": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "b200md_find_thermo_strided": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

@@ -187,7 +187,13 @@ int b200md_scale_velocity(int n, double factor, double* d_velocity, void* stream
  *   b200md_nhc_*                 <- Ensemble_NHC (src/integrate/ensemble_nhc.cu:31-50, 101-237):
  *                                   one call = find chain factor from d_thermo[0] + scale velocities,
  *                                   i.e. the thermostat half of integrate_nvt_nhc_1 / _2.  The chain
- *                                   is integrated on the device: no D2H copy per half step. */
+ *                                   is integrated on the device: no D2H copy per half step.
+ *   b200md_bdp_*                 <- Ensemble_BDP, NVT branch (src/integrate/ensemble_bdp.cu:69-101,
+ *                                   svr_utilities.cuh:27-135): stochastic velocity rescaling after
+ *                                   the second half step.  The generator (std::mt19937 semantics)
+ *                                   lives on the device; seed 12345678 reproduces the reference's
+ *                                   -DDEBUG stream (ensemble_bdp.cu:31-32).  3*n_global must fit an
+ *                                   int, as in the reference. */
 int b200md_berendsen_temperature(
   int n, int stride, double temperature, double temperature_coupling, const double* d_thermo,
   double* d_velocity, void* stream);
@@ -199,6 +205,13 @@ void b200md_nhc_destroy(b200md_nhc* p);
 int b200md_nhc_half_step(
   b200md_nhc* p, int n, int stride, double time_step, const double* d_thermo, double* d_velocity,
   void* stream);
+typedef struct b200md_bdp b200md_bdp;
+int b200md_bdp_create(
+  long long n_global, double temperature, double temperature_coupling, unsigned seed,
+  b200md_bdp** out);
+void b200md_bdp_destroy(b200md_bdp* p);
+int b200md_bdp_step(
+  b200md_bdp* p, int n, int stride, const double* d_thermo, double* d_velocity, void* stream);
 
 /* ------------------------------------------------------------------------------------------
  * Spatial-domain sharding (replaces the hub-and-spoke scatter/gather of NEP_MULTIGPU,

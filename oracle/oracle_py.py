@@ -8,6 +8,8 @@ import os
 import subprocess
 from pathlib import Path
 
+import math
+
 import numpy as np
 
 HERE = Path(__file__).resolve().parent
@@ -284,6 +286,111 @@ def nhc_state(n_atoms, temperature, temperature_coupling, time_step):
 def berendsen_factor(temperature, temperature_coupling, t_now):
     """gpu_berendsen_temperature, src/integrate/ensemble_ber.cu:70-86 (coupling = 1/tau, :34)."""
     return np.sqrt(1.0 + (1.0 / temperature_coupling) * (temperature / t_now - 1.0))
+
+
+class BdpOracle:
+    """Bussi-Donadio-Parrinello rescaling factor with the reference's random stream: restates
+    resamplekin / resamplekin_sumnoises / gamdev / gasdev (src/integrate/svr_utilities.cuh:27-135, the
+    published routines of G. Bussi) on std::mt19937 + uniform_real_distribution<double>(0,1) semantics
+    (libstdc++: two 32-bit draws, low word first, / 2^64), and Ensemble_BDP::integrate_nvt_bdp_2
+    (src/integrate/ensemble_bdp.cu:91-100).  Pure Python: a few hundred draws per step."""
+
+    def __init__(self, seed=12345678):  # the -DDEBUG seed, ensemble_bdp.cu:31-32
+        mt = [seed & 0xFFFFFFFF]
+        for i in range(1, 624):
+            mt.append((1812433253 * (mt[-1] ^ (mt[-1] >> 30)) + i) & 0xFFFFFFFF)
+        self.mt, self.idx = mt, 624
+        self.iset, self.gset = 0, 0.0
+
+    def raw(self):
+        mt = self.mt
+        if self.idx >= 624:
+            for k in range(624):
+                y = (mt[k] & 0x80000000) | (mt[(k + 1) % 624] & 0x7FFFFFFF)
+                mt[k] = mt[(k + 397) % 624] ^ (y >> 1) ^ (0x9908B0DF if y & 1 else 0)
+            self.idx = 0
+        y = mt[self.idx]
+        self.idx += 1
+        y ^= y >> 11
+        y ^= (y << 7) & 0x9D2C5680
+        y ^= (y << 15) & 0xEFC60000
+        y ^= y >> 18
+        return y & 0xFFFFFFFF
+
+    def rand01(self):
+        lo = float(self.raw())
+        hi = float(self.raw())
+        r = (lo + hi * 4294967296.0) / 18446744073709551616.0
+        return r if r < 1.0 else float(np.nextafter(1.0, 0.0))
+
+    def gasdev(self):
+        if self.iset == 0:
+            while True:
+                v1 = 2.0 * self.rand01() - 1.0
+                v2 = 2.0 * self.rand01() - 1.0
+                rsq = v1 * v1 + v2 * v2
+                if 0.0 < rsq < 1.0:
+                    break
+            fac = math.sqrt(-2.0 * math.log(rsq) / rsq)
+            self.gset, self.iset = v1 * fac, 1
+            return v2 * fac
+        self.iset = 0
+        return self.gset
+
+    def gamdev(self, ia):
+        if ia < 6:
+            x = 1.0
+            for _ in range(ia):
+                x *= self.rand01()
+            return -math.log(x)
+        while True:
+            while True:
+                while True:
+                    v1 = self.rand01()
+                    v2 = 2.0 * self.rand01() - 1.0
+                    if v1 * v1 + v2 * v2 <= 1.0:
+                        break
+                y = v2 / v1
+                am = ia - 1
+                s = math.sqrt(2.0 * am + 1.0)
+                x = s * y + am
+                if x > 0.0:
+                    break
+            e = (1.0 + y * y) * math.exp(am * math.log(x / am) - s * y)
+            if self.rand01() <= e:
+                return x
+
+    def sumnoises(self, nn):
+        if nn == 0:
+            return 0.0
+        if nn == 1:
+            rr = self.gasdev()
+            return rr * rr
+        if nn % 2 == 0:
+            return 2.0 * self.gamdev(nn // 2)
+        rr = self.gasdev()
+        return 2.0 * self.gamdev((nn - 1) // 2) + rr * rr
+
+    def resamplekin(self, kk, sigma, ndeg, taut):
+        factor = math.exp(-1.0 / taut) if taut > 0.1 else 0.0
+        rr = self.gasdev()
+        noise = self.sumnoises(ndeg - 1)
+        return (kk + (1.0 - factor) * (sigma * (noise + rr * rr) / ndeg - kk)
+                + 2.0 * rr * math.sqrt(kk * sigma / ndeg * (1.0 - factor) * factor))
+
+    def factor(self, t_instant, n_atoms, temperature, temperature_coupling):
+        ndeg = 3 * n_atoms
+        ek = t_instant * ndeg * 8.617343e-5 * 0.5
+        sigma = ndeg * 8.617343e-5 * temperature * 0.5
+        return math.sqrt(self.resamplekin(ek, sigma, ndeg, temperature_coupling) / ek)
+
+
+def stdrng():
+    """ctypes handle on oracle/libstdrng.so (the C++ standard library's own generator objects)."""
+    R = C.CDLL(str(HERE / "libstdrng.so"))
+    R.stdrng_uniform01.argtypes = [C.c_uint, C.c_int, C.c_void_p]
+    R.stdrng_raw.argtypes = [C.c_uint, C.c_int, C.c_void_p]
+    return R
 
 
 # ---------------------------------------------------------------- the reference's own NEP_CPU

@@ -33,7 +33,12 @@ def write_model(path, s, symbols, vel=None):
     write_xyz(path, s, symbols, vel)
 
 
+ONLY = None  # --only REGEX: run just the matching cases
+
+
 def run_case(name, s, symbols, potential, run_in, vel=None, timeout=900):
+    if ONLY and not re.search(ONLY, name):
+        return None, None
     d = OUT / name
     shutil.rmtree(d, ignore_errors=True)
     d.mkdir(parents=True)
@@ -52,6 +57,8 @@ def run_case(name, s, symbols, potential, run_in, vel=None, timeout=900):
 
 
 def collect_single_point(d, s, symbols):
+    if d is None:
+        return
     out = read_xyz(d / "dump.xyz", symbols)
     np.savez_compressed(
         d / "single_point.npz", type=s["type"], h=s["h"], pbc=s["pbc"], pos=s["pos"],
@@ -63,7 +70,10 @@ def collect_single_point(d, s, symbols):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--skip-speed", action="store_true")
+    ap.add_argument("--only", default=None, help="regex: run only the matching cases")
     args = ap.parse_args()
+    global ONLY
+    ONLY = args.only
     if not BIN.exists():
         raise SystemExit(f"{BIN} missing: build it with make -C oracle -f Makefile.gpumd_ref")
     OUT.mkdir(parents=True, exist_ok=True)
@@ -113,7 +123,9 @@ def main():
     # NVT from the same start: Nose-Hoover chain and Berendsen (deterministic thermostats)
     s = rocksalt_pbte(20, rattle=0.02, seed=1)
     vel = init_velocities(s["mass"], 300.0, seed=42)
-    for name, ens in (("md_pbte_nhc", "nvt_nhc 300 300 100"), ("md_pbte_ber", "nvt_ber 300 300 100")):
+    # ... and Bussi-Donadio-Parrinello: the reference binary is built -DDEBUG, i.e. std::mt19937(12345678)
+    for name, ens in (("md_pbte_nhc", "nvt_nhc 300 300 100"), ("md_pbte_ber", "nvt_ber 300 300 100"),
+                      ("md_pbte_bdp", "nvt_bdp 300 300 100")):
         d, i = run_case(name, s, pbte_sym, GOLDEN / "nep_PbTe.txt",
                         f"ensemble {ens}\ntime_step 1\ndump_thermo 10\nrun 200\n", vel)
         infos.append(i)
@@ -141,6 +153,7 @@ def main():
                         "ensemble nvt_ber 300 300 100\ntime_step 1\ndump_thermo 100\nrun 100\n", vel,
                         timeout=1500)
         infos.append(i)
+    infos = [i for i in infos if i is not None]
     (OUT / "summary.json").write_text(json.dumps(infos, indent=1))
     print(json.dumps(infos, indent=1))
 

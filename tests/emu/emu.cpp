@@ -9,6 +9,7 @@
 // and are therefore covered only by the `-m gpu` tests.
 #include "../../gpumd_b200/csrc/b2_common.cuh"
 #include "../../gpumd_b200/csrc/b2_eam.cuh"
+#include "../../gpumd_b200/csrc/b2_bdp.cuh"
 #include "../../gpumd_b200/csrc/b2_integrate.cuh"
 #include "../../gpumd_b200/csrc/b2_lj.cuh"
 #include "../../gpumd_b200/csrc/b2_neighbor.cuh"
@@ -637,5 +638,19 @@ void emu_find_thermo(
   thermo[1] = s[1];
   for (int k = 2; k < 8; ++k)
     thermo[k] = s[k] / volume;
+}
+
+// ---- BDP thermostat body (b2_bdp.cuh) ----
+void* emu_bdp_create(unsigned seed)
+{
+  B2BdpState* st = new B2BdpState;
+  b2_mt_seed(*st, seed);
+  return st;
+}
+void emu_bdp_destroy(void* st) { delete static_cast<B2BdpState*>(st); }
+double emu_bdp_rand01(void* st) { return b2_rand01(*static_cast<B2BdpState*>(st)); }
+double emu_bdp_factor(void* st, double t_instant, int ndeg, double temperature, double coupling)
+{
+  return b2_bdp_factor(*static_cast<B2BdpState*>(st), t_instant, ndeg, temperature, coupling);
 }
 }

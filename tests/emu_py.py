@@ -161,6 +161,13 @@ class Emu:
         E.emu_apply_pbc.argtypes = [C.c_int, _dp, _ip, _dp]
         E.emu_velocity_verlet.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp]
         E.emu_find_thermo.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp]
+        E.emu_bdp_create.restype = C.c_void_p
+        E.emu_bdp_create.argtypes = [C.c_uint]
+        E.emu_bdp_destroy.argtypes = [C.c_void_p]
+        E.emu_bdp_rand01.restype = C.c_double
+        E.emu_bdp_rand01.argtypes = [C.c_void_p]
+        E.emu_bdp_factor.restype = C.c_double
+        E.emu_bdp_factor.argtypes = [C.c_void_p, C.c_double, C.c_int, C.c_double, C.c_double]
         self.E = E
 
     def nep(self, path, n):

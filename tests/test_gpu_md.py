@@ -23,6 +23,8 @@ def run_nve(eng, s, pot_file, steps, dt_fs, temperature, seed=42, every=None, en
         ens = eng.Ensemble_BER(n, 300.0, 100.0)
     elif ensemble == "nvt_nhc":
         ens = eng.Ensemble_NHC(n, 300.0, 100.0, dt_fs / TIME_UNIT_CONVERSION)
+    elif ensemble == "nvt_bdp":
+        ens = eng.Ensemble_BDP(n, 300.0, 100.0)
     else:
         ens = eng.Ensemble_NVE(n)
     thermo = torch.zeros(8, dtype=torch.float64, device="cuda")
@@ -89,7 +91,7 @@ def read_thermo(path):
     return np.array(rows, dtype=np.float64)
 
 
-@pytest.mark.parametrize("case", ["md_pbte", "md_lj", "md_si", "md_pbte_nhc", "md_pbte_ber"])
+@pytest.mark.parametrize("case", ["md_pbte", "md_lj", "md_si", "md_pbte_nhc", "md_pbte_ber", "md_pbte_bdp"])
 def test_nve_trajectory_matches_reference_gpu(eng_mod, case):
     """tests/golden/refgpu_md_*_thermo.out: thermo.out (every 10 steps, 200 steps) written by the
     unmodified reference gpumd on a B200 from the same positions and velocities

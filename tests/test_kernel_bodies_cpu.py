@@ -234,3 +234,23 @@ def test_eam_cohesive_energy_is_physical(oracle):
     r = oracle.eam_compute(model, nt, para, s["type"], s["h"], s["pbc"], s["pos"])
     assert abs(r["pe"].mean() + 3.54) < 0.01
     assert np.abs(r["force"]).max() < 1e-5
+
+
+def test_bdp_body_matches_oracle(oracle, emu):
+    """b2_bdp.cuh (host build): same uniform stream as the oracle bit for bit, and the same velocity
+    scale factors along a sequence of steps (libm exp/log/sqrt on both sides here: exact)."""
+    E = emu.E
+    st = E.emu_bdp_create(12345678)
+    o = oracle.BdpOracle(12345678)
+    assert [E.emu_bdp_rand01(st) for _ in range(500)] == [o.rand01() for _ in range(500)]
+    E.emu_bdp_destroy(st)
+    st = E.emu_bdp_create(12345678)
+    o = oracle.BdpOracle(12345678)
+    rng = np.random.default_rng(0)
+    for n_atoms, tc in [(64000, 100.0), (250, 10.0), (3, 100.0), (1, 0.05)]:
+        for _ in range(20):
+            t = float(rng.uniform(200, 400))
+            a = E.emu_bdp_factor(st, t, 3 * n_atoms, 300.0, tc)
+            b = o.factor(t, n_atoms, 300.0, tc)
+            assert a == pytest.approx(b, rel=1e-15), (n_atoms, tc)
+    E.emu_bdp_destroy(st)

@@ -190,3 +190,30 @@ def test_md_oracle_basics(oracle):
     h = np.diag([10.0, 11.0, 12.0]).reshape(9)
     w = oracle.apply_pbc(h, [1, 1, 0], np.array([[-1.0, 10.5], [5.0, 12.0], [-3.0, 13.0]]))
     assert np.allclose(w, [[9.0, 0.5], [5.0, 1.0], [-3.0, 13.0]])
+
+
+def test_bdp_random_stream_is_the_standard_librarys(oracle):
+    """The reference's BDP thermostat draws from std::mt19937(12345678) through
+    std::uniform_real_distribution<double>(0,1) (ensemble_bdp.cu:29-36, svr_utilities.cuh:29,54).  The
+    restatement must produce the very same raw words and doubles as those library objects (built
+    from <random> by oracle/Makefile with the compiler that builds the reference)."""
+    R = oracle.stdrng()
+    for seed in (12345678, 1, 4294967295):
+        raw = np.zeros(2000, np.uint32)
+        R.stdrng_raw(seed, raw.size, raw.ctypes.data)
+        u = np.zeros(1000, np.float64)
+        R.stdrng_uniform01(seed, u.size, u.ctypes.data)
+        a = oracle.BdpOracle(seed)
+        assert [a.raw() for _ in range(raw.size)] == raw.tolist()
+        b = oracle.BdpOracle(seed)
+        assert [b.rand01() for _ in range(u.size)] == u.tolist()  # bit-exact
+
+
+def test_bdp_factor_statistics(oracle):
+    """Known answer of the published algorithm: with tau -> 0 the resampled kinetic energy is a fresh
+    Gamma(ndeg/2) draw, so <factor^2 * T_inst / T0> = 1 and its variance is 2/ndeg."""
+    o = oracle.BdpOracle(7)
+    n_atoms = 40
+    x = np.array([o.factor(250.0, n_atoms, 300.0, 0.05) ** 2 * 250.0 / 300.0 for _ in range(4000)])
+    assert abs(x.mean() - 1.0) < 4 * np.sqrt(2.0 / 120 / 4000)
+    assert abs(x.var() - 2.0 / 120) < 0.15 * 2.0 / 120
