@@ -6,6 +6,7 @@
 #include "b2_nep.cuh"
 #include "b2_nep_tc.cuh"
 #include "b2_nep_model.h"
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <new>
@@ -193,13 +194,18 @@ __global__ void __launch_bounds__(BLK) k_force_angular(B2NepView P, B2Box box)
 
 // parity hooks ---------------------------------------------------------------------------------
 __global__ void k_export_list(
-  int n, const int* perm, const int* nn, const int* nl, size_t si, size_t sk, int mn_out,
-  int* NN_out, int* NL_out, int* flags)
+  int n, int n_cell, const int* perm, const int* nn, const int* nl, size_t si, size_t sk,
+  int mn_out, int* NN_out, int* NL_out, int* flags)
 {
+  // n_cell < n: a supercell was evaluated; report the first replica with neighbour indices folded
+  // back into the caller's cell (an atom then appears once per periodic image, like in the
+  // reference's small-box lists, nep_small_box.cuh:56-150)
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n)
     return;
   const int a = perm[i];
+  if (a >= n_cell)
+    return;
   int cnt = nn[i];
   if (cnt > mn_out) {
     atomicOr(&flags[1], (int)B2_ERR_RADIAL_OVERFLOW);
@@ -207,7 +213,7 @@ __global__ void k_export_list(
   }
   int* row = NL_out + (size_t)a * mn_out;
   for (int k = 0; k < cnt; ++k) { // insertion sort into ascending caller index
-    const int v = perm[nl[(size_t)i * si + (size_t)k * sk]];
+    const int v = perm[nl[(size_t)i * si + (size_t)k * sk]] % n_cell;
     int q = k - 1;
     while (q >= 0 && row[q] > v) {
       row[q + 1] = row[q];
@@ -218,14 +224,49 @@ __global__ void k_export_list(
   NN_out[a] = cnt;
 }
 
-__global__ void k_export_q(B2NepView P, float* out)
+__global__ void k_export_q(B2NepView P, int n_cell, float* out)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.n)
     return;
   const int a = P.perm[i];
+  if (a >= n_cell)
+    return;
   for (int d = 0; d < P.dim; ++d)
-    out[(size_t)d * P.n + a] = P.q[(size_t)d * P.n + i] * P.q_scaler[d];
+    out[(size_t)d * n_cell + a] = P.q[(size_t)d * P.n + i] * P.q_scaler[d];
+}
+
+// ---- small periodic boxes: evaluate a supercell, keep the first replica -----------------------
+// replica r = (a*ry + b)*rz + c of atom i sits at index r*n + i, shifted by a*A + b*B + c*C
+__global__ void __launch_bounds__(BLK) k_replicate(
+  int n, int rx, int ry, int rz, B2Box box, const int* __restrict__ type,
+  const double* __restrict__ pos, int* type_out, double* pos_out)
+{
+  const size_t nR = (size_t)n * rx * ry * rz;
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nR)
+    return;
+  const int r = (int)(e / n), i = (int)(e - (size_t)r * n);
+  const int c = r % rz, b = (r / rz) % ry, a = r / (rz * ry);
+  type_out[e] = type[i];
+  // lattice vectors are the columns of h (box.cuh:18-35)
+  pos_out[e] = pos[i] + a * box.h[0] + b * box.h[1] + c * box.h[2];
+  pos_out[nR + e] = pos[(size_t)n + i] + a * box.h[3] + b * box.h[4] + c * box.h[5];
+  pos_out[2 * nR + e] = pos[2 * (size_t)n + i] + a * box.h[6] + b * box.h[7] + c * box.h[8];
+}
+
+// outputs of the first replica are the outputs of the original cell (+= convention)
+__global__ void __launch_bounds__(BLK) k_fold_replica(
+  int n, size_t nR, const double* __restrict__ acc, double* pe, double* force, double* virial)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n)
+    return;
+  pe[i] += acc[i];
+  for (int k = 0; k < 3; ++k)
+    force[(size_t)k * n + i] += acc[nR + (size_t)k * nR + i];
+  for (int k = 0; k < 9; ++k)
+    virial[(size_t)k * n + i] += acc[4 * nR + (size_t)k * nR + i];
 }
 
 template <typename T>
@@ -259,6 +300,10 @@ struct b200md_nep {
   int variant = 0;         // B200MD_NEP_VARIANT: kernel tuning variants for A/B measurements
   bool fuse_split = false; // many-type path: neighbour split inside the radial descriptor pass
   bool use_tc = false; // hidden layer on the tensor cores (k_mlp_tc) instead of k_mlp
+  // small periodic boxes: supercell replication, see b200md_nep_compute
+  DevBuf<int> rep_type;
+  DevBuf<double> rep_pos, rep_out;
+  int rep_n = 0; // atoms of the caller's cell while a supercell is being evaluated (else 0)
   // staging for the host-buffer entry point
   DevBuf<int> h_type;
   DevBuf<double> h_pos, h_out;
@@ -678,7 +723,56 @@ int b200md_nep_compute(
   const double* d_position, double* d_potential, double* d_force, double* d_virial, void* stream)
 {
   cudaStream_t st = (cudaStream_t)stream;
-  const B2Box box = make_box(h, pbc);
+  B2Box box = make_box(h, pbc);
+  // Small periodic box (a periodic thickness <= 2.5*(rc+skin); the reference switches to explicit
+  // images at 2.5*rc, nep.cu:1304-1312, nep_small_box.cuh): evaluate the smallest supercell that
+  // the cell-list path accepts and keep the first replica.  Every atom of that replica sees each
+  // periodic image of its neighbours as a distinct atom, exactly the reference's pair set.
+  int reps[3] = {1, 1, 1};
+  const double need = 2.5 * (p->nb.rc + p->nb.skin);
+  for (int d = 0; d < 3; ++d)
+    if (box.pbc[d] && box.thickness[d] <= need)
+      reps[d] = (int)std::floor(need / box.thickness[d]) + 1;
+  const long long R = (long long)reps[0] * reps[1] * reps[2];
+  p->rep_n = 0;
+  if (R > 1) {
+    if (R * n > 50000000LL) {
+      set_error("small-box supercell would exceed 5e7 atoms");
+      return B200MD_ERR_SMALL_BOX;
+    }
+    const int nR = (int)(R * n);
+    if (nR > p->nb.capacity) { // first small-box call (or a shrinking box): grow the scratch
+      B2_CUDA(cudaStreamSynchronize(st));
+      B2_TRY(nep_setup(p, nR));
+    }
+    B2_CUDA(p->rep_type.reserve(nR));
+    B2_CUDA(p->rep_pos.reserve(3 * (size_t)nR));
+    B2_CUDA(p->rep_out.reserve(13 * (size_t)nR));
+    k_replicate<<<grid_for(nR, BLK), BLK, 0, st>>>(
+      n, reps[0], reps[1], reps[2], box, d_type, d_position, p->rep_type.p, p->rep_pos.p);
+    B2_LAUNCHED();
+    B2_CUDA(cudaMemsetAsync(p->rep_out.p, 0, sizeof(double) * 13 * (size_t)nR, st));
+    double hs[9];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c)
+        hs[3 * r + c] = h[3 * r + c] * reps[c]; // scale lattice vector c (a column)
+    box = make_box(hs, pbc);
+    p->prof.next_step();
+    p->prof.begin(st, ST_NEIGHBOR);
+    B2_TRY(p->nb.update(box, p->rep_type.p, p->rep_pos.p, nR, st));
+    p->n = nR;
+    p->view.n = nR;
+    if (!p->view.team)
+      p->view.skin_sk = (size_t)nR;
+    p->rep_n = n;
+    p->prof.end(st, ST_NEIGHBOR);
+    double* acc = p->rep_out.p;
+    B2_TRY(nep_pipeline(p, box, st, acc, acc + nR, acc + 4 * (size_t)nR));
+    k_fold_replica<<<grid_for(n, BLK), BLK, 0, st>>>(
+      n, (size_t)nR, acc, d_potential, d_force, d_virial);
+    B2_LAUNCHED();
+    return B200MD_OK;
+  }
   p->prof.next_step();
   p->prof.begin(st, ST_NEIGHBOR);
   B2_TRY(p->nb.update(box, d_type, d_position, n, st));
@@ -722,13 +816,15 @@ int b200md_nep_export_neighbors(
   const int n = p->n;
   if (d_NN_r && d_NL_r) {
     k_export_list<<<grid_for(n, 128), 128, 0, st>>>(
-      n, p->nb.perm.p, p->nn_r.p, p->nl_r.p, p->view.team ? (size_t)p->view.pitch_r : 1,
+      n, p->rep_n ? p->rep_n : n, p->nb.perm.p, p->nn_r.p, p->nl_r.p,
+      p->view.team ? (size_t)p->view.pitch_r : 1,
       p->view.team ? 1 : (size_t)n, mn_r, d_NN_r, d_NL_r, p->nb.flags.p);
     B2_LAUNCHED();
   }
   if (d_NN_a && d_NL_a) {
     k_export_list<<<grid_for(n, 128), 128, 0, st>>>(
-      n, p->nb.perm.p, p->nn_a.p, p->nl_a.p, 1, (size_t)n, mn_a, d_NN_a, d_NL_a, p->nb.flags.p);
+      n, p->rep_n ? p->rep_n : n, p->nb.perm.p, p->nn_a.p, p->nl_a.p, 1, (size_t)n, mn_a, d_NN_a,
+      d_NL_a, p->nb.flags.p);
     B2_LAUNCHED();
   }
   return B200MD_OK;
@@ -736,7 +832,8 @@ int b200md_nep_export_neighbors(
 
 int b200md_nep_export_descriptors(b200md_nep* p, float* d_q, void* stream)
 {
-  k_export_q<<<grid_for(p->n, 128), 128, 0, (cudaStream_t)stream>>>(p->view, d_q);
+  k_export_q<<<grid_for(p->n, 128), 128, 0, (cudaStream_t)stream>>>(
+    p->view, p->rep_n ? p->rep_n : p->n, d_q);
   B2_LAUNCHED();
   return B200MD_OK;
 }

@@ -1,4 +1,4 @@
-"""Seeded input structures shared by the CPU and GPU parity tests (all large-box)."""
+"""Seeded input structures shared by the CPU and GPU parity tests."""
 import numpy as np
 
 from conftest import GOLDEN
@@ -56,3 +56,57 @@ NEP_CASES = {
         6, 3.9, rattle=0.08, seed=7, num_types=16,
         symbols=nep_type_order(GOLDEN / "nep_UNEP_v1.txt"))),
 }
+
+
+def _golden_static():
+    order = nep_type_order(GOLDEN / "nep_PbTe_static.txt")
+    return read_xyz(GOLDEN / "gpumd_static_model.xyz", order)
+
+
+def _golden_bazro3():
+    order = nep_type_order(GOLDEN / "nep_BaZrO3.txt")
+    return read_xyz(GOLDEN / "BaZrO3-nat40-rattled.xyz", order)
+
+
+# small periodic boxes (the reference's explicit-image path, nep_small_box.cuh): evaluated through a
+# supercell by the library; the oracle sums explicit images like the reference
+NEP_SMALL_CASES = {
+    # config C1: 216-atom PbTe, 19.7 A box (< 2.5 * 9 A)
+    "PbTe_C1": ("nep_PbTe.txt", lambda: rocksalt_pbte(3, rattle=0.05, seed=1)),
+    # examples/gpumd_static: 250 atoms, triclinic
+    "PbTe_static_golden": ("nep_PbTe_static.txt", _golden_static),
+    # tests_pytest bulk_bazro3 fixture: 40 atoms, 8.4 A box -> 3 replicas per direction
+    "BaZrO3_40": ("nep_BaZrO3.txt", _golden_bazro3),
+    # thin slab: periodic in x,y (one of them short), open in z
+    "PbTe_thin": ("nep_PbTe.txt", lambda: slab(rocksalt_pbte((5, 2, 2), rattle=0.05, seed=6))),
+}
+
+
+def check_reference_goldens(dev_factory, assert_close, TOL):
+    """The reference's own known answers for the path, applied DIRECTLY to an implementation
+    (dev_factory(model_file, n) -> object with .compute(type, h, pbc, pos) -> (rc, dict)):
+    examples/gpumd_static/dump.xyz (250-atom PbTe: energy, 9-virial, per-atom forces) and
+    tests_pytest/fixtures/golden/bulk_bazro3.npz (40-atom BaZrO3: energy, forces, stress).  Both are
+    small-box inputs."""
+    order = nep_type_order(GOLDEN / "nep_PbTe_static.txt")
+    s = read_xyz(GOLDEN / "gpumd_static_model.xyz", order)
+    gold = read_xyz(GOLDEN / "gpumd_static_dump.xyz", order)
+    rc, r = dev_factory("nep_PbTe_static.txt", s["type"].shape[0]).compute(s["type"], s["h"], s["pbc"], s["pos"])
+    assert rc == 0
+    assert_close(r["pe"].sum(), gold["energy"], **TOL["energy"], what="energy")
+    assert_close(r["force"], gold["forces"], **TOL["force"], what="force")
+    v = r["virial"].sum(axis=1)  # GPUMD order xx yy zz xy xz yz yx zx zy -> row-major 3x3
+    v33 = np.array([v[0], v[3], v[4], v[6], v[1], v[5], v[7], v[8], v[2]])
+    assert_close(v33, gold["virial"], rtol=1e-4, atol=2e-4, what="virial")
+
+    order = nep_type_order(GOLDEN / "nep_BaZrO3.txt")
+    s = read_xyz(GOLDEN / "BaZrO3-nat40-rattled.xyz", order)
+    g = np.load(GOLDEN / "bulk_bazro3.npz")
+    rc, r = dev_factory("nep_BaZrO3.txt", s["type"].shape[0]).compute(s["type"], s["h"], s["pbc"], s["pos"])
+    assert rc == 0
+    assert_close(r["pe"].sum(), g["energy"], **TOL["energy"], what="energy")
+    assert_close(r["force"].T, g["forces"], rtol=1e-4, atol=2e-5, what="forces")
+    vol = abs(np.linalg.det(s["h"].reshape(3, 3)))
+    v = r["virial"].sum(axis=1)
+    stress = -np.array([v[0], v[1], v[2], v[5], v[4], v[3]]) / vol  # Voigt xx yy zz yz xz xy
+    assert_close(stress, g["stress"], rtol=1e-4, atol=1e-6, what="stress")

@@ -170,6 +170,7 @@ struct emu_nep {
   std::vector<float> cov;
   B2NepView P;
   bool team = false, fuse_split = false; // same choices as nep_setup() in b2_nep.cu
+  int n_cell = 0;                        // atoms of the caller's cell (n > n_cell: supercell)
 };
 
 template <int K1>
@@ -232,14 +233,9 @@ extern "C" {
 
 const char* emu_last_error(void) { return g_err.c_str(); }
 
-emu_nep* emu_nep_create(const char* path, int n)
+// (re)size every per-atom buffer for n atoms and point the view at them (nep_setup's host twin)
+static void emu_nep_alloc(emu_nep* p, int n)
 {
-  emu_nep* p = new emu_nep;
-  g_err = p->m.load(path);
-  if (!g_err.empty()) {
-    delete p;
-    return nullptr;
-  }
   b2::NepModel& m = p->m;
   p->n = n;
   const size_t N = n;
@@ -285,6 +281,18 @@ emu_nep* emu_nep_create(const char* path, int n)
   P.f12 = p->f12.data(); P.acc = p->acc.data();
   P.team = p->team ? 1 : 0;
   P.pitch_r = pitch_r;
+}
+
+emu_nep* emu_nep_create(const char* path, int n)
+{
+  emu_nep* p = new emu_nep;
+  g_err = p->m.load(path);
+  if (!g_err.empty()) {
+    delete p;
+    return nullptr;
+  }
+  p->n_cell = n;
+  emu_nep_alloc(p, n);
   return p;
 }
 
@@ -292,13 +300,68 @@ void emu_nep_destroy(emu_nep* p) { delete p; }
 int emu_nep_rebuilds(emu_nep* p) { return p->nb.flags[2]; }
 int emu_nep_error_bits(emu_nep* p) { return p->nb.flags[1]; }
 
+// the pipeline proper on p->n atoms (declared below)
+static int emu_nep_pipeline(
+  emu_nep* p, const B2Box& box, const int* type, const double* pos, double* pe, double* force,
+  double* virial);
+
 int emu_nep_compute(
   emu_nep* p, int n, const double h[9], const int pbc[3], const int* type, const double* pos,
   double* pe, double* force, double* virial)
 {
-  if (n != p->n)
+  if (n != p->n_cell)
     return 1;
-  const B2Box box = make_box(h, pbc);
+  B2Box box = make_box(h, pbc);
+  // small periodic boxes: supercell replication, the host twin of b200md_nep_compute
+  int reps[3] = {1, 1, 1};
+  const double need = 2.5 * (p->nb.rc + p->nb.skin);
+  for (int d = 0; d < 3; ++d)
+    if (box.pbc[d] && box.thickness[d] <= need)
+      reps[d] = (int)std::floor(need / box.thickness[d]) + 1;
+  const int R = reps[0] * reps[1] * reps[2];
+  if (R == 1) {
+    if (p->n != n)
+      emu_nep_alloc(p, n);
+    return emu_nep_pipeline(p, box, type, pos, pe, force, virial);
+  }
+  const int nR = n * R;
+  if (p->n != nR)
+    emu_nep_alloc(p, nR);
+  std::vector<int> t2(nR);
+  std::vector<double> x2((size_t)3 * nR), out((size_t)13 * nR, 0.0);
+  for (int r = 0; r < R; ++r) {
+    const int c = r % reps[2], b = (r / reps[2]) % reps[1], a = r / (reps[2] * reps[1]);
+    for (int i = 0; i < n; ++i) {
+      const size_t e = (size_t)r * n + i;
+      t2[e] = type[i];
+      x2[e] = pos[i] + a * box.h[0] + b * box.h[1] + c * box.h[2];
+      x2[nR + e] = pos[(size_t)n + i] + a * box.h[3] + b * box.h[4] + c * box.h[5];
+      x2[2 * (size_t)nR + e] = pos[2 * (size_t)n + i] + a * box.h[6] + b * box.h[7] + c * box.h[8];
+    }
+  }
+  double hs[9];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c)
+      hs[3 * r + c] = h[3 * r + c] * reps[c];
+  box = make_box(hs, pbc);
+  const int rc = emu_nep_pipeline(
+    p, box, t2.data(), x2.data(), out.data(), out.data() + nR, out.data() + 4 * (size_t)nR);
+  for (int i = 0; i < n; ++i) {
+    pe[i] += out[i];
+    for (int k = 0; k < 3; ++k)
+      force[(size_t)k * n + i] += out[nR + (size_t)k * nR + i];
+    for (int k = 0; k < 9; ++k)
+      virial[(size_t)k * n + i] += out[4 * (size_t)nR + (size_t)k * nR + i];
+  }
+  return rc;
+}
+}
+
+static int emu_nep_pipeline(
+  emu_nep* p, const B2Box& box, const int* type, const double* pos, double* pe, double* force,
+  double* virial)
+{
+  const int n = p->n;
   const int rc = p->nb.update(box, type, pos);
   if (rc)
     return rc;
@@ -351,16 +414,20 @@ int emu_nep_compute(
   return p->nb.flags[1] ? 5 : 0;
 }
 
+extern "C" {
+
 static void export_list(
-  int n, const int* perm, const int* nn, const int* nl, size_t si, size_t sk, int mn, int* NN,
-  int* NL)
+  int n, int n_cell, const int* perm, const int* nn, const int* nl, size_t si, size_t sk, int mn,
+  int* NN, int* NL)
 {
   for (int i = 0; i < n; ++i) {
     const int a = perm[i];
+    if (a >= n_cell)
+      continue; // supercell: report the first replica only
     const int cnt = nn[i] < mn ? nn[i] : mn;
     int* row = NL + (size_t)a * mn;
     for (int k = 0; k < cnt; ++k) {
-      const int v = perm[nl[(size_t)i * si + (size_t)k * sk]];
+      const int v = perm[nl[(size_t)i * si + (size_t)k * sk]] % n_cell;
       int q = k - 1;
       while (q >= 0 && row[q] > v) {
         row[q + 1] = row[q];
@@ -376,24 +443,26 @@ void emu_nep_export_neighbors(
   emu_nep* p, int mn_r, int* NN_r, int* NL_r, int mn_a, int* NN_a, int* NL_a)
 {
   export_list(
-    p->n, p->P.perm, p->nn_r.data(), p->nl_r.data(), p->team ? (size_t)p->P.pitch_r : 1,
-    p->team ? 1 : (size_t)p->n, mn_r, NN_r, NL_r);
-  export_list(p->n, p->P.perm, p->nn_a.data(), p->nl_a.data(), 1, (size_t)p->n, mn_a, NN_a, NL_a);
+    p->n, p->n_cell, p->P.perm, p->nn_r.data(), p->nl_r.data(),
+    p->team ? (size_t)p->P.pitch_r : 1, p->team ? 1 : (size_t)p->n, mn_r, NN_r, NL_r);
+  export_list(
+    p->n, p->n_cell, p->P.perm, p->nn_a.data(), p->nl_a.data(), 1, (size_t)p->n, mn_a, NN_a, NL_a);
 }
 
 void emu_nep_export_descriptors(emu_nep* p, float* q)
 {
   for (int i = 0; i < p->n; ++i)
     for (int d = 0; d < p->m.dim; ++d)
-      q[(size_t)d * p->n + p->P.perm[i]] = p->q[(size_t)d * p->n + i] * p->m.q_scaler[d];
+      if (p->P.perm[i] < p->n_cell)
+        q[(size_t)d * p->n_cell + p->P.perm[i]] = p->q[(size_t)d * p->n + i] * p->m.q_scaler[d];
 }
 
 // skin list of the last rebuild, in caller indices (row-major, ascending) -- neighbour tests
 void emu_nep_export_skin(emu_nep* p, int mn, int* NN, int* NL)
 {
   export_list(
-    p->n, p->P.perm, p->nb.nn_skin.data(), p->nb.nl_skin.data(), p->nb.v.skin_si, p->nb.v.skin_sk,
-    mn, NN, NL);
+    p->n, p->n_cell, p->P.perm, p->nb.nn_skin.data(), p->nb.nl_skin.data(), p->nb.v.skin_si,
+    p->nb.v.skin_sk, mn, NN, NL);
 }
 
 // ---- LJ -------------------------------------------------------------------------------------

@@ -136,14 +136,40 @@ def test_cutoff_boundary_membership(oracle, eng):
     assert np.array_equal(NLr, r["NL_radial"]) and np.array_equal(NLa, r["NL_angular"])
 
 
-def test_small_box_fails_loudly(eng):
-    """The 250-atom / 40-atom golden single points are small-box cases (nep_small_box.cuh): the CUDA
-    path must refuse them, not approximate them."""
-    from gpumd_b200 import lib
-    s = rocksalt_pbte(3, rattle=0.0)
-    dev = GpuNep(eng, "nep_PbTe.txt", s["type"].shape[0])
-    with pytest.raises(lib.B200mdError, match="small-box"):
-        dev.compute(s["type"], s["h"], s["pbc"], s["pos"])
+@pytest.mark.parametrize("case", ["PbTe_C1", "PbTe_static_golden", "BaZrO3_40", "PbTe_thin"])
+def test_small_box_through_supercell(oracle, eng, case):
+    """Boxes thinner than 2.5*(rc+skin) -- the reference's explicit-image path (nep_small_box.cuh):
+    the library evaluates the smallest admissible supercell and keeps the first replica; lists hold
+    one entry per periodic image and must equal the oracle's exactly."""
+    from cases import NEP_SMALL_CASES
+    from test_kernel_bodies_cpu import check_nep
+    model, make = NEP_SMALL_CASES[case]
+    s = make()
+    n = s["type"].shape[0]
+    check_nep(oracle, GpuNep(eng, model, n), model, s, n)
+
+
+def test_reference_goldens_directly(eng):
+    """examples/gpumd_static/dump.xyz and tests_pytest bulk_bazro3.npz through the C-ABI."""
+    from cases import check_reference_goldens
+    check_reference_goldens(lambda model, n: GpuNep(eng, model, n), assert_close, TOL)
+
+
+def test_small_then_large_box_on_one_handle(oracle, eng):
+    """A handle created for n atoms grows its scratch on the first small-box call and keeps
+    serving large boxes afterwards (NPT-style box changes across the 2.5*(rc+skin) threshold)."""
+    s = rocksalt_pbte(3, rattle=0.05, seed=1)
+    n = s["type"].shape[0]
+    dev = GpuNep(eng, "nep_PbTe.txt", n)
+    orc = oracle.NepOracle(GOLDEN / "nep_PbTe.txt")
+    for scale in (1.0, 1.0, 2.4, 1.0):  # small, small again, large (dilute), small
+        h = s["h"] * scale
+        pos = s["pos"] * scale
+        r = orc.compute(s["type"], h, s["pbc"], pos, precision=32)
+        _, out = dev.compute(s["type"], h, s["pbc"], pos)
+        assert abs(out["pe"].sum() - r["pe"].sum()) / n < TOL["energy_per_atom"]
+        assert_close(out["force"], r["force"], rtol=1e-4, atol=1e-5 * max(1.0, np.abs(r["force"]).max()),
+                     what="force")
 
 
 def test_host_buffer_entry_point(oracle, eng):

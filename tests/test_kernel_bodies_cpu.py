@@ -122,11 +122,22 @@ def test_cutoff_boundary_membership(oracle, emu):
     assert 5 < sum(eng) < 55
 
 
-def test_small_box_is_rejected(emu):
-    s = rocksalt_pbte(3, rattle=0.0)  # 19.7 A < 2.5*(8+1)
-    dev = emu.nep(GOLDEN / "nep_PbTe.txt", s["type"].shape[0])
-    rc, _ = dev.compute(s["type"], s["h"], s["pbc"], s["pos"])
-    assert rc == 4  # B200MD_ERR_SMALL_BOX
+@pytest.mark.parametrize("case", ["PbTe_C1", "PbTe_static_golden", "BaZrO3_40", "PbTe_thin"])
+def test_small_box_through_supercell(oracle, emu, case):
+    """Boxes thinner than 2.5*(rc+skin) (the reference's nep_small_box.cuh path): the library
+    evaluates the smallest admissible supercell and keeps the first replica.  Same assertions as the
+    large-box cases; lists then hold one entry per periodic image, like the reference's."""
+    from cases import NEP_SMALL_CASES
+    model, make = NEP_SMALL_CASES[case]
+    s = make()
+    n = s["type"].shape[0]
+    check_nep(oracle, emu.nep(GOLDEN / model, n), model, s, n)
+
+
+def test_reference_goldens_directly(emu):
+    """The reference's checked-in known answers (small boxes), no oracle in between."""
+    from cases import check_reference_goldens
+    check_reference_goldens(lambda model, n: emu.nep(GOLDEN / model, n), assert_close, TOL)
 
 
 def test_lj_bodies_match_oracle(oracle, emu):
