@@ -19,6 +19,10 @@ void Force::parse_potential(const char* file_potential, const int num_atoms)
     potentials.emplace_back(new NEP_B200(file_potential, num_atoms));
   } else if (name == "lj") {
     potentials.emplace_back(new LJ_B200(file_potential, num_atoms));
+  } else if (name == "tersoff_1989") {
+    potentials.emplace_back(new Tersoff1989_B200(file_potential, num_atoms));
+  } else if (name == "eam_zhou_2004" || name == "eam_dai_2006") {
+    potentials.emplace_back(new EAM_B200(file_potential, num_atoms));
   } else {
     fprintf(stderr, "Input Error:\n    illegal potential model '%s' for the b200md backend.\n",
             name.c_str());

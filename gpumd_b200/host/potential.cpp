@@ -1,4 +1,4 @@
-// potential.cpp -- NEP_B200 / LJ_B200: forward the Potential virtuals to the C-ABI.
+// potential.cpp -- NEP_B200 / LJ_B200 / Tersoff1989_B200 / EAM_B200: forward the Potential virtuals to the C-ABI.
 // Error convention of the reference: print and exit(1) (src/utilities/error.cuh:22-62).
 #include "potential.h"
 #include <cstdio>
@@ -90,4 +90,80 @@ void LJ_B200::check()
 {
   if (b200md_lj_check(handle_, nullptr) != B200MD_OK)
     b2h_fail("LJ_B200::check");
+}
+
+Tersoff1989_B200::Tersoff1989_B200(const char* file_potential, const int num_atoms)
+{
+  if (b200md_tersoff_create(file_potential, num_atoms, &handle_) != B200MD_OK)
+    b2h_fail("Tersoff1989_B200");
+  N1 = 0;
+  N2 = num_atoms;
+  rc = b200md_tersoff_rc(handle_);
+  printf("Use the b200md Tersoff-1989 backend with %d atom type(s).\n", b200md_tersoff_info(handle_, 0));
+}
+
+Tersoff1989_B200::~Tersoff1989_B200() { b200md_tersoff_destroy(handle_); }
+
+void Tersoff1989_B200::compute(
+  Box& box, const GPU_Vector<int>& type, const GPU_Vector<double>& position,
+  GPU_Vector<double>& potential, GPU_Vector<double>& force, GPU_Vector<double>& virial)
+{
+  int pbc[3];
+  box.pbc(pbc);
+  if (b200md_tersoff_compute(
+        handle_, (int)type.size(), box.cpu_h, pbc, type.data(), position.data(), potential.data(),
+        force.data(), virial.data(), nullptr) != B200MD_OK)
+    b2h_fail("Tersoff1989_B200::compute");
+}
+
+int Tersoff1989_B200::type_of(const std::string& symbol) const
+{
+  for (int t = 0; t < b200md_tersoff_info(handle_, 0); ++t)
+    if (symbol == b200md_tersoff_symbol(handle_, t))
+      return t;
+  return -1;
+}
+
+void Tersoff1989_B200::check()
+{
+  if (b200md_tersoff_check(handle_, nullptr) != B200MD_OK)
+    b2h_fail("Tersoff1989_B200::check");
+}
+
+EAM_B200::EAM_B200(const char* file_potential, const int num_atoms)
+{
+  if (b200md_eam_create(file_potential, num_atoms, &handle_) != B200MD_OK)
+    b2h_fail("EAM_B200");
+  N1 = 0;
+  N2 = num_atoms;
+  rc = b200md_eam_rc(handle_);
+  printf("Use the b200md EAM backend with %d atom type(s).\n", b200md_eam_info(handle_, 0));
+}
+
+EAM_B200::~EAM_B200() { b200md_eam_destroy(handle_); }
+
+void EAM_B200::compute(
+  Box& box, const GPU_Vector<int>& type, const GPU_Vector<double>& position,
+  GPU_Vector<double>& potential, GPU_Vector<double>& force, GPU_Vector<double>& virial)
+{
+  int pbc[3];
+  box.pbc(pbc);
+  if (b200md_eam_compute(
+        handle_, (int)type.size(), box.cpu_h, pbc, type.data(), position.data(), potential.data(),
+        force.data(), virial.data(), nullptr) != B200MD_OK)
+    b2h_fail("EAM_B200::compute");
+}
+
+int EAM_B200::type_of(const std::string& symbol) const
+{
+  for (int t = 0; t < b200md_eam_info(handle_, 0); ++t)
+    if (symbol == b200md_eam_symbol(handle_, t))
+      return t;
+  return -1;
+}
+
+void EAM_B200::check()
+{
+  if (b200md_eam_check(handle_, nullptr) != B200MD_OK)
+    b2h_fail("EAM_B200::check");
 }

@@ -1,5 +1,5 @@
 // potential.h -- GPUMD's Potential plugin interface (src/force/potential.cuh:20-113, the members and
-// the pure virtual the run loop uses) and the two adapters that forward it to libb200md's C-ABI.
+// the pure virtual the run loop uses) and the adapters that forward it to libb200md's C-ABI.
 // Inside the reference tree these adapters derive from the reference's own class Potential
 // (INTEGRATION.md); here a same-shaped base keeps the standalone executable self-contained.
 #pragma once
@@ -54,6 +54,38 @@ public:
 
 private:
   b200md_lj* handle_ = nullptr;
+};
+
+// replaces class Tersoff1989 : Potential, src/force/tersoff1989.cuh:22-60 (FP64 like the reference)
+class Tersoff1989_B200 : public Potential
+{
+public:
+  Tersoff1989_B200(const char* file_potential, const int num_atoms);
+  ~Tersoff1989_B200() override;
+  void compute(
+    Box& box, const GPU_Vector<int>& type, const GPU_Vector<double>& position,
+    GPU_Vector<double>& potential, GPU_Vector<double>& force, GPU_Vector<double>& virial) override;
+  int type_of(const std::string& symbol) const override;
+  void check() override;
+
+private:
+  b200md_tersoff* handle_ = nullptr;
+};
+
+// replaces class EAM : Potential, src/force/eam.cuh:44-75 (eam_zhou_2004, eam_dai_2006)
+class EAM_B200 : public Potential
+{
+public:
+  EAM_B200(const char* file_potential, const int num_atoms);
+  ~EAM_B200() override;
+  void compute(
+    Box& box, const GPU_Vector<int>& type, const GPU_Vector<double>& position,
+    GPU_Vector<double>& potential, GPU_Vector<double>& force, GPU_Vector<double>& virial) override;
+  int type_of(const std::string& symbol) const override;
+  void check() override;
+
+private:
+  b200md_eam* handle_ = nullptr;
 };
 
 [[noreturn]] void b2h_fail(const char* where);

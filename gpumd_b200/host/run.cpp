@@ -8,8 +8,13 @@
 //   initialize_position (model.xyz)                 src/model/read_xyz.cu:145-425, 482-557
 //   Velocity::initialize                            src/main_gpumd/velocity.cu:55-75, 312-347
 //   Dump_Thermo                                     src/measure/dump_thermo.cu:57-129
-// Keywords: potential, velocity <T> [seed <s>], ensemble nve | nvt_ber|nvt_nhc|nvt_bdp T T tau,
-// time_step <fs>, dump_thermo <n>, run <n>.  Anything else is an input error (exit 1), as in the reference.
+//   Dump_XYZ (extended XYZ)                         src/measure/dump_xyz.cu:68-437
+//   Dump_Restart (restart.xyz)                      src/measure/dump_restart.cu:66-140
+//   Replicate                                       src/main_gpumd/replicate.cu:20-111
+// Keywords: replicate <na nb nc>, potential, velocity <T> [seed <s>], ensemble nve |
+// nvt_ber|nvt_nhc|nvt_bdp T T tau, time_step <fs>, dump_thermo <n>, dump_xyz <n> <file> [precision
+// single|double] [mass velocity force potential virial], dump_restart <n>, run <n>.  Anything else is an
+// input error (exit 1), as in the reference.
 #include "ensemble.h"
 #include "force.h"
 #include <algorithm>
@@ -210,6 +215,16 @@ private:
   std::vector<Group> group_;
   double time_step_ = 1.0 / TIME_UNIT_CONVERSION;
   int dump_thermo_ = 0;
+  int dump_restart_ = 0;
+  // dump_xyz: interval, file, "%.9g" / "%.17g", optional per-atom columns (dump_xyz.cu:68-150)
+  struct XyzDump {
+    int interval = 0;
+    std::string file;
+    bool separated = false;
+    int precision = 2;
+    bool mass = false, velocity = false, force = false, potential = false, virial = false;
+  } dump_xyz_;
+  double global_time_ = 0.0; // natural units, as Run::global_time (run.cu:316)
   bool state_on_gpu_ = false;
   bool has_potential_ = false;
   long global_step_ = 0;
@@ -304,12 +319,212 @@ private:
       time_step_ = std::atof(t[1].c_str()) / TIME_UNIT_CONVERSION; // run.cu:657
     } else if (t[0] == "dump_thermo") {
       dump_thermo_ = std::atoi(t[1].c_str());
+    } else if (t[0] == "dump_restart") {
+      if (t.size() != 2 || std::atoi(t[1].c_str()) <= 0)
+        input_error("dump_restart should have 1 positive parameter (the interval).");
+      dump_restart_ = std::atoi(t[1].c_str());
+    } else if (t[0] == "dump_xyz") {
+      parse_dump_xyz(t);
+    } else if (t[0] == "replicate") {
+      if (state_on_gpu_ || has_potential_)
+        input_error("replicate must come before 'potential' (run.cu:356-358).");
+      replicate(t);
     } else if (t[0] == "run") {
       perform_a_run(std::atoi(t[1].c_str()));
       dump_thermo_ = 0; // non-propagating keywords are reset after each run (run.cu:329-340)
+      dump_restart_ = 0;
+      dump_xyz_ = XyzDump();
     } else {
       input_error("'" + t[0] + "' is not a keyword supported by the b200md backend.");
     }
+  }
+
+  // Replicate: copies ordered a-slowest, c-fastest, atoms innermost; box columns scaled
+  void replicate(const std::vector<std::string>& t)
+  {
+    if (t.size() != 4)
+      input_error("Replicate should have 3 parameters: number of replications in a, b and c directions.");
+    int r[3];
+    for (int d = 0; d < 3; ++d) {
+      r[d] = std::atoi(t[1 + d].c_str());
+      if (r[d] < 1)
+        input_error("Number of replications should be a positive integer.");
+    }
+    Atom& a = model_.atom;
+    Box& box = model_.box;
+    const int n = a.number_of_atoms, N = n * r[0] * r[1] * r[2];
+    std::vector<std::string> sym(N);
+    std::vector<double> mass(N), pos((size_t)3 * N), vel((size_t)3 * N);
+    int cur = 0;
+    for (int i = 0; i < r[0]; ++i)
+      for (int j = 0; j < r[1]; ++j)
+        for (int k = 0; k < r[2]; ++k)
+          for (int m = 0; m < n; ++m, ++cur) {
+            sym[cur] = a.cpu_atom_symbol[m];
+            mass[cur] = a.cpu_mass[m];
+            for (int d = 0; d < 3; ++d) {
+              pos[cur + (size_t)d * N] = a.cpu_position_per_atom[m + (size_t)d * n] +
+                                         i * box.cpu_h[d * 3] + j * box.cpu_h[d * 3 + 1] +
+                                         k * box.cpu_h[d * 3 + 2];
+              vel[cur + (size_t)d * N] = a.cpu_velocity_per_atom[m + (size_t)d * n];
+            }
+          }
+    for (int e = 0; e < 9; ++e)
+      box.cpu_h[e] *= r[e % 3];
+    a.number_of_atoms = N;
+    a.cpu_atom_symbol.swap(sym);
+    a.cpu_mass.swap(mass);
+    a.cpu_position_per_atom.swap(pos);
+    a.cpu_velocity_per_atom.swap(vel);
+    printf("Replicate cell by %d * %d * %d.\nNumber of atoms is %d.\n", r[0], r[1], r[2], N);
+  }
+
+  void parse_dump_xyz(const std::vector<std::string>& t)
+  {
+    if (t.size() < 3)
+      input_error("dump_xyz should have at least 2 parameters.");
+    XyzDump d;
+    d.interval = std::atoi(t[1].c_str());
+    if (d.interval <= 0)
+      input_error("dump interval should > 0.");
+    d.file = t[2];
+    if (d.file.back() == '*') {
+      d.separated = true;
+      d.file.pop_back();
+    }
+    for (size_t m = 3; m < t.size(); ++m) {
+      if (t[m] == "precision") {
+        if (m + 1 >= t.size() || (t[m + 1] != "single" && t[m + 1] != "double"))
+          input_error("Invalid precision.");
+        d.precision = t[++m] == "single" ? 1 : 2;
+      } else if (t[m] == "mass") {
+        d.mass = true;
+      } else if (t[m] == "velocity") {
+        d.velocity = true;
+      } else if (t[m] == "force") {
+        d.force = true;
+      } else if (t[m] == "potential") {
+        d.potential = true;
+      } else if (t[m] == "virial") {
+        d.virial = true;
+      } else {
+        input_error("Unrecognized argument in dump_xyz (supported: precision, mass, velocity, force, "
+                    "potential, virial).");
+      }
+    }
+    dump_xyz_ = d;
+  }
+
+  // one frame of extended XYZ: header keys and value formats of dump_xyz.cu:197-437
+  void write_xyz_frame(int step)
+  {
+    const XyzDump& d = dump_xyz_;
+    Atom& a = model_.atom;
+    const Box& box = model_.box;
+    const int N = a.number_of_atoms;
+    const char* fmt = d.precision == 1 ? " %.9g" : " %.17g";
+    std::vector<double> pos((size_t)3 * N), vel, frc, pe, vir((size_t)9 * N);
+    a.position_per_atom.copy_to_host(pos.data());
+    a.virial_per_atom.copy_to_host(vir.data());
+    if (d.velocity) {
+      vel.resize((size_t)3 * N);
+      a.velocity_per_atom.copy_to_host(vel.data());
+    }
+    if (d.force) {
+      frc.resize((size_t)3 * N);
+      a.force_per_atom.copy_to_host(frc.data());
+    }
+    if (d.potential) {
+      pe.resize(N);
+      a.potential_per_atom.copy_to_host(pe.data());
+    }
+    double th[8];
+    thermo_.copy_to_host(th, 8);
+    const std::string name = d.separated ? d.file + std::to_string(step + 1) : d.file;
+    FILE* fid = fopen(name.c_str(), d.separated ? "w" : "a");
+    if (!fid)
+      input_error("Failed to open " + name + ".");
+    auto tensor = [&](const char* key, const double* v9) {
+      fprintf(fid, " %s=\"", key);
+      for (int k = 0; k < 9; ++k)
+        fprintf(fid, k == 0 ? fmt + 1 : fmt, v9[k]);
+      fprintf(fid, "\"");
+    };
+    fprintf(fid, "%d\n", N);
+    fprintf(fid, "Time=%.8f", global_time_ * TIME_UNIT_CONVERSION);
+    fprintf(fid, " pbc=\"%c %c %c\"", box.pbc_x ? 'T' : 'F', box.pbc_y ? 'T' : 'F', box.pbc_z ? 'T' : 'F');
+    const double* h = box.cpu_h;
+    const double lattice[9] = {h[0], h[3], h[6], h[1], h[4], h[7], h[2], h[5], h[8]};
+    tensor("Lattice", lattice);
+    fprintf(fid, " energy=");
+    fprintf(fid, fmt + 1, th[1]);
+    double tv[6] = {0, 0, 0, 0, 0, 0}; // totals of xx yy zz xy xz yz
+    for (int c = 0; c < 6; ++c)
+      for (int n = 0; n < N; ++n)
+        tv[c] += vir[(size_t)c * N + n];
+    const double virial[9] = {tv[0], tv[3], tv[4], tv[3], tv[1], tv[5], tv[4], tv[5], tv[2]};
+    tensor("virial", virial);
+    const double stress[9] = {th[2], th[5], th[6], th[5], th[3], th[7], th[6], th[7], th[4]};
+    tensor("stress", stress);
+    fprintf(fid, " Properties=species:S:1:pos:R:3");
+    if (d.mass)
+      fprintf(fid, ":mass:R:1");
+    if (d.velocity)
+      fprintf(fid, ":vel:R:3");
+    if (d.force)
+      fprintf(fid, ":forces:R:3");
+    if (d.potential)
+      fprintf(fid, ":energy_atom:R:1");
+    if (d.virial)
+      fprintf(fid, ":virial:R:9");
+    fprintf(fid, "\n");
+    const int vidx[9] = {0, 3, 4, 6, 1, 5, 7, 8, 2}; // GPUMD component order -> row-major 3x3
+    for (int n = 0; n < N; ++n) {
+      fprintf(fid, "%s", a.cpu_atom_symbol[n].c_str());
+      for (int k = 0; k < 3; ++k)
+        fprintf(fid, fmt, pos[n + (size_t)N * k]);
+      if (d.mass)
+        fprintf(fid, fmt, a.cpu_mass[n]);
+      if (d.velocity)
+        for (int k = 0; k < 3; ++k)
+          fprintf(fid, fmt, vel[n + (size_t)N * k] / TIME_UNIT_CONVERSION);
+      if (d.force)
+        for (int k = 0; k < 3; ++k)
+          fprintf(fid, fmt, frc[n + (size_t)N * k]);
+      if (d.potential)
+        fprintf(fid, fmt, pe[n]);
+      if (d.virial)
+        for (int k = 0; k < 9; ++k)
+          fprintf(fid, fmt, vir[n + (size_t)N * vidx[k]]);
+      fprintf(fid, "\n");
+    }
+    fclose(fid);
+  }
+
+  // restart.xyz: the model.xyz the next run can start from (dump_restart.cu:83-139)
+  void write_restart()
+  {
+    Atom& a = model_.atom;
+    const Box& box = model_.box;
+    const int N = a.number_of_atoms;
+    std::vector<double> pos((size_t)3 * N), vel((size_t)3 * N);
+    a.position_per_atom.copy_to_host(pos.data());
+    a.velocity_per_atom.copy_to_host(vel.data());
+    FILE* fid = fopen("restart.xyz", "w");
+    if (!fid)
+      input_error("Failed to open restart.xyz.");
+    const double* h = box.cpu_h;
+    fprintf(fid, "%d\n", N);
+    fprintf(fid, "pbc=\"%c %c %c\" ", box.pbc_x ? 'T' : 'F', box.pbc_y ? 'T' : 'F', box.pbc_z ? 'T' : 'F');
+    fprintf(fid, "Lattice=\"%g %g %g %g %g %g %g %g %g\" ", h[0], h[3], h[6], h[1], h[4], h[7], h[2],
+            h[5], h[8]);
+    fprintf(fid, "Properties=species:S:1:pos:R:3:mass:R:1:vel:R:3\n");
+    for (int n = 0; n < N; ++n)
+      fprintf(fid, "%s %g %g %g %g %g %g %g \n", a.cpu_atom_symbol[n].c_str(), pos[n],
+              pos[n + (size_t)N], pos[n + 2 * (size_t)N], a.cpu_mass[n],
+              vel[n] / TIME_UNIT_CONVERSION, vel[n + (size_t)N] / TIME_UNIT_CONVERSION,
+              vel[n + 2 * (size_t)N] / TIME_UNIT_CONVERSION);
+    fclose(fid);
   }
 
   void write_thermo(FILE* fid)
@@ -354,8 +569,13 @@ private:
                      a.virial_per_atom);
       ensemble_->compute2(time_step_, group_, model_.box, a, thermo_);
       ++global_step_;
+      global_time_ += time_step_;
       if (fid && (step + 1) % dump_thermo_ == 0)
         write_thermo(fid);
+      if (dump_xyz_.interval > 0 && (step + 1) % dump_xyz_.interval == 0)
+        write_xyz_frame(step);
+      if (dump_restart_ > 0 && (step + 1) % dump_restart_ == 0)
+        write_restart();
     }
     B2H_CHECK(cudaDeviceSynchronize());
     force_.potentials[0]->check();
