@@ -453,13 +453,14 @@ int nep_pipeline(
   pf.end(st, ST_DESC_A);
   pf.begin(st, ST_MLP);
   if (p->use_tc) {
-    const size_t bytes = b2_tc_smem_bytes(p->model.tc_img_floats, p->model.HN, p->model.DK);
+    const size_t bytes =
+      b2_tc_smem_bytes(p->model.tc_img_floats, p->model.HN, p->model.DK, p->view.N3 ? p->model.K3 : 0);
     if (bytes > 48 * 1024)
       B2_CUDA(cudaFuncSetAttribute(
         k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     // persistent CTAs: as many as fit per SM (shared memory, TMEM columns), each walking tiles
     int per_sm = (int)((size_t)220 * 1024 / (bytes + 2048));
-    const int by_tmem = 512 / b2_tc_tmem_cols(p->model.HN, p->model.DN);
+    const int by_tmem = 512 / b2_tc_tmem_cols(p->model.HN, p->model.DN, p->view.N3);
     per_sm = per_sm < by_tmem ? per_sm : by_tmem;
     per_sm = per_sm < 1 ? 1 : (per_sm > 8 ? 8 : per_sm);
     const int tiles = p->nb.max_tiles();
@@ -477,12 +478,14 @@ int nep_pipeline(
     case 112: B2_TRY(launch_mlp<112>(p, st)); break;
     default: B2_TRY(launch_mlp<128>(p, st)); break;
   }
-  switch (p->model.K1R) {
-    case 9: k_utable<9><<<grid_for(n, BLK), BLK, 0, st>>>(p->view); break;
-    case 13: k_utable<13><<<grid_for(n, BLK), BLK, 0, st>>>(p->view); break;
-    default: k_utable<17><<<grid_for(n, BLK), BLK, 0, st>>>(p->view); break;
+  if (!(p->use_tc && p->view.N3)) { // otherwise k_mlp_tc produced the U table as its third GEMM
+    switch (p->model.K1R) {
+      case 9: k_utable<9><<<grid_for(n, BLK), BLK, 0, st>>>(p->view); break;
+      case 13: k_utable<13><<<grid_for(n, BLK), BLK, 0, st>>>(p->view); break;
+      default: k_utable<17><<<grid_for(n, BLK), BLK, 0, st>>>(p->view); break;
+    }
+    B2_LAUNCHED();
   }
-  B2_LAUNCHED();
   pf.end(st, ST_MLP);
   pf.begin(st, ST_FORCE_A);
   switch (p->model.K1A) {
@@ -634,6 +637,10 @@ int nep_setup(b200md_nep* p, int num_atoms)
     P.HN = m.HN;
     P.DK = m.DK;
     P.DN = m.DN;
+    P.K3 = m.K3;
+    // the U table as a third GEMM of the same kernel (AoS rows only: the lane-team path keeps planes)
+    const char* u_env = std::getenv("B200MD_NEP_UTABLE");
+    P.N3 = (m.tc3_ok && !team && !(u_env && std::strcmp(u_env, "simt") == 0)) ? m.N3 : 0;
     P.tile_atom = p->nb.tile_atom.p;
     P.tile_type = p->nb.tile_type.p;
     P.tile_meta = p->nb.tile_meta.p;

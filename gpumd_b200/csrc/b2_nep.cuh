@@ -97,6 +97,7 @@ struct B2NepView {
   // ---- tensor-core hidden layer (k_mlp_tc; null / 0 when the SIMT k_mlp is used) ----
   const float* tc_img;  // [nt][tc_img_floats] shared-memory images, see NepModel::tc_img
   int tc_img_floats, HN, DK, DN;
+  int K3, N3;           // U-table GEMM inside k_mlp_tc (N3 = 0: done by k_utable instead)
   const int* tile_atom; // B2NeighborView::tile_atom / tile_type / tile_meta
   const int* tile_type;
   const int* tile_meta;

@@ -229,16 +229,35 @@ std::string NepModel::load(const char* path)
   const float b1 = para[p++];
   for (int t = 0; t < nt; ++t)
     bias[t] = (version == 5) ? bias[t] + b1 : b1; // nep_utilities.cuh:193, 309
+  // ---- expansion coefficients: file order [(n*(K+1)+k)*nt^2 + t1*nt + t2] ----
+  c_r.assign((size_t)ntsq * nr1 * K1R, 0.0f);
+  c_a.assign((size_t)ntsq * na1 * K1A, 0.0f);
+  const float* cr = para.data() + num_para_ann;
+  const float* ca = cr + (size_t)ntsq * nbr;
+  for (int pair = 0; pair < ntsq; ++pair) {
+    for (int n = 0; n < nr1; ++n)
+      for (int k = 0; k < kr1; ++k)
+        c_r[((size_t)pair * nr1 + n) * K1R + k] = cr[(size_t)(n * kr1 + k) * ntsq + pair];
+    for (int n = 0; n < na1; ++n)
+      for (int k = 0; k < ka1; ++k)
+        c_a[((size_t)pair * na1 + n) * K1A + k] = ca[(size_t)(n * ka1 + k) * ntsq + pair];
+  }
   // ---- tensor-core images of the hidden layer (layout documented in b2_nep_model.h) ----
   HN = (nneu + 15) / 16 * 16;
   DK = (dim + 7) / 8 * 8;
   DN = (dim + 15) / 16 * 16;
-  tc_img_floats = 2 * HN * DK + 2 * DN * HN + 2 * HN;
+  K3 = (nr1 + 7) / 8 * 8;
+  N3 = (nt * KP + 15) / 16 * 16;
+  tc3_ok = N3 <= 256 && K3 <= 16; // k_mlp_tc stages the radial dU/dq from one 16-column chunk
+  tc_img_floats = 2 * HN * DK + 2 * DN * HN + 2 * HN + (tc3_ok ? 2 * N3 * K3 : 0);
   {
     int cols = 32;
-    while (cols < HN + DN)
+    while (cols < HN + DN || (tc3_ok && cols < N3))
       cols <<= 1;
-    const size_t smem = (size_t)tc_img_floats * 4 + 2 * 128 * (size_t)(DK > HN ? DK : HN) * 4 + 64;
+    int ka = DK > HN ? DK : HN;
+    if (tc3_ok && K3 > ka)
+      ka = K3;
+    const size_t smem = (size_t)tc_img_floats * 4 + 2 * 128 * (size_t)ka * 4 + 256;
     tc_ok = HN <= 256 && DN <= 256 && cols <= 512 && smem <= 200 * 1024;
   }
   if (tc_ok) {
@@ -264,20 +283,21 @@ std::string NepModel::load(const char* path)
         ib0[n] = b0[(size_t)t * nneu + n];
         iw1[n] = w1[(size_t)t * nneu + n];
       }
+      if (tc3_ok) {
+        float* b3_hi = iw1 + HN;
+        float* b3_lo = b3_hi + N3 * K3;
+        for (int t2 = 0; t2 < nt; ++t2)
+          for (int n = 0; n < nr1; ++n)
+            for (int k = 0; k < K1R; ++k) {
+              float hi, lo;
+              split_tf32(c_r[((size_t)(t * nt + t2) * nr1 + n) * K1R + k], hi, lo);
+              const int row = t2 * KP + k; // column of the U row
+              const size_t o = (size_t)row * 4 + (size_t)(n / 4) * (N3 * 4) + (n % 4);
+              b3_hi[o] = hi;
+              b3_lo[o] = lo;
+            }
+      }
     }
-  }
-  // ---- expansion coefficients: file order [(n*(K+1)+k)*nt^2 + t1*nt + t2] ----
-  c_r.assign((size_t)ntsq * nr1 * K1R, 0.0f);
-  c_a.assign((size_t)ntsq * na1 * K1A, 0.0f);
-  const float* cr = para.data() + num_para_ann;
-  const float* ca = cr + (size_t)ntsq * nbr;
-  for (int pair = 0; pair < ntsq; ++pair) {
-    for (int n = 0; n < nr1; ++n)
-      for (int k = 0; k < kr1; ++k)
-        c_r[((size_t)pair * nr1 + n) * K1R + k] = cr[(size_t)(n * kr1 + k) * ntsq + pair];
-    for (int n = 0; n < na1; ++n)
-      for (int k = 0; k < ka1; ++k)
-        c_a[((size_t)pair * na1 + n) * K1A + k] = ca[(size_t)(n * ka1 + k) * ntsq + pair];
   }
   q_scaler.assign(DIMP, 0.0f);
   for (int d = 0; d < dim; ++d)

@@ -29,12 +29,16 @@ struct NepModel {
   std::vector<float> c_r, c_a, w0p, b0, w1, bias, q_scaler;
 
   // tensor-core hidden layer (k_mlp_tc): per type one ready-to-copy shared-memory image
-  //   [B1_hi | B1_lo | B2_hi | B2_lo | b0 | w1]  (tc_img_floats floats, a multiple of 4)
+  //   [B1_hi | B1_lo | B2_hi | B2_lo | b0 | w1 | B3_hi | B3_lo]  (tc_img_floats floats, multiple of 4)
   // B1 = W0 as the [N = HN x K = DK] operand of Z = Q . W0^T, B2 = W0^T as the [N = DN x K = HN]
   // operand of dU/dq = C . W0, both split into TF32 hi/lo parts and stored K-major in 8 x 16-byte
   // core matrices: float offset of (row r, column k) = r*4 + (k/4)*(rows*4) + (k%4).
-  int HN = 0, DK = 0, DN = 0, tc_img_floats = 0;
-  bool tc_ok = false; // shapes fit the tcgen05 kernel (else the SIMT k_mlp is the only path)
+  // A third operand pair B3 = the radial expansion coefficients of the type, [N3 = nt*KP rows x
+  // K3 = nr1 columns] with row t2*KP + k = c[t,t2,n,k]: U = FpR . B3^T, the pre-contracted radial
+  // table, comes out of the same kernel (tc3_ok; otherwise k_utable does it).
+  int HN = 0, DK = 0, DN = 0, K3 = 0, N3 = 0, tc_img_floats = 0;
+  bool tc_ok = false;  // shapes fit the tcgen05 kernel (else the SIMT k_mlp is the only path)
+  bool tc3_ok = false; // nt*KP <= 256: the U table is a third GEMM of k_mlp_tc
   std::vector<float> tc_img; // [nt][tc_img_floats]
 
   // returns empty string on success, else the error message

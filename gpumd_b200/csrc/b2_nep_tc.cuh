@@ -15,10 +15,11 @@
 
 namespace b2 {
 
-__host__ __device__ inline int b2_tc_tmem_cols(int HN, int DN)
+// N3 = 0 when the U-table GEMM is not part of the kernel
+__host__ __device__ inline int b2_tc_tmem_cols(int HN, int DN, int N3)
 {
   int c = 32;
-  while (c < HN + DN)
+  while (c < HN + DN || c < N3)
     c <<= 1;
   return c;
 }
@@ -26,9 +27,14 @@ __host__ __device__ inline size_t b2_tc_img_bytes(int img_floats)
 {
   return ((size_t)img_floats * 4 + 127) / 128 * 128;
 }
-__host__ __device__ inline size_t b2_tc_smem_bytes(int img_floats, int HN, int DK)
+__host__ __device__ inline int b2_tc_ka(int HN, int DK, int K3)
 {
-  return b2_tc_img_bytes(img_floats) + 2 * 128 * (size_t)(DK > HN ? DK : HN) * 4;
+  int ka = DK > HN ? DK : HN;
+  return K3 > ka ? K3 : ka;
+}
+__host__ __device__ inline size_t b2_tc_smem_bytes(int img_floats, int HN, int DK, int K3)
+{
+  return b2_tc_img_bytes(img_floats) + 2 * 128 * (size_t)b2_tc_ka(HN, DK, K3) * 4;
 }
 
 // Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... so that the TMEM
@@ -45,13 +51,14 @@ __global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
   const int tid = threadIdx.x, warp = tid >> 5;
   const size_t N = (size_t)P.n;
   const int HN = P.HN, DK = P.DK, DN = P.DN;
-  const int KA = DK > HN ? DK : HN;
+  const int K3 = P.K3, N3 = P.N3; // N3 = 0: the U table is left to k_utable
+  const int KA = b2_tc_ka(HN, DK, N3 ? K3 : 0);
   float* img = reinterpret_cast<float*>(tc_smem);
   const float* sb0 = img + 2 * HN * DK + 2 * DN * HN;
   const float* sw1 = sb0 + HN;
   unsigned char* a_hi = tc_smem + b2_tc_img_bytes(P.tc_img_floats);
   unsigned char* a_lo = a_hi + (size_t)128 * KA * 4;
-  const uint32_t ncols = (uint32_t)b2_tc_tmem_cols(HN, DN);
+  const uint32_t ncols = (uint32_t)b2_tc_tmem_cols(HN, DN, N3);
 
   if (warp == 0)
     b2tc::tmem_alloc(&tmem_slot, ncols);
@@ -176,26 +183,88 @@ __global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
     b2tc::mbar_wait(&bar_mma, mma_phase);
     mma_phase ^= 1u;
     b2tc::fence_after_sync();
-    // ---- epilogue 2: dU/dq (times q_scaler): radial part for k_utable, angular part for the rest
+    // ---- epilogue 2: dU/dq (times q_scaler).  Angular part -> FpA for k_force_angular; radial part
+    //      -> the A operand of GEMM 3 (or FpR for k_utable when the table GEMM is not fused) ----
     for (int c0 = 0; c0 < DN; c0 += 16) {
       uint32_t v[16];
       b2tc::tmem_ld16(tmem + lane_base + (uint32_t)(HN + c0), v);
+      float f[16];
+#pragma unroll
+      for (int c = 0; c < 16; ++c) {
+        const int d = c0 + c;
+        f[c] = (i >= 0 && d < P.dim) ? __uint_as_float(v[c]) * __ldg(&P.q_scaler[d]) : 0.0f;
+      }
       if (i >= 0) {
 #pragma unroll
         for (int c = 0; c < 16; ++c) {
           const int d = c0 + c;
           if (d < P.dim) {
-            const float f = __uint_as_float(v[c]) * __ldg(&P.q_scaler[d]);
-            if (d < P.nr1)
-              P.FpR[(size_t)d * N + i] = f;
-            else
-              P.FpA[(size_t)(d - P.nr1) * N + i] = f;
+            if (d >= P.nr1)
+              P.FpA[(size_t)(d - P.nr1) * N + i] = f[c];
+            else if (N3 == 0)
+              P.FpR[(size_t)d * N + i] = f[c];
+          }
+        }
+      }
+      if (N3 && c0 < K3) { // nr1 <= K3 <= 16: the radial part sits in the first chunk
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          if (4 * g < K3) {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              b2tc::split_tf32((4 * g + c < P.nr1) ? f[4 * g + c] : 0.0f, hi[c], lo[c]);
+            const uint32_t off = (uint32_t)tid * 16u + (uint32_t)g * 2048u;
+            *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
           }
         }
       }
     }
     if (i >= 0)
       P.acc[i] = (double)(F - __ldg(&P.bias[t]));
+    if (N3) {
+      // ---- GEMM 3: U[128 x N3] = FpR[128 x K3] . B3^T, accumulator at column 0 (Z is dead; every
+      //      thread has finished its epilogue-2 loads at the barrier below) ----
+      b2tc::fence_async_smem();
+      b2tc::fence_before_sync();
+      __syncthreads();
+      b2tc::fence_after_sync();
+      if (tid == 0) {
+        const uint32_t idesc = b2tc::make_idesc_tf32(128, N3);
+        const uint32_t bh = b2tc::smem_u32(img) + (2u * HN * DK + 2u * DN * HN + 2u * HN) * 4u;
+        const uint32_t bl = bh + (uint32_t)N3 * K3 * 4u;
+        const uint32_t lbo_b = (uint32_t)N3 * 16u;
+        for (int ks = 0; ks < K3 / 8; ++ks) {
+          const uint64_t dah = b2tc::make_desc(ah + ks * 4096u, 2048u, 128u);
+          const uint64_t dal = b2tc::make_desc(al + ks * 4096u, 2048u, 128u);
+          const uint64_t dbh = b2tc::make_desc(bh + ks * 2u * lbo_b, lbo_b, 128u);
+          const uint64_t dbl = b2tc::make_desc(bl + ks * 2u * lbo_b, lbo_b, 128u);
+          b2tc::mma_tf32(tmem, dal, dbh, idesc, ks > 0 ? 1u : 0u);
+          b2tc::mma_tf32(tmem, dah, dbl, idesc, 1u);
+          b2tc::mma_tf32(tmem, dah, dbh, idesc, 1u);
+        }
+        b2tc::mma_commit(&bar_mma);
+      }
+      b2tc::mbar_wait(&bar_mma, mma_phase);
+      mma_phase ^= 1u;
+      b2tc::fence_after_sync();
+      // ---- epilogue 3: this thread's row of the U table (AoS, UST floats per atom) ----
+      float* Urow = P.U + (size_t)(i >= 0 ? i : 0) * P.UST;
+      for (int c0 = 0; c0 < N3; c0 += 16) {
+        uint32_t v[16];
+        b2tc::tmem_ld16(tmem + lane_base + (uint32_t)c0, v);
+        if (i >= 0) {
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            if (c0 + 4 * g < P.UST) // UST = nt*KP is a multiple of 4
+              *reinterpret_cast<float4*>(Urow + c0 + 4 * g) =
+                make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                            __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+          }
+        }
+      }
+    }
     // the next tile's GEMM 1 overwrites Z (columns [0, HN)) only after the barrier in its staging
     // phase, i.e. after every thread's epilogue-1 loads above; its GEMM 2 after the next barrier
   }

@@ -94,11 +94,13 @@ def test_b200md_dump_xyz_single_point_matches_reference(tmp_path):
     assert abs(out["energy"] - float(d["energy"])) / n < 1e-6
     assert np.allclose(out["forces"], d["force"], rtol=1e-4, atol=1e-5)
     assert np.allclose(out["virial"], d["virial"], rtol=1e-4, atol=2e-3)
-    assert np.allclose(out["pos"], d["wrapped_pos"], rtol=0, atol=1e-9)
+    L = np.diag(d["h"].reshape(3, 3))[:, None]  # orthogonal box: wrapped positions are pos mod L
+    wrapped = np.mod(d["pos"], L)
+    assert np.allclose(out["pos"], wrapped, rtol=0, atol=1e-9)
     # restart.xyz is a model.xyz (%g columns, like the reference's): positions and masses round-trip
     rs = read_xyz(tmp_path / "restart.xyz", sym)
     assert np.array_equal(rs["type"], s["type"])
-    assert np.allclose(rs["pos"], d["wrapped_pos"], rtol=2e-6, atol=1e-5)
+    assert np.allclose(rs["pos"], wrapped, rtol=2e-6, atol=1e-5)
 
 
 def test_b200md_replicate(tmp_path):
