@@ -837,6 +837,16 @@ int b200md_nep_export_neighbors(
   return B200MD_OK;
 }
 
+int b200md_nep_set_owned(b200md_nep* p, int n_owned)
+{
+  if (n_owned < 0) {
+    set_error("b200md_nep_set_owned: negative count");
+    return B200MD_ERR_ARG;
+  }
+  p->view.n_own = n_owned;
+  return B200MD_OK;
+}
+
 int b200md_nep_export_descriptors(b200md_nep* p, float* d_q, void* stream)
 {
   k_export_q<<<grid_for(p->n, 128), 128, 0, (cudaStream_t)stream>>>(

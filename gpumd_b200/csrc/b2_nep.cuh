@@ -94,6 +94,8 @@ struct B2NepView {
   size_t skin_si, skin_sk; // B2NeighborView::skin_si / skin_sk
   int pitch_r;             // row pitch of nl_r when team != 0 (else nl_r is column-major)
   int team;                // 1: k_team_* kernels own the radial passes
+  int n_own;               // > 0: only caller indices < n_own get outputs (domain decomposition:
+                           // the rest are ghosts whose forces the caller discards)
   // ---- tensor-core hidden layer (k_mlp_tc; null / 0 when the SIMT k_mlp is used) ----
   const float* tc_img;  // [nt][tc_img_floats] shared-memory images, see NepModel::tc_img
   int tc_img_floats, HN, DK, DN;
@@ -1074,6 +1076,8 @@ template <int NT, int K1, int DEPTH = 1>
 B2_HD void b2_body_force_final(
   int i, const B2NepView& P, const B2Box& box, double* pe, double* force, double* virial)
 {
+  if (P.n_own > 0 && P.perm[i] >= P.n_own)
+    return; // ghost atom of a spatial domain
   float r[12], a[12], z[12];
   float zpe = 0.0f;
   b2_force_radial_sum<NT, K1, DEPTH>(i, P, box, r);
@@ -1227,6 +1231,8 @@ B2_HD void b2_team_force_final(
 {
   constexpr int G = B2_TEAM;
   constexpr int KP4 = (K1 + 3) / 4;
+  if (P.n_own > 0 && P.perm[i] >= P.n_own)
+    return; // ghost atom of a spatial domain (uniform over the team)
   const B2Geo geo = b2_geo(box);
   const size_t N = (size_t)P.n;
   const B2Atom a1 = P.atoms[i];

@@ -240,6 +240,7 @@ class DomainMD:
         cap = int(dom.n_loc * capacity_factor) + 1024
         self.pot = engine.Force().parse_potential(potential_file, cap)
         self.capacity = cap
+        self._set_owned()
         self.box = engine.Box(dom.local_h, dom.local_pbc)
         self.thermo = torch.zeros(8, dtype=torch.float64, device=dom.device)
         nbytes = self.L.b200md_thermo_scratch_bytes(cap)
@@ -275,6 +276,11 @@ class DomainMD:
 
     def _st(self):
         return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def _set_owned(self):
+        # forces / virials of ghosts are never used here: let the potential skip them
+        if hasattr(self.pot, "set_owned"):
+            self.pot.set_owned(self.dom.n_own)
 
     # ---- optional per-phase device timing (CUDA events on the current stream) ----
     def enable_profile(self, on=True):
@@ -402,6 +408,7 @@ class DomainMD:
         if d.n_loc > self.capacity:
             raise RuntimeError("local atom count exceeds the capacity of the potential instance")
         self.pot.invalidate(d.n_loc)
+        self._set_owned()
         self.steps_since_exchange = 0
 
     def maybe_exchange(self, check_every=5):

@@ -130,6 +130,10 @@ class NEP(Potential):
     def invalidate(self, n_new):
         _lib.check(self._L.b200md_nep_invalidate(self._h, int(n_new), _stream()))
 
+    def set_owned(self, n_owned):
+        """Spatial domains: only caller indices < n_owned get outputs (0 = all)."""
+        _lib.check(self._L.b200md_nep_set_owned(self._h, int(n_owned)))
+
     @property
     def num_rebuilds(self):
         return self._L.b200md_nep_info(self._h, 6)

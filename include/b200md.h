@@ -237,6 +237,11 @@ int b200md_halo_pack(
   int m, const int* d_index, int stride, const double* d_position, const double shift[3],
   double* d_out, void* stream);
 int b200md_nep_invalidate(b200md_nep* p, int n_new, void* stream);
+/* Only the atoms with caller index < n_owned receive energy / force / virial from the following
+ * b200md_nep_compute calls (0 = all atoms, the default): in a spatial domain the rest are ghosts,
+ * whose results the owner rank computes and the local rank would discard
+ * (cf. nep_multigpu.cu:1764-1802, which copies back the owned range only). */
+int b200md_nep_set_owned(b200md_nep* p, int n_owned);
 
 /* ---------------------------------------------------------------------------------------------
  * Tensor-core self-test (no reference counterpart): one CTA computes D[128 x N] = A[128 x K] .
