@@ -183,13 +183,13 @@ __global__ void __launch_bounds__(BLK, MINB)
     b2_body_force_final<NT, K1, DEPTH>(i, P, box, pe, force, virial);
 }
 
-template <int K1>
-__global__ void __launch_bounds__(BLK) k_force_angular(B2NepView P, B2Box box)
+template <int K1, int NTHR>
+__global__ void __launch_bounds__(NTHR) k_force_angular(B2NepView P, B2Box box)
 {
   extern __shared__ float dyn_smem[];
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * NTHR + threadIdx.x;
   if (i < P.n)
-    b2_body_force_angular<K1>(i, P, box, dyn_smem, blockDim.x, threadIdx.x);
+    b2_body_force_angular<K1, NTHR>(i, P, box, dyn_smem, threadIdx.x);
 }
 
 // parity hooks ---------------------------------------------------------------------------------
@@ -394,7 +394,11 @@ int launch_angular(const b200md_nep* p, const B2Box& box, cudaStream_t st, bool 
     B2_LAUNCHED();
     return B200MD_OK;
   }
-  auto kern = k_force_angular<K1>;
+  void (*kern)(B2NepView, B2Box) = k_force_angular<K1, 128>;
+  if (p->ang_block == 64)
+    kern = k_force_angular<K1, 64>;
+  else if (p->ang_block == 32)
+    kern = k_force_angular<K1, 32>;
   if (p->ang_smem > 48 * 1024)
     B2_CUDA(cudaFuncSetAttribute(
       kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ang_smem));

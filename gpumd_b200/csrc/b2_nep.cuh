@@ -438,6 +438,8 @@ B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
 #pragma unroll
       for (int abc = 0; abc < B2_NABC; ++abc)
         s[c][abc] = 0.0f;
+    // (no software pipelining here: with NCH*24 accumulators live it costs registers and was
+    // measured slower, 0.31 vs 0.29 ms)
     for (int m = 0; m < nn; ++m) {
       const int j = P.nl_a[(size_t)m * P.n + i];
       const B2Atom a2 = b2_load_atom(&P.atoms[j]);
@@ -783,10 +785,12 @@ B2_HD void b2_force_radial_sum(int i, const B2NepView& P, const B2Box& box, floa
 // nep_utilities.cuh:1523-1672).  `w` is scratch for the per-atom weights dU/ds[n][abc], laid out
 // w[(n*24+abc)*stride + lane] (shared memory on the device).
 // ---------------------------------------------------------------------------------------------
-template <int K1>
-B2_HD void b2_body_force_angular(
-  int i, const B2NepView& P, const B2Box& box, float* w, int stride, int lane)
+// STRIDE = threads per block (compile-time so that the scratch offsets are immediates; the host
+// build of tests/emu uses 1)
+template <int K1, int STRIDE>
+B2_HD void b2_body_force_angular(int i, const B2NepView& P, const B2Box& box, float* w, int lane)
 {
+  constexpr size_t stride = STRIDE;
   const float C3B[B2_NABC] = {B2_C3B_LIST};
   const size_t N = (size_t)P.n;
   // ---- weights: 3-body (calculate_s_one, nep_utilities.cuh:1327-1340) + chain rule of the
@@ -837,9 +841,14 @@ B2_HD void b2_body_force_angular(
   const int t1 = a1.type;
   const int nn = P.nn_a[i];
   const size_t plane = (size_t)P.mn_a * N;
+  // gathers one neighbour ahead (record) / two ahead (index), as in the radial kernels
+  int jn = nn > 0 ? P.nl_a[i] : i;
+  B2Atom an = b2_load_atom(&P.atoms[jn]);
+  int j2 = nn > 1 ? P.nl_a[N + i] : i;
   for (int m = 0; m < nn; ++m) {
-    const int j = P.nl_a[(size_t)m * N + i];
-    const B2Atom a2 = b2_load_atom(&P.atoms[j]);
+    const B2Atom a2 = an;
+    an = b2_load_atom(&P.atoms[j2]);
+    j2 = (m + 2 < nn) ? P.nl_a[(size_t)(m + 2) * N + i] : i;
     float x12, y12, z12;
     b2_r12(geo, box, a1, a2, x12, y12, z12);
     const float d = sqrtf(b2_d2(x12, y12, z12));

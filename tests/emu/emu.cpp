@@ -217,7 +217,7 @@ static void run_angular(emu_nep* p, const B2Box& box, bool force)
   std::vector<float> w((size_t)p->m.na1 * B2_NABC + 1);
   for (int i = 0; i < p->n; ++i) {
     if (force)
-      b2_body_force_angular<K1>(i, p->P, box, w.data(), 1, 0);
+      b2_body_force_angular<K1, 1>(i, p->P, box, w.data(), 0);
     else
       b2_body_desc_angular<K1, 5>(i, p->P, box);
   }
