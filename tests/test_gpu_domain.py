@@ -19,7 +19,7 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _worker(rank, world, port, out_dir, steps):
+def _worker(rank, world, port, out_dir, steps, ensemble):
     import torch
     import torch.distributed as dist
     sys.path.insert(0, str(ROOT))
@@ -34,11 +34,12 @@ def _worker(rank, world, port, out_dir, steps):
         vel = init_velocities(s["mass"], 600.0, seed=42)
         dom = SlabDomain(s["h"], s["pbc"], 8.0, rank, world, "cuda")
         dom.distribute(s["type"], s["pos"], s["mass"], vel)
-        md = DomainMD(dom, GOLDEN / "nep_PbTe.txt")
+        dt = 2.0 / TIME_UNIT_CONVERSION
+        md = DomainMD(dom, GOLDEN / "nep_PbTe.txt", ensemble=ensemble, temperature=450.0,
+                      temperature_coupling=50.0, time_step=dt)
         md.compute_force()
         md.find_thermo()
         rows = [md.read_thermo()]
-        dt = 2.0 / TIME_UNIT_CONVERSION
         for k in range(steps):
             if k == 30:
                 md.exchange()  # a forced migration/re-order in the middle of the run
@@ -54,7 +55,10 @@ def _worker(rank, world, port, out_dir, steps):
         dist.destroy_process_group()
 
 
-def test_two_domains_track_single_gpu(tmp_path):
+@pytest.mark.parametrize("ensemble", ["nve", "nvt_bdp", "nvt_nhc"])
+def test_two_domains_track_single_gpu(tmp_path, ensemble):
+    """NVE, and two thermostats whose state (BDP generator, NHC chain) is replicated on every rank and
+    advanced from the all-reduced temperature."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -63,7 +67,7 @@ def test_two_domains_track_single_gpu(tmp_path):
     from gpumd_b200.structures import TIME_UNIT_CONVERSION, init_velocities, rocksalt_pbte
     build.build_lib()
     steps = 100
-    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), steps), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), str(tmp_path), steps, ensemble), nprocs=2, join=True)
     multi = np.load(tmp_path / "multi.npy")
     # single GPU, full periodic box
     s = rocksalt_pbte((12, 6, 6), rattle=0.02, seed=1)
@@ -72,14 +76,19 @@ def test_two_domains_track_single_gpu(tmp_path):
     box = engine.Box(s["h"], s["pbc"])
     force = engine.Force()
     pot = force.parse_potential(GOLDEN / "nep_PbTe.txt", n)
-    ens = engine.Ensemble_NVE(n)
+    dt = 2.0 / TIME_UNIT_CONVERSION
+    if ensemble == "nvt_bdp":
+        ens = engine.Ensemble_BDP(n, 450.0, 50.0)
+    elif ensemble == "nvt_nhc":
+        ens = engine.Ensemble_NHC(n, 450.0, 50.0, dt)
+    else:
+        ens = engine.Ensemble_NVE(n)
     thermo = torch.zeros(8, dtype=torch.float64, device="cuda")
     args = (box, atom.position_per_atom, atom.type, atom.potential_per_atom, atom.force_per_atom,
             atom.virial_per_atom)
     force.compute(*args)
     ens.find_thermo(box.get_volume(), atom, thermo)
     single = [thermo.cpu().numpy().copy()]
-    dt = 2.0 / TIME_UNIT_CONVERSION
     for k in range(steps):
         ens.compute1(dt, box, atom, thermo)
         force.compute(*args)
