@@ -246,15 +246,15 @@ B2_HD void b2_body_desc_radial(
     for (int m = 0; m < P.nt * K1; ++m)
       acc[(size_t)m * stride + lane] = 0.0f;
   }
-  int jn = nn > 0 ? list[i] : i;
+  int jn = nn > 0 ? B2_LDCS(&list[i]) : i;
   B2Atom an = b2_load_atom(&P.atoms[jn]);
-  int j2 = nn > 1 ? list[(size_t)P.n + i] : i;
+  int j2 = nn > 1 ? B2_LDCS(&list[(size_t)P.n + i]) : i;
   for (int s = 0; s < nn; ++s) {
     const int j = jn;
     const B2Atom a2 = an;
     jn = j2;
     an = b2_load_atom(&P.atoms[j2]);
-    j2 = (s + 2 < nn) ? list[(size_t)(s + 2) * P.n + i] : i;
+    j2 = (s + 2 < nn) ? B2_LDCS(&list[(size_t)(s + 2) * P.n + i]) : i;
     float x12, y12, z12;
     b2_r12(geo, box, a1, a2, x12, y12, z12);
     const float d2 = b2_d2(x12, y12, z12);
@@ -264,7 +264,7 @@ B2_HD void b2_body_desc_radial(
       if (d2 >= B2_LDG(&P.rc2_r[pair]))
         continue;
       if (cr < P.mn_r)
-        P.nl_r[(size_t)cr * P.n + i] = j;
+        B2_STCS(&P.nl_r[(size_t)cr * P.n + i], j);
       ++cr;
       if (d2 < B2_LDG(&P.rc2_a[pair])) {
         if (ca < P.mn_a)
@@ -736,13 +736,13 @@ B2_HD void b2_force_radial_sum(int i, const B2NepView& P, const B2Box& box, floa
   float4 un[DEPTH][KP4];
 #pragma unroll
   for (int p = 0; p < DEPTH; ++p) {
-    const int jp = p < nn ? P.nl_r[(size_t)p * N + i] : i;
+    const int jp = p < nn ? B2_LDCS(&P.nl_r[(size_t)p * N + i]) : i;
     an[p] = b2_load_atom(&P.atoms[jp]);
 #pragma unroll
     for (int q = 0; q < KP4; ++q)
       un[p][q] = B2_LDG(&Ubase[(size_t)jp * ust4 + q]);
   }
-  int jnext = DEPTH < nn ? P.nl_r[(size_t)DEPTH * N + i] : i;
+  int jnext = DEPTH < nn ? B2_LDCS(&P.nl_r[(size_t)DEPTH * N + i]) : i;
   for (int s = 0; s < nn; s += DEPTH) {
 #pragma unroll
     for (int p = 0; p < DEPTH; ++p) {
@@ -761,7 +761,7 @@ B2_HD void b2_force_radial_sum(int i, const B2NepView& P, const B2Box& box, floa
 #pragma unroll
       for (int q = 0; q < KP4; ++q)
         un[p][q] = B2_LDG(&Ubase[(size_t)jl * ust4 + q]);
-      jnext = (s + p + DEPTH + 1 < nn) ? P.nl_r[(size_t)(s + p + DEPTH + 1) * N + i] : i;
+      jnext = (s + p + DEPTH + 1 < nn) ? B2_LDCS(&P.nl_r[(size_t)(s + p + DEPTH + 1) * N + i]) : i;
       if (s + p < nn)
         b2_radial_pair<NT, K1>(P, geo, box, a1, t1, a2, Uj, Ur, rcv, rciv, Ui, acc);
     }
