@@ -163,38 +163,100 @@ static void read_model(const char* path, Model& m)
   }
 }
 
-// Velocity::initialize: uniform random velocities, zero linear momentum, scale to T
-// (velocity.cu:55-75,312-347; angular-momentum removal is skipped: periodic bulk systems only)
+// Velocity::initialize (velocity.cu:55-75, 312-347): uniform random velocities from rand() -- the
+// reference never calls srand() unless a seed is given, so `velocity T` is reproducible --, then
+// Velocity::correct_velocity (:77-270: zero linear momentum, then remove the rigid rotation
+// w = I^-1 L about the centre of mass unless the inertia tensor is singular), then scale to T (:38-53).
 static void initialize_velocity(Atom& a, double temperature, bool use_seed, int seed)
 {
   const int N = a.number_of_atoms;
-  double* v = a.cpu_velocity_per_atom.data();
-  if (use_seed) {
-    for (int n = 0; n < N; ++n)
-      for (int d = 0; d < 3; ++d) {
-        srand((unsigned)seed + n * 3 + d);
-        v[n + (size_t)N * d] = -1.0 + (rand() * 2.0) / RAND_MAX;
-      }
-  } else {
-    for (int n = 0; n < N; ++n)
-      for (int d = 0; d < 3; ++d)
-        v[n + (size_t)N * d] = -1.0 + (rand() * 2.0) / RAND_MAX;
+  double* vx = a.cpu_velocity_per_atom.data();
+  double* vy = vx + N;
+  double* vz = vy + N;
+  const double* x = a.cpu_position_per_atom.data();
+  const double* y = x + N;
+  const double* z = y + N;
+  const double* m = a.cpu_mass.data();
+  for (int n = 0; n < N; ++n) {
+    if (use_seed)
+      srand((unsigned)seed + n * 3);
+    vx[n] = -1.0 + (rand() * 2.0) / RAND_MAX;
+    if (use_seed)
+      srand((unsigned)seed + n * 3 + 1);
+    vy[n] = -1.0 + (rand() * 2.0) / RAND_MAX;
+    if (use_seed)
+      srand((unsigned)seed + n * 3 + 2);
+    vz[n] = -1.0 + (rand() * 2.0) / RAND_MAX;
   }
+  // linear momentum
   double p[3] = {0, 0, 0}, mt = 0;
   for (int n = 0; n < N; ++n) {
-    mt += a.cpu_mass[n];
-    for (int d = 0; d < 3; ++d)
-      p[d] += a.cpu_mass[n] * v[n + (size_t)N * d];
+    mt += m[n];
+    p[0] += m[n] * vx[n];
+    p[1] += m[n] * vy[n];
+    p[2] += m[n] * vz[n];
   }
+  for (int n = 0; n < N; ++n) {
+    vx[n] -= p[0] / mt;
+    vy[n] -= p[1] / mt;
+    vz[n] -= p[2] / mt;
+  }
+  // angular momentum about the centre of mass
+  double r0[3] = {0, 0, 0};
+  for (int n = 0; n < N; ++n) {
+    r0[0] += x[n] * m[n];
+    r0[1] += y[n] * m[n];
+    r0[2] += z[n] * m[n];
+  }
+  for (double& c : r0)
+    c /= mt;
+  double L[3] = {0, 0, 0}, I[3][3] = {{0, 0, 0}, {0, 0, 0}, {0, 0, 0}};
+  for (int n = 0; n < N; ++n) {
+    const double dx = x[n] - r0[0], dy = y[n] - r0[1], dz = z[n] - r0[2];
+    L[0] += m[n] * (dy * vz[n] - dz * vy[n]);
+    L[1] += m[n] * (dz * vx[n] - dx * vz[n]);
+    L[2] += m[n] * (dx * vy[n] - dy * vx[n]);
+    I[0][0] += m[n] * (dy * dy + dz * dz);
+    I[1][1] += m[n] * (dx * dx + dz * dz);
+    I[2][2] += m[n] * (dx * dx + dy * dy);
+    I[0][1] -= m[n] * dx * dy;
+    I[1][2] -= m[n] * dy * dz;
+    I[0][2] -= m[n] * dx * dz;
+  }
+  I[1][0] = I[0][1];
+  I[2][1] = I[1][2];
+  I[2][0] = I[0][2];
+  const double det = I[0][0] * I[1][1] * I[2][2] + I[0][1] * I[1][2] * I[2][0] +
+                     I[0][2] * I[1][0] * I[2][1] - I[0][0] * I[1][2] * I[2][1] -
+                     I[0][1] * I[1][0] * I[2][2] - I[2][0] * I[1][1] * I[0][2];
+  if (!(det > -1.0e-10 && det < 1.0e-10)) {
+    double inv[3][3];
+    inv[0][0] = I[1][1] * I[2][2] - I[1][2] * I[2][1];
+    inv[0][1] = -(I[0][1] * I[2][2] - I[0][2] * I[2][1]);
+    inv[0][2] = I[0][1] * I[1][2] - I[0][2] * I[1][1];
+    inv[1][0] = -(I[1][0] * I[2][2] - I[1][2] * I[2][0]);
+    inv[1][1] = I[0][0] * I[2][2] - I[0][2] * I[2][0];
+    inv[1][2] = -(I[0][0] * I[1][2] - I[0][2] * I[1][0]);
+    inv[2][0] = I[1][0] * I[2][1] - I[1][1] * I[2][0];
+    inv[2][1] = -(I[0][0] * I[2][1] - I[0][1] * I[2][0]);
+    inv[2][2] = I[0][0] * I[1][1] - I[0][1] * I[1][0];
+    double w[3];
+    for (int r = 0; r < 3; ++r)
+      w[r] = (inv[r][0] / det) * L[0] + (inv[r][1] / det) * L[1] + (inv[r][2] / det) * L[2];
+    for (int n = 0; n < N; ++n) { // v_i -= w x dr_i
+      const double dx = x[n] - r0[0], dy = y[n] - r0[1], dz = z[n] - r0[2];
+      vx[n] -= w[1] * dz - w[2] * dy;
+      vy[n] -= w[2] * dx - w[0] * dz;
+      vz[n] -= w[0] * dy - w[1] * dx;
+    }
+  }
+  // scale to the target temperature
   double ke2 = 0;
   for (int n = 0; n < N; ++n)
-    for (int d = 0; d < 3; ++d) {
-      v[n + (size_t)N * d] -= p[d] / mt;
-      ke2 += a.cpu_mass[n] * v[n + (size_t)N * d] * v[n + (size_t)N * d];
-    }
+    ke2 += m[n] * (vx[n] * vx[n] + vy[n] * vy[n] + vz[n] * vz[n]);
   const double factor = std::sqrt(temperature / (ke2 / (3.0 * K_B * N)));
   for (size_t k = 0; k < (size_t)3 * N; ++k)
-    v[k] *= factor;
+    vx[k] *= factor;
 }
 
 class Run
