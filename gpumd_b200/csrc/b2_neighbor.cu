@@ -359,12 +359,13 @@ int Neighbor::update(
     if (rc_inv != B200MD_OK)
       return rc_inv;
   }
-  // large-box requirement of the reference: nep.cu:1304-1312 (small boxes use explicit images)
+  // the cell list needs >= 5 half-(rc+skin) cells per periodic direction.  b200md_nep_compute never
+  // gets here with a thinner box (it evaluates a supercell instead); LJ / Tersoff / EAM do
   for (int d = 0; d < 3; ++d) {
     if (box.pbc[d] && box.thickness[d] <= 2.5 * (rc + skin)) {
       set_error(
-        "periodic box thickness <= 2.5*(rc+1): this is the reference's small-box path "
-        "(nep_small_box.cuh), which libb200md does not implement");
+        "periodic box thickness <= 2.5*(rc+1): small boxes are supported for NEP only (supercell "
+        "path); this potential needs a larger box or a replicated cell");
       return B200MD_ERR_SMALL_BOX;
     }
   }

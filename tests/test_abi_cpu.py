@@ -42,3 +42,17 @@ def test_no_cpu_fallback(b200md_lib):
     from gpumd_b200 import engine
     with pytest.raises(lib.B200mdError):
         engine.NEP(GOLDEN / "nep_PbTe.txt", 512)
+
+
+def test_standalone_driver_refuses_to_run_without_a_gpu(tmp_path):
+    """The C++ driver has no CPU path either: on a machine without a CUDA device it must say so and
+    exit 1 before touching any input file (the reference's error convention, error.cuh:22-62)."""
+    import subprocess
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    from gpumd_b200 import build
+    exe = build.build_host()
+    r = subprocess.run([str(exe)], cwd=tmp_path, capture_output=True, text=True, timeout=60)
+    assert r.returncode == 1
+    assert "no CUDA device" in r.stderr and "no CPU fallback" in r.stderr
