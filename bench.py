@@ -560,10 +560,14 @@ def ours(args, rank, world):
     tf = ROOT / "profiles" / "ncu_traffic.json"
     if tf.exists():
         traffic = json.loads(tf.read_text()).get(top)
+    ncu_metrics = None
+    mf = ROOT / "profiles" / "ncu_metrics.json"
+    if mf.exists():  # issue / FMA / L1 utilisation of the same kernel from the committed ncu capture:
+        ncu_metrics = json.loads(mf.read_text()).get(top)  # the NEP kernels are not HBM-bound
     total_bytes = sum(abytes.values()) - abytes["descriptor+MLP"] + abytes["descriptor+MLP"]
     roofline = {
         "bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src, "ncu": ncu_metrics,
         "algorithmic_bytes_per_atom": abytes[key], "kernel_ms": top_ms,
         "step_algorithmic_bytes_per_atom": total_bytes,
         "step_hbm_frac": total_bytes * n / (ms / args.steps * 1e-3) / 1e9 / peak,
