@@ -163,8 +163,9 @@ static void read_model(const char* path, Model& m)
   }
 }
 
-// Velocity::initialize (velocity.cu:55-75, 312-347): uniform random velocities from rand() -- the
-// reference never calls srand() unless a seed is given, so `velocity T` is reproducible --, then
+// Velocity::initialize (velocity.cu:55-75, 312-347): uniform random velocities from rand().  Like the
+// reference's -DDEBUG build (main_common.cu:30-35: no srand, a release build seeds from the clock)
+// this driver never seeds the stream unless `seed` is given, so `velocity T` is reproducible.  Then
 // Velocity::correct_velocity (:77-270: zero linear momentum, then remove the rigid rotation
 // w = I^-1 L about the centre of mass unless the inertia tensor is singular), then scale to T (:38-53).
 static void initialize_velocity(Atom& a, double temperature, bool use_seed, int seed)
