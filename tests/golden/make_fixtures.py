@@ -26,6 +26,15 @@ COPIES = {
     # BaZrO3 40-atom golden regression (tests_pytest/test_regression.py:35-44)
     "tests_pytest/fixtures/models/nep_BaZrO3.txt": "nep_BaZrO3.txt",
     "tests_pytest/fixtures/structures/BaZrO3-nat40-rattled.xyz": "BaZrO3-nat40-rattled.xyz",
+    # the other structure / model pairs of the reference's property tests (tests_pytest/conftest.py:
+    # invariances, finite-difference forces): 3-type ZBL perovskite, 1-type carbon with 17/13 basis
+    # functions and a 100-neuron layer, 2-type water with the 4-body term
+    "tests_pytest/fixtures/models/nep_BaTiO3.txt": "nep_BaTiO3.txt",
+    "tests_pytest/fixtures/structures/BaTiO3-nat40-rattled.xyz": "BaTiO3-nat40-rattled.xyz",
+    "tests_pytest/fixtures/models/nep_C.txt": "nep_C_pytest.txt",
+    "tests_pytest/fixtures/structures/C-nat16-rattled.xyz": "C-nat16-rattled.xyz",
+    "tests_pytest/fixtures/models/nep_water.txt": "nep_water.txt",
+    "tests_pytest/fixtures/structures/water-nat63-from-md.xyz": "water-nat63-from-md.xyz",
     # carbon 64 000-atom NVE trajectory golden (tests/gpumd/carbon): thermo + neighbour maxima
     "potentials/nep/C_2022_NEP4.txt": "nep_C_2022_NEP4.txt",
     "tests/gpumd/carbon/thermo1.out": "carbon_thermo1.out",

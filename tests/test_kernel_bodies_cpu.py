@@ -24,7 +24,10 @@ def check_fv(out, ref, noise=1.0):
                  atol=TOL["virial"]["atol"] * vs, what="virial")
 
 
-def check_nep(oracle, dev, model, s, n):
+def check_nep(oracle, dev, model, s, n, energy_tol=None):
+    """energy_tol: eV/atom bound against the FP32 restatement (default 1e-6).  Callers with
+    deep-well models (|E|/N of several eV) pass 1e-6 * |E|/N: FP32 rounding is relative."""
+    energy_tol = TOL["energy_per_atom"] if energy_tol is None else energy_tol
     orc = oracle.NepOracle(GOLDEN / model)
     r32 = orc.compute(s["type"], s["h"], s["pbc"], s["pos"], precision=32, lists=True, descriptors=True)
     r64 = orc.compute(s["type"], s["h"], s["pbc"], s["pos"], precision=64)
@@ -38,8 +41,8 @@ def check_nep(oracle, dev, model, s, n):
     # |dE|/N <= 1e-6 eV against the FP32 restatement (the reference GPU's arithmetic); against the
     # FP64 truth allow the FP32 pair-math noise itself (the restatement's own f32-f64 gap) on top
     gap = abs(r32["pe"].sum() - r64["pe"].sum()) / n
-    assert abs(out["pe"].sum() - r32["pe"].sum()) / n < TOL["energy_per_atom"]
-    assert abs(out["pe"].sum() - r64["pe"].sum()) / n < TOL["energy_per_atom"] + 2 * gap
+    assert abs(out["pe"].sum() - r32["pe"].sum()) / n < energy_tol
+    assert abs(out["pe"].sum() - r64["pe"].sum()) / n < energy_tol + 2 * gap
     assert_close(out["pe"].sum(), r32["pe"].sum(), **TOL["energy"], what="energy")
     check_fv(out, r32)
     check_fv(out, r64)
