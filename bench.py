@@ -320,7 +320,7 @@ def side_bench(args, rank, world, local, torch, dist, engine):
 def ours_multi(args, rank, world, local, torch, dist, engine):
     """N > 1: weak scaling, one slab of cells^3 conventional cells (1 M atoms) per GPU, owned-atom
     integration, NCCL ghost-position halo per force evaluation, 8-double thermo all-reduce per
-    step, migration/ghost-list exchange every 50 steps (gpumd_b200/domain.py)."""
+    step, displacement-triggered migration / ghost-list exchange (gpumd_b200/domain.py)."""
     from gpumd_b200.domain import DomainMD, SlabDomain
     from gpumd_b200.structures import TIME_UNIT_CONVERSION, init_velocities, rocksalt_pbte
     s = rocksalt_pbte((args.cells * world, args.cells, args.cells), rattle=0.02, seed=1)

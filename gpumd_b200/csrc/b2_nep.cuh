@@ -16,8 +16,11 @@
 //    gradients of the real solid harmonics up to L = 4.  The reference re-derives the 4-/5-body
 //    prefactors for every pair (nep_utilities.cuh:625-718) and walks generic coefficient tables
 //    (nep_utilities.cuh:1342-1434);
-//  * the per-atom MLP is a separate pass over type-sorted tiles of atoms with zero-padded weight
-//    rows (apply_ann_one_layer, nep_utilities.cuh:169-194).
+//  * the per-atom MLP (apply_ann_one_layer, nep_utilities.cuh:169-194) is a separate pass over
+//    128-atom tiles of one type on the tensor cores (b2_nep_tc.cuh); the SIMT body below
+//    (b2_body_mlp: type-sorted tiles, zero-padded weight rows) is the fallback for layer sizes the
+//    tensor-core kernel does not cover and what tests/emu runs on the host;
+//  * the neighbour-set split (nep.cu:436-486) is folded into the radial descriptor pass.
 // Summation orders therefore differ from the reference at the FP32 rounding level; the membership
 // of the radial/angular neighbour sets does not (b2_r12 / b2_d2 in b2_common.cuh).
 #pragma once

@@ -106,7 +106,8 @@ class SlabDomain:
 
     def exchange(self):
         """Migrate atoms that left the slab, rebuild the ghost send lists, size the local arrays.
-        Rare (fixed cadence); plain torch ops."""
+        Rare (triggered by DomainMD.maybe_exchange when atoms have moved too far); host-orchestrated
+        torch ops, tens to hundreds of ms per event."""
         dev = self.device
         if self.world == 1:
             raise RuntimeError("SlabDomain is for world_size > 1")

@@ -1,6 +1,6 @@
 #!/bin/bash
 # One gpurun call: smoke, GPU parity tests, a short bench, an ncu launch list and full captures of
-# the two radial kernels.  Everything lands in gpurun_out/.
+# the dominant kernels.  Everything lands in gpurun_out/.
 #   /usr/local/graft/bin/gpurun --timeout 1700 -- bash scripts/gpu_check.sh
 set -u
 mkdir -p gpurun_out
@@ -20,7 +20,7 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
   python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 tail -3 gpurun_out/ncu_bench.log
 echo "== ncu full: radial kernels"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-k_force_radial|k_desc_radial|k_split}" -s ${NCU_SKIP:-6} -c ${NCU_COUNT:-6} \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"${NCU_KERNELS:-k_force_final|k_desc_radial|k_mlp_tc}" -s ${NCU_SKIP:-6} -c ${NCU_COUNT:-6} \
   -o gpurun_out/prof_radial -f python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full.log 2>&1
 tail -3 gpurun_out/ncu_full.log
 fi
