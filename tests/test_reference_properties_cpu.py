@@ -43,6 +43,8 @@ def wrap(s):
 
 
 def evaluate(emu, model, s):
+    """emu: tests/emu_py.Emu, or any object with .nep(model_path, n) -> .compute(...) (the GPU tests
+    pass an adapter over the C-ABI)."""
     n = s["type"].shape[0]
     rc, out = emu.nep(GOLDEN / model, n).compute(s["type"], s["h"], s["pbc"], s["pos"])
     assert rc == 0
