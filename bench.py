@@ -17,6 +17,9 @@ Printed JSON (one line, rank 0):
              (positions/types H2D from pinned memory, energies/forces/virials D2H, every step)
   roofline   dominant kernel: SURVEY.md 8(d) algorithmic bytes per atom x atoms / mean launch time
   cpu_baseline  the reference's own CPU implementation (NEP_CPU, oracle/_ref) on the host cores
+  reference_gpu the unmodified reference gpumd (oracle/_ref/gpumd_ref) on the same GPU(s), same
+                model.xyz / run.in / step count, run after our timed region -- the bar north_star names
+  neighbor      cost of one neighbour rebuild and the measured steps per rebuild
 --impl reference times NEP_CPU alone on the same crystal/model/metric (bounded sample per step).
 """
 import argparse
@@ -116,6 +119,48 @@ def crystal(cells, workload="pbte"):
     s = rocksalt_pbte(cells, rattle=0.02, seed=1)
     s["vel"] = init_velocities(s["mass"], 300.0, seed=42)
     return s
+
+
+def reference_gpu(s, vel, n_gpus, steps, potential=MODEL, symbols=None, ensemble="nve", dt_fs=1.0):
+    """The bar north_star names: the UNMODIFIED reference gpumd (oracle/_ref/gpumd_ref, built from
+    /root/reference by oracle/Makefile.gpumd_ref) on the same model.xyz / run.in for the same number of
+    steps, on the same box, OUTSIDE our timed region; with n_gpus > 1 visible devices it takes its own
+    NEP_MULTIGPU path (src/force/force.cu:139-160).  Value = its "Speed of this run" line
+    (src/main_gpumd/run.cu:321-326).  Returns None when the binary did not travel to this box."""
+    import re
+    import shutil
+    import tempfile
+    from gpumd_b200.structures import nep_type_order, write_xyz
+    exe = ROOT / "oracle" / "_ref" / "gpumd_ref"
+    if not exe.exists():
+        return None
+    d = Path(tempfile.mkdtemp(prefix="refgpu_"))
+    try:
+        t0 = time.time()
+        write_xyz(d / "model.xyz", s, symbols or nep_type_order(potential), vel)
+        shutil.copyfile(potential, d / "potential.txt")
+        (d / "run.in").write_text(f"potential potential.txt\nensemble {ensemble}\ntime_step {dt_fs:g}\n"
+                                  f"dump_thermo {max(steps, 1)}\nrun {steps}\n")
+        t_write = time.time() - t0
+        env = dict(os.environ)
+        vis = env.get("CUDA_VISIBLE_DEVICES")
+        ids = [x for x in vis.split(",") if x] if vis else [str(k) for k in range(n_gpus)]
+        env["CUDA_VISIBLE_DEVICES"] = ",".join(ids[:n_gpus])
+        t0 = time.time()
+        r = subprocess.run([str(exe)], cwd=d, capture_output=True, text=True, timeout=1500, env=env)
+        wall = time.time() - t0
+        speed = re.findall(r"Speed of this run = ([0-9.eE+-]+) atom\*step/second", r.stdout)
+        tail = [ln.strip() for ln in r.stdout.splitlines() if ln.strip() and not ln.startswith("---")][-6:]
+        out = {"value": float(speed[-1]) if speed else None, "unit": "atom-steps/s", "steps": steps,
+               "n_gpus": n_gpus, "n_atoms": int(s["type"].shape[0]), "returncode": r.returncode,
+               "wall_s": round(wall, 2), "input_write_s": round(t_write, 2),
+               "binary": "oracle/_ref/gpumd_ref (unmodified reference, nvcc -O3 -arch=sm_100 -DDEBUG)",
+               "path": "NEP_MULTIGPU" if n_gpus > 1 else "NEP", "stdout_tail": tail}
+        if r.returncode != 0:
+            out["stderr_tail"] = r.stderr[-500:]
+        return out
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def reference_arm(args, rank, world):
@@ -417,6 +462,12 @@ def ours_multi(args, rank, world, local, torch, dist, engine):
     torch.cuda.synchronize()
     e2e_t = torch.tensor([time.time() - t0], dtype=torch.float64, device="cuda")
     dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    ref_gpu = None
+    torch.cuda.synchronize()
+    if rank == 0 and not args.no_reference_gpu:
+        s_ref = rocksalt_pbte((args.cells * world, args.cells, args.cells), rattle=0.02, seed=1)
+        ref_gpu = reference_gpu(s_ref, init_velocities(s_ref["mass"], 300.0, seed=42), world, args.steps)
+        del s_ref
     if rank == 0:
         print(json.dumps({
             "metric": METRIC, "value": n_global * args.steps / (ms * 1e-3), "unit": "atom-steps/s",
@@ -442,8 +493,9 @@ def ours_multi(args, rank, world, local, torch, dist, engine):
                     "steps": e2e_steps,
                     "what": "per rank: b200md_nep_compute_host on its local (owned+ghost) system, pinned "
                             "host buffers, H2D+D2H inside the timed region; owned atoms x ranks / max time"},
-            "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None}))
-    dist.barrier()
+            "gpu_launches": int(launches), "roofline": None, "cpu_baseline": None,
+            "reference_gpu": ref_gpu}))
+    dist.barrier(group=args.cpu_group)
 
 
 def ours(args, rank, world):
@@ -458,6 +510,9 @@ def ours(args, rank, world):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl")
+        # host-side barrier for the wait on rank 0's reference-GPU run (an NCCL barrier would spin on
+        # the very GPUs the reference is being timed on)
+        args.cpu_group = dist.new_group(backend="gloo")
     if rank == 0:
         build.build_lib()
     if world > 1:
@@ -577,6 +632,25 @@ def ours(args, rank, world):
         "stage_share_of_step": {k: round(v / step_ms_prof, 4) for k, v in per_stage_ms.items()},
     }
 
+    # ---------------- cost of one neighbour rebuild (outside the headline: a 300 K solid does not
+    # trigger one in K steps, and neither does the reference, neighbor.cu:741-776) ----------------
+    rb = [torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)]
+    rebuild_ms = []
+    for _ in range(3):
+        pot.invalidate(n)  # forget the ordering and lists: the next force call rebuilds everything
+        torch.cuda.synchronize()
+        rb[0].record(); force.compute(*fargs); rb[1].record()
+        torch.cuda.synchronize()
+        rebuild_ms.append(rb[0].elapsed_time(rb[1]) - acc["force_call"] / prof_steps)
+    neighbor = {
+        "rebuild_ms": round(float(np.median(rebuild_ms)), 4),
+        "what": "extra device time of a force call that rebuilds cell sort + skin list + type tiles "
+                "(median of 3 forced rebuilds) over a force call that reuses them",
+        "rebuilds_in_timed_region": rebuilds,
+        "steps_per_rebuild_measured": (args.steps / rebuilds) if rebuilds else None,
+        "ms_per_step_if_rebuilt_every_20_steps": round(ms / args.steps + float(np.median(rebuild_ms)) / 20.0, 4),
+    }
+
     # ---------------- end to end: host buffers through b200md_nep_compute_host ----------------
     e2e_steps = max(3, min(args.steps, 10))
     h_type = torch.from_numpy(s["type"].copy()).pin_memory()
@@ -602,6 +676,11 @@ def ours(args, rank, world):
     del pot2
 
     cpu = cpu_baseline() if not args.no_cpu_baseline else None
+    ref_gpu = None
+    if not args.no_reference_gpu:
+        del atom, force, pot, ens
+        torch.cuda.empty_cache()
+        ref_gpu = reference_gpu(s, s["vel"], 1, args.steps)
     out = {
         "metric": METRIC, "value": value, "unit": "atom-steps/s", "n_gpus": world,
         "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
@@ -616,7 +695,7 @@ def ours(args, rank, world):
             "final_T_K": float(t_final[0]), "final_U_eV_per_atom": float(t_final[1]) / n,
         },
         "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-        "cpu_baseline": cpu,
+        "cpu_baseline": cpu, "neighbor": neighbor, "reference_gpu": ref_gpu,
     }
     print(json.dumps(out))
     if world > 1:
@@ -631,6 +710,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=50, help="conventional cells per edge (50 -> 1M atoms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true",
+                    help="skip the run of oracle/_ref/gpumd_ref (the reference on the same GPU) after the bench")
     ap.add_argument("--workload", default="pbte", choices=["pbte", "lj", "unep", "si"],
                     help="pbte = the BASELINE metric (C3); lj / unep / si = secondary lines for C2 / C4 / C5")
     args = ap.parse_args()

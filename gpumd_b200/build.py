@@ -40,7 +40,16 @@ def _stale(target, deps):
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build_lib(force=False, verbose=False):
+def build_lib(force=False, verbose=False, variant=None, defs=()):
+    """variant / defs: a diagnostic build with extra -D flags -> gpumd_b200/libb200md_<variant>.so
+    (objects under build_<variant>/); selected at run time with B200MD_LIB=<path> (lib.py)."""
+    if variant:
+        return _build_lib(PKG / f"libb200md_{variant}.so", PKG / f"build_{variant}",
+                          [f"-D{d}" for d in defs], force, verbose)
+    return _build_lib(LIB, OBJ, [], force, verbose)
+
+
+def _build_lib(LIB, OBJ, extra, force, verbose):
     nvcc = _nvcc()
     OBJ.mkdir(exist_ok=True)
     headers = list(CSRC.glob("*.cuh")) + list(CSRC.glob("*.h")) + [PKG.parent / "include" / "b200md.h"]
@@ -51,7 +60,7 @@ def build_lib(force=False, verbose=False):
         o = OBJ / (s.stem + ".o")
         objs.append(o)
         if force or _stale(o, [s] + headers):
-            jobs.append([nvcc] + NVCC_FLAGS + ["-c", str(s), "-o", str(o)])
+            jobs.append([nvcc] + NVCC_FLAGS + extra + ["-c", str(s), "-o", str(o)])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

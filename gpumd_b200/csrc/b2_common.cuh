@@ -27,6 +27,9 @@
 struct float4 {
   float x, y, z, w;
 };
+struct int4 {
+  int x, y, z, w;
+};
 #endif
 
 #if defined(__CUDA_ARCH__)
@@ -245,10 +248,11 @@ B2_HD void b2_sincospi(float x, float& s, float& c)
 #endif
 }
 
-// 1/sqrt(x): hardware approximation (<= 2 ulp) on the device
+// 1/sqrt(x): hardware approximation (<= 2 ulp) on the device.  -DB2_EXACT_RSQRT builds the
+// correctly rounded 1/sqrt (diagnostic builds only: gpumd_b200.build.build_lib(variant=...)).
 B2_HD float b2_rsqrt(float x)
 {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDA_ARCH__) && !defined(B2_EXACT_RSQRT)
   return rsqrtf(x);
 #else
   return 1.0f / sqrtf(x);

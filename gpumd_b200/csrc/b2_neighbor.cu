@@ -324,6 +324,8 @@ B2NeighborView Neighbor::view() const
   v.mn_skin = mn_skin;
   v.atoms = atoms.p;
   v.atoms_tmp = atoms_tmp.p;
+  v.plane0 = planes ? plane0.p : nullptr;
+  v.plane1 = planes ? plane1.p : nullptr;
   v.snap = snap.p;
   v.perm = perm.p;
   v.perm_tmp = perm_tmp.p;
@@ -424,6 +426,14 @@ int Neighbor::update(
   }
   k_rebuild_done<<<1, 1, 0, st>>>(flags.p);
   B2_LAUNCHED();
+  return B200MD_OK;
+}
+
+int Neighbor::enable_planes()
+{
+  B2_CUDA(plane0.reserve(capacity));
+  B2_CUDA(plane1.reserve(capacity));
+  planes = true;
   return B200MD_OK;
 }
 

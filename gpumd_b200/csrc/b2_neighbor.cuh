@@ -29,6 +29,11 @@ struct B2NeighborView {
   int mn_skin;       // skin-list capacity per atom
   B2Atom* atoms;     // [n] sorted records (current positions)
   B2Atom* atoms_tmp; // [n] scratch for re-ordering
+  // optional 16-byte PLANES of the same records for the gather-heavy radial NEP kernels:
+  // plane0[j] = {x, y}, plane1[j] = {z, type, pad}.  A warp-wide 128-bit gather then touches half as
+  // many 128-byte lines as with the 32-byte records (8 atoms per line instead of 4); null = off
+  int4* plane0 = nullptr;
+  int4* plane1 = nullptr;
   double* snap;      // [3n] positions at the last rebuild, sorted order (x0,y0,z0 SoA)
   int* perm;         // [n] sorted index -> caller index
   int* perm_tmp;     // [n]
@@ -56,6 +61,29 @@ struct B2NeighborView {
 
 // ---- pack: caller SoA -> sorted B2Atom records, and displacement trigger -------------------
 // (gpu_check_atom_distance, neighbor.cu:646-684; the trigger only needs to be conservative)
+B2_HD void b2_store_planes(const B2NeighborView& v, int i, const B2Atom& a)
+{
+#if defined(__CUDA_ARCH__)
+  if (v.plane0) {
+    int4 lo, hi;
+    lo.x = __double2loint(a.x);
+    lo.y = __double2hiint(a.x);
+    lo.z = __double2loint(a.y);
+    lo.w = __double2hiint(a.y);
+    hi.x = __double2loint(a.z);
+    hi.y = __double2hiint(a.z);
+    hi.z = a.type;
+    hi.w = 0;
+    v.plane0[i] = lo;
+    v.plane1[i] = hi;
+  }
+#else
+  (void)v;
+  (void)i;
+  (void)a;
+#endif
+}
+
 B2_HD void b2_body_pack_check(
   int i, const B2NeighborView& v, const B2Box& box, const int* type, const double* x,
   const double* y, const double* z, float trigger_d2)
@@ -68,6 +96,7 @@ B2_HD void b2_body_pack_check(
   a.type = type[src];
   a.pad = 0;
   v.atoms[i] = a;
+  b2_store_planes(v, i, a);
   float dx = (float)(a.x - v.snap[i]);
   float dy = (float)(a.y - v.snap[(size_t)v.n + i]);
   float dz = (float)(a.z - v.snap[(size_t)2 * v.n + i]);
@@ -130,6 +159,7 @@ B2_HD void b2_body_commit(int i, const B2NeighborView& v)
 {
   const B2Atom a = v.atoms_tmp[i];
   v.atoms[i] = a;
+  b2_store_planes(v, i, a);
   v.perm[i] = v.perm_tmp[i];
   v.snap[i] = a.x;
   v.snap[(size_t)v.n + i] = a.y;

@@ -21,6 +21,8 @@ public:
   bool have_grid = false;
 
   DevBuf<B2Atom> atoms, atoms_tmp;
+  DevBuf<int4> plane0, plane1; // see B2NeighborView::plane0 (enable_planes)
+  bool planes = false;
   DevBuf<double> snap;
   DevBuf<int> perm, perm_tmp, cell_of, order_tmp, cell_count, cell_fill, cell_start, nn_skin,
     nl_skin, flags;
@@ -31,6 +33,8 @@ public:
   int init(int num_atoms, double rc, int mn_skin);
   // also keep the type-bucketed tile order up to date at every rebuild (num_types <= 94)
   int enable_type_tiles(int num_types);
+  // also maintain the 16-byte planes of the sorted records (call after init)
+  int enable_planes();
   int max_tiles() const { return (n + 127) / 128 + tile_nt; }
   // Neighbor::find_neighbor_global, src/force/neighbor.cu:756-800 (fully asynchronous here)
   int update(const B2Box& box, const int* d_type, const double* d_pos, int n, cudaStream_t st);

@@ -5,6 +5,7 @@
 #include "b2_neighbor_host.h"
 #include "b2_nep.cuh"
 #include "b2_nep_tc.cuh"
+#include "b2_nep_radial.cuh"
 #include "b2_nep_model.h"
 #include <cmath>
 #include <cstdlib>
@@ -131,7 +132,7 @@ __global__ void __launch_bounds__(BLK) k_utable(B2NepView P)
   __shared__ float tile[BLK][KP + 1];
   const int base = blockIdx.x * BLK;
   const int i = base + threadIdx.x;
-  if (P.team) {
+  if (P.u_planes) {
     if (i < P.n)
       b2_body_utable_planes<K1>(i, P);
     return;
@@ -300,6 +301,7 @@ struct b200md_nep {
   int variant = 0;         // B200MD_NEP_VARIANT: kernel tuning variants for A/B measurements
   bool fuse_split = false; // many-type path: neighbour split inside the radial descriptor pass
   bool use_tc = false; // hidden layer on the tensor cores (k_mlp_tc) instead of k_mlp
+  bool radial_v2 = false; // few-type radial passes of b2_nep_radial.cuh (planes, branch-free loop)
   // small periodic boxes: supercell replication, see b200md_nep_compute
   DevBuf<int> rep_type;
   DevBuf<double> rep_pos, rep_out;
@@ -336,6 +338,24 @@ int dispatch_desc_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
     k_team_desc_radial<1, K1><<<team_grid, BLK, 0, st>>>(p->view, box);
   } else if (p->view.team) {
     k_team_desc_radial<2, K1><<<team_grid, BLK, 0, st>>>(p->view, box);
+  } else if (p->radial_v2) {
+    const B2NepView& P = p->view;
+    B2RadialDescArgs A;
+    A.n = P.n; A.nt = P.nt; A.nr1 = P.nr1; A.mn_r = P.mn_r; A.mn_a = P.mn_a;
+    A.plane0 = p->nb.plane0.p; A.plane1 = p->nb.plane1.p;
+    A.nn_skin = P.nn_skin; A.nl_skin = P.nl_skin;
+    A.nn_r = P.nn_r; A.nl_r = P.nl_r; A.nn_a = P.nn_a; A.nl_a = P.nl_a;
+    A.q = P.q; A.flags = P.flags;
+    A.rc_r = P.rc_r; A.rcinv_r = P.rcinv_r; A.rc2_r = P.rc2_r; A.rc2_a = P.rc2_a; A.c_r = P.c_r;
+    const int g = grid_for(p->n, BLK);
+    if (p->model.nt == 1 && box.ortho)
+      k_desc_radial2<1, K1, true><<<g, BLK, 0, st>>>(A, box);
+    else if (p->model.nt == 1)
+      k_desc_radial2<1, K1, false><<<g, BLK, 0, st>>>(A, box);
+    else if (box.ortho)
+      k_desc_radial2<2, K1, true><<<g, BLK, 0, st>>>(A, box);
+    else
+      k_desc_radial2<2, K1, false><<<g, BLK, 0, st>>>(A, box);
   } else if (p->model.nt == 1) {
     return launch_desc_radial<1, K1, true>(p, box, st);
   } else if (p->model.nt == 2) {
@@ -376,6 +396,30 @@ int dispatch_force_final(
     k_team_force_final<1, K1><<<team_grid, BLK, 0, st>>>(p->view, box, pe, f, v);
   else if (p->view.team)
     k_team_force_final<2, K1><<<team_grid, BLK, 0, st>>>(p->view, box, pe, f, v);
+  else if (p->radial_v2) {
+    const int g = grid_for(p->n, BLK);
+    const int4* p0 = p->nb.plane0.p;
+    const int4* p1 = p->nb.plane1.p;
+    // B200MD_NEP_VARIANT: resident blocks per SM the register allocation targets (A/B runs)
+#define B2_FF2(NT_, ORTHO_)                                                                      \
+  do {                                                                                           \
+    if (p->variant == 1)                                                                         \
+      k_force_final2<NT_, K1, ORTHO_, 5><<<g, BLK, 0, st>>>(p->view, p0, p1, box, pe, f, v);     \
+    else if (p->variant == 2)                                                                    \
+      k_force_final2<NT_, K1, ORTHO_, 4><<<g, BLK, 0, st>>>(p->view, p0, p1, box, pe, f, v);     \
+    else                                                                                         \
+      k_force_final2<NT_, K1, ORTHO_, 6><<<g, BLK, 0, st>>>(p->view, p0, p1, box, pe, f, v);     \
+  } while (0)
+    if (p->model.nt == 1 && box.ortho)
+      B2_FF2(1, true);
+    else if (p->model.nt == 1)
+      B2_FF2(1, false);
+    else if (box.ortho)
+      B2_FF2(2, true);
+    else
+      B2_FF2(2, false);
+#undef B2_FF2
+  }
   else if (p->model.nt == 1)
     return launch_force_final<1, K1>(p, box, st, pe, f, v);
   else if (p->model.nt == 2)
@@ -546,6 +590,13 @@ int nep_setup(b200md_nep* p, int num_atoms)
   // fused split pays when few skin candidates fail the radial test: (rc+skin)^3 / rc^3 small
   p->fuse_split = rs * rs * rs / (rc * rc * rc) < 1.45;
   B2_TRY(p->nb.init(num_atoms, rc, mn_skin));
+  // one- and two-type models: the plane-based radial kernels (B200MD_NEP_RADIAL=v1 keeps the
+  // round-1 kernels for A/B runs)
+  const char* rad_env = std::getenv("B200MD_NEP_RADIAL");
+  p->radial_v2 = m.nt <= 2 && !team && !(rad_env && std::strcmp(rad_env, "v1") == 0) &&
+                 (double)num_atoms * (mn_skin + 2) < 4.0e9; // 32-bit list offsets in those kernels
+  if (p->radial_v2)
+    B2_TRY(p->nb.enable_planes());
   const int pitch_r = (m.MN_radial + 7) / 8 * 8;
 
   B2_CUDA(p->nn_r.reserve(N));
@@ -620,6 +671,7 @@ int nep_setup(b200md_nep* p, int num_atoms)
   P.acc = p->acc.p;
   P.flags = p->nb.flags.p;
   P.team = team ? 1 : 0;
+  P.u_planes = (team || p->radial_v2) ? 1 : 0;
   P.pitch_r = pitch_r;
   {
     const B2NeighborView nv = p->nb.view();
@@ -642,9 +694,9 @@ int nep_setup(b200md_nep* p, int num_atoms)
     P.DK = m.DK;
     P.DN = m.DN;
     P.K3 = m.K3;
-    // the U table as a third GEMM of the same kernel (AoS rows only: the lane-team path keeps planes)
+    // the U table as a third GEMM of the same kernel (AoS rows or float4 planes, see epilogue 3)
     const char* u_env = std::getenv("B200MD_NEP_UTABLE");
-    P.N3 = (m.tc3_ok && !team && !(u_env && std::strcmp(u_env, "simt") == 0)) ? m.N3 : 0;
+    P.N3 = (m.tc3_ok && !(u_env && std::strcmp(u_env, "simt") == 0)) ? m.N3 : 0;
     P.tile_atom = p->nb.tile_atom.p;
     P.tile_type = p->nb.tile_type.p;
     P.tile_meta = p->nb.tile_meta.p;

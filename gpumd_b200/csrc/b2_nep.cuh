@@ -97,6 +97,8 @@ struct B2NepView {
   size_t skin_si, skin_sk; // B2NeighborView::skin_si / skin_sk
   int pitch_r;             // row pitch of nl_r when team != 0 (else nl_r is column-major)
   int team;                // 1: k_team_* kernels own the radial passes
+  int u_planes;            // 1: U is stored as float4 planes [(t*KP4+q)*n + i] (few-type kernels and
+                           //    lane teams), 0: AoS rows of UST floats (many-type path, tests/emu)
   int n_own;               // > 0: only caller indices < n_own get outputs (domain decomposition:
                            // the rest are ghosts whose forces the caller discards)
   // ---- tensor-core hidden layer (k_mlp_tc; null / 0 when the SIMT k_mlp is used) ----

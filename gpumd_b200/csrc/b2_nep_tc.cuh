@@ -249,18 +249,25 @@ __global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
       b2tc::mbar_wait(&bar_mma, mma_phase);
       mma_phase ^= 1u;
       b2tc::fence_after_sync();
-      // ---- epilogue 3: this thread's row of the U table (AoS, UST floats per atom) ----
+      // ---- epilogue 3: this thread's row of the U table: AoS (UST floats per atom) or, for the
+      //      few-type kernels, float4 planes [(t2*KP4 + q)*n + i] (row offset 4*(t2*KP4+q)) ----
       float* Urow = P.U + (size_t)(i >= 0 ? i : 0) * P.UST;
+      float4* Upl = reinterpret_cast<float4*>(P.U) + (i >= 0 ? i : 0);
       for (int c0 = 0; c0 < N3; c0 += 16) {
         uint32_t v[16];
         b2tc::tmem_ld16(tmem + lane_base + (uint32_t)c0, v);
         if (i >= 0) {
 #pragma unroll
           for (int g = 0; g < 4; ++g) {
-            if (c0 + 4 * g < P.UST) // UST = nt*KP is a multiple of 4
-              *reinterpret_cast<float4*>(Urow + c0 + 4 * g) =
+            if (c0 + 4 * g < P.UST) { // UST = nt*KP is a multiple of 4
+              const float4 val =
                 make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
                             __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+              if (P.u_planes)
+                Upl[(size_t)(c0 / 4 + g) * N] = val;
+              else
+                *reinterpret_cast<float4*>(Urow + c0 + 4 * g) = val;
+            }
           }
         }
       }

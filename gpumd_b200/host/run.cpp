@@ -30,13 +30,17 @@ static const double K_B = 8.617343e-5;                     // common.cuh:21
 static const double TIME_UNIT_CONVERSION = 1.018051e+1;    // common.cuh:26
 static const double PRESSURE_UNIT_CONVERSION = 1.602177e+2; // common.cuh:25
 
-static const std::map<std::string, double> MASS_TABLE = {
-  // subset of read_xyz.cu:36-142 covering the shipped potentials on the target configs
-  {"H", 1.008},     {"C", 12.011},      {"N", 14.007},     {"O", 15.999},    {"Mg", 24.305},
-  {"Al", 26.9815385}, {"Si", 28.085},   {"Ar", 39.948},    {"Ti", 47.867},   {"V", 50.9415},
-  {"Cr", 51.9961},  {"Ni", 58.6934},    {"Cu", 63.546},    {"Zr", 91.224},   {"Mo", 95.95},
-  {"Pd", 106.42},   {"Ag", 107.8682},   {"Te", 127.6},     {"Ba", 137.327},  {"Ta", 180.94788},
-  {"W", 183.84},    {"Pt", 195.084},    {"Au", 196.966569}, {"Pb", 207.2}};
+#include "element_mass.h" // the reference's full MASS_TABLE (read_xyz.cu:36-142)
+
+static bool element_mass(const std::string& symbol, double* mass)
+{
+  for (int k = 0; k < NUM_ELEMENT_MASS; ++k)
+    if (symbol == ELEMENT_MASS[k].symbol) {
+      *mass = ELEMENT_MASS[k].mass;
+      return true;
+    }
+  return false;
+}
 
 [[noreturn]] static void input_error(const std::string& msg)
 {
@@ -151,10 +155,8 @@ static void read_model(const char* path, Model& m)
     if (off_mass >= 0) {
       a.cpu_mass[n] = std::atof(tok[off_mass].c_str());
     } else {
-      auto it = MASS_TABLE.find(tok[off_species]);
-      if (it == MASS_TABLE.end())
+      if (!element_mass(tok[off_species], &a.cpu_mass[n]))
         input_error("Atom symbol " + tok[off_species] + " is not in the mass table.");
-      a.cpu_mass[n] = it->second;
     }
     if (off_vel >= 0)
       for (int d = 0; d < 3; ++d) // A/fs -> natural units (read_xyz.cu:380-387)
@@ -274,6 +276,14 @@ private:
   Model model_;
   Force force_;
   std::unique_ptr<Ensemble> ensemble_;
+  // what the `ensemble` keyword asked for; the object itself is built at `run` from the time step
+  // and atom count in force THEN, and rebuilt for every run (Integrate::initialize, integrate.cu:76-280)
+  struct EnsembleSpec {
+    int type = -1; // 0 nve, 1 nvt_ber, 2 nvt_nhc, 4 nvt_bdp (the reference's type codes)
+    double T = 0.0, Tc = 0.0;
+    bool has_seed = false;
+    unsigned seed = 0;
+  } ensemble_spec_;
   GPU_Vector<double> thermo_;
   std::vector<Group> group_;
   double time_step_ = 1.0 / TIME_UNIT_CONVERSION;
@@ -351,36 +361,45 @@ private:
         input_error("velocity should have 1 or 3 parameters.");
       if (!model_.has_velocity) {
         const bool use_seed = t.size() == 4 && t[2] == "seed";
+        if (state_on_gpu_) // a later run: start from where the atoms are now
+          a.position_per_atom.copy_to_host(a.cpu_position_per_atom.data());
         initialize_velocity(a, std::atof(t[1].c_str()), use_seed, use_seed ? std::atoi(t[3].c_str()) : 0);
+        if (state_on_gpu_)
+          a.velocity_per_atom.copy_from_host(a.cpu_velocity_per_atom.data());
       }
     } else if (t[0] == "ensemble") {
       // Integrate::parse_ensemble, integrate.cu:406-432,569-600: nvt_* take T1 T2 tau_T/dt
+      EnsembleSpec e;
       if (t.size() == 2 && t[1] == "nve") {
-        ensemble_.reset(new Ensemble_NVE_B200(0));
-      } else if (t.size() == 5 && (t[1] == "nvt_ber" || t[1] == "nvt_nhc" || t[1] == "nvt_bdp")) {
+        e.type = 0;
+      } else if ((t.size() == 5 || (t.size() == 7 && t[1] == "nvt_bdp" && t[5] == "seed")) &&
+                 (t[1] == "nvt_ber" || t[1] == "nvt_nhc" || t[1] == "nvt_bdp")) {
         const double T1 = std::atof(t[2].c_str()), T2 = std::atof(t[3].c_str());
-        const double Tc = std::atof(t[4].c_str());
+        e.T = T1;
+        e.Tc = std::atof(t[4].c_str());
         if (T1 <= 0.0 || T2 <= 0.0)
           input_error("Temperatures should > 0.");
         if (T1 != T2)
           input_error("temperature ramps are not supported by the b200md backend.");
-        if (Tc < 1.0)
+        if (e.Tc < 1.0)
           input_error("Temperature coupling should >= 1.");
-        if (t[1] == "nvt_ber")
-          ensemble_.reset(new Ensemble_BER_B200(1, T1, Tc));
-        else if (t[1] == "nvt_bdp")
-          ensemble_.reset(new Ensemble_BDP_B200(4, a.number_of_atoms, T1, Tc));
-        else
-          ensemble_.reset(new Ensemble_NHC_B200(2, a.number_of_atoms, T1, Tc, time_step_));
+        e.type = t[1] == "nvt_ber" ? 1 : (t[1] == "nvt_bdp" ? 4 : 2);
+        if (t.size() == 7) { // extension: `nvt_bdp T T tau seed S` fixes the noise stream
+          e.has_seed = true;
+          e.seed = (unsigned)std::strtoul(t[6].c_str(), nullptr, 10);
+        }
       } else {
         input_error("only 'ensemble nve', 'nvt_ber|nvt_nhc|nvt_bdp T T tau' are supported "
                     "by the b200md backend.");
       }
+      ensemble_spec_ = e;
     } else if (t[0] == "time_step") {
       if (t.size() < 2)
         input_error("time_step should have at least 1 parameter.");
       time_step_ = std::atof(t[1].c_str()) / TIME_UNIT_CONVERSION; // run.cu:657
     } else if (t[0] == "dump_thermo") {
+      if (t.size() != 2 || std::atoi(t[1].c_str()) <= 0)
+        input_error("dump_thermo should have 1 positive parameter (the interval).");
       dump_thermo_ = std::atoi(t[1].c_str());
     } else if (t[0] == "dump_restart") {
       if (t.size() != 2 || std::atoi(t[1].c_str()) <= 0)
@@ -393,6 +412,8 @@ private:
         input_error("replicate must come before 'potential' (run.cu:356-358).");
       replicate(t);
     } else if (t[0] == "run") {
+      if (t.size() != 2 || std::atoi(t[1].c_str()) < 0)
+        input_error("run should have 1 parameter (the number of steps).");
       perform_a_run(std::atoi(t[1].c_str()));
       dump_thermo_ = 0; // non-propagating keywords are reset after each run (run.cu:329-340)
       dump_restart_ = 0;
@@ -608,9 +629,28 @@ private:
 
   void perform_a_run(int number_of_steps)
   {
-    if (!has_potential_ || !ensemble_)
+    if (!has_potential_ || ensemble_spec_.type < 0)
       input_error("'potential' and 'ensemble' must precede 'run'.");
     Atom& a = model_.atom;
+    { // Integrate::initialize: a fresh ensemble object per run, from the CURRENT time step
+      const EnsembleSpec& e = ensemble_spec_;
+      if (e.type == 0) {
+        ensemble_.reset(new Ensemble_NVE_B200(0));
+      } else if (e.type == 1) {
+        ensemble_.reset(new Ensemble_BER_B200(1, e.T, e.Tc));
+      } else if (e.type == 4) {
+        // the reference seeds std::mt19937 with 12345678 under -DDEBUG and from the clock otherwise
+        // (ensemble_bdp.cu:31-37); B200MD_DEBUG_SEED=1 selects the former for trajectory parity
+        unsigned seed = e.seed;
+        if (!e.has_seed)
+          seed = std::getenv("B200MD_DEBUG_SEED")
+                   ? 12345678u
+                   : (unsigned)std::chrono::system_clock::now().time_since_epoch().count();
+        ensemble_.reset(new Ensemble_BDP_B200(4, a.number_of_atoms, e.T, e.Tc, seed));
+      } else {
+        ensemble_.reset(new Ensemble_NHC_B200(2, a.number_of_atoms, e.T, e.Tc, time_step_));
+      }
+    }
     if (!state_on_gpu_)
       upload_state();
     FILE* fid = nullptr;

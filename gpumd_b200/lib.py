@@ -6,8 +6,11 @@ point raises.  PyTorch is used only as the owner of device memory and streams.
 import ctypes as C
 from pathlib import Path
 
+import os
+
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libb200md.so"
+# B200MD_LIB: a diagnostic build of the same library (gpumd_b200.build.build_lib(variant=...))
+LIB_PATH = Path(os.environ.get("B200MD_LIB") or PKG / "libb200md.so")
 
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int)

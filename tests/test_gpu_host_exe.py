@@ -1,6 +1,7 @@
 """The C++ host layer (gpumd_b200/host: Potential/Force/Ensemble adapters + the standalone `b200md`
 driver) end to end: GPUMD's own input files in, thermo.out in the reference's format out, compared
 with the thermo.out the unmodified reference gpumd wrote for the same inputs on a B200."""
+import os
 import shutil
 import subprocess
 
@@ -45,7 +46,9 @@ def test_b200md_executable_reproduces_reference_thermo(tmp_path, case):
     shutil.copyfile(GOLDEN / potfile, tmp_path / "potential.txt")
     (tmp_path / "run.in").write_text(
         f"potential potential.txt\nensemble {ensemble}\ntime_step {dt}\ndump_thermo 10\nrun 200\n")
-    r = subprocess.run([str(exe)], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    # the fixture was written by a -DDEBUG build of the reference: std::mt19937(12345678) for nvt_bdp
+    env = dict(os.environ, B200MD_DEBUG_SEED="1")
+    r = subprocess.run([str(exe)], cwd=tmp_path, capture_output=True, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "Speed of this run" in r.stdout
     mine = read_thermo(tmp_path / "thermo.out")
@@ -58,6 +61,36 @@ def test_b200md_executable_reproduces_reference_thermo(tmp_path, case):
         assert np.allclose(mine[k, 3:6], ref[k, 3:6], rtol=1e-3, atol=2e-3)
         assert np.array_equal(mine[k, 9:], ref[k, 9:])  # the box columns
     assert abs(mine[0, 0] - ref[0, 0]) < 2e-3 and abs(mine[0, 2] - ref[0, 2]) / n < 2e-7
+
+
+def test_b200md_ensemble_is_built_at_run_with_the_final_time_step(tmp_path):
+    """`ensemble nvt_nhc ...` BEFORE `time_step 0.5` (the usual run.in order): the chain masses
+    Q = kT (dt Tc)^2 must use the 0.5 fs step in force at `run` (Integrate::initialize,
+    integrate.cu:76-280), and a second `run` starts from a fresh chain.  Checked against the Python
+    mirror driving the same library with the thermostat constructed from dt = 0.5 fs."""
+    from gpumd_b200 import build, engine
+    from test_gpu_md import run_nve
+    exe = build.build_host()
+    s = rocksalt_pbte(8, rattle=0.02, seed=1)
+    vel = init_velocities(s["mass"], 300.0, seed=42)
+    write_xyz(tmp_path / "model.xyz", s, nep_type_order(GOLDEN / "nep_PbTe.txt"), vel)
+    shutil.copyfile(GOLDEN / "nep_PbTe.txt", tmp_path / "potential.txt")
+    (tmp_path / "run.in").write_text(
+        "potential potential.txt\nensemble nvt_nhc 300 300 100\ntime_step 0.5\ndump_thermo 10\nrun 100\n")
+    r = subprocess.run([str(exe)], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    mine = read_thermo(tmp_path / "thermo.out")
+    _, _, rows = run_nve(engine, s, GOLDEN / "nep_PbTe.txt", 100, 0.5, 300.0, seed=42, every=10,
+                         ensemble="nvt_nhc")
+    ref = rows[1:-1]
+    assert mine.shape[0] == ref.shape[0] == 10
+    # model.xyz carries 17 significant digits, so both runs start from the same state; the same
+    # kernels in the same order give the same trajectory up to the text round trip
+    assert np.allclose(mine[:, 0], ref[:, 0], rtol=1e-7, atol=0)
+    # with the 1 fs default (the bug) T(100 steps) differs in the 4th digit
+    _, _, wrong = run_nve(engine, s, GOLDEN / "nep_PbTe.txt", 100, 0.5, 300.0, seed=42, every=10,
+                          ensemble="nvt_nhc_dt1")
+    assert abs(wrong[-2, 0] - ref[-1, 0]) > 1e-5 * ref[-1, 0]
 
 
 def test_b200md_rejects_unknown_keyword(tmp_path):

@@ -23,6 +23,8 @@ def run_nve(eng, s, pot_file, steps, dt_fs, temperature, seed=42, every=None, en
         ens = eng.Ensemble_BER(n, 300.0, 100.0)
     elif ensemble == "nvt_nhc":
         ens = eng.Ensemble_NHC(n, 300.0, 100.0, dt_fs / TIME_UNIT_CONVERSION)
+    elif ensemble == "nvt_nhc_dt1":  # chain masses from a 1 fs step whatever dt is (a former driver bug)
+        ens = eng.Ensemble_NHC(n, 300.0, 100.0, 1.0 / TIME_UNIT_CONVERSION)
     elif ensemble == "nvt_bdp":
         ens = eng.Ensemble_BDP(n, 300.0, 100.0)
     else:

@@ -11,17 +11,20 @@ from conftest import GOLDEN, TOL, assert_close
 from gpumd_b200.structures import fcc, rocksalt_pbte
 
 
-def check_fv(out, ref, noise=1.0):
+def check_fv(out, ref, noise=1.0, gap_f=0.0, gap_v=0.0):
     """force: rtol 1e-4 + atol 1e-5 eV/A, virial: rtol 1e-4 + atol 2e-5 eV, with the
     atol scaled by the largest component when that exceeds 1 -- FP32 accumulation noise is
     relative to the magnitude of the terms being summed, not to the (possibly cancelling) result.
-    `noise` widens the atol for potentials whose per-pair terms cancel heavily (stated at the call)."""
+    `noise` widens the atol for potentials whose per-pair terms cancel heavily (stated at the call).
+    gap_f / gap_v: the FP32 restatement's own distance from the FP64 truth on this input (max over
+    components); a second FP32 evaluation with a different summation order cannot be expected to
+    sit closer to either of them than they sit to each other, so it is added to the atol."""
     fs = noise * max(1.0, np.abs(ref["force"]).max())
     vs = noise * max(1.0, np.abs(ref["virial"]).max())
     assert_close(out["force"], ref["force"], rtol=TOL["force"]["rtol"],
-                 atol=TOL["force"]["atol"] * fs, what="force")
+                 atol=TOL["force"]["atol"] * fs + gap_f, what="force")
     assert_close(out["virial"], ref["virial"], rtol=TOL["virial"]["rtol"],
-                 atol=TOL["virial"]["atol"] * vs, what="virial")
+                 atol=TOL["virial"]["atol"] * vs + gap_v, what="virial")
 
 
 def check_nep(oracle, dev, model, s, n, energy_tol=None):
@@ -43,9 +46,15 @@ def check_nep(oracle, dev, model, s, n, energy_tol=None):
     gap = abs(r32["pe"].sum() - r64["pe"].sum()) / n
     assert abs(out["pe"].sum() - r32["pe"].sum()) / n < energy_tol
     assert abs(out["pe"].sum() - r64["pe"].sum()) / n < energy_tol + 2 * gap
-    assert_close(out["pe"].sum(), r32["pe"].sum(), **TOL["energy"], what="energy")
-    check_fv(out, r32)
-    check_fv(out, r64)
+    # the reference suite's total-energy tolerance (rtol 1e-5, tests_pytest/conftest.py:51-62) applied to
+    # the magnitude that is being summed: site energies of opposite sign can cancel in the total (the
+    # water fixture: sum |E_i| = 289 eV, E = -1.0 eV), and FP32 noise does not cancel with them
+    e_scale = np.abs(r64["pe"]).sum()
+    assert abs(out["pe"].sum() - r32["pe"].sum()) <= TOL["energy"]["atol"] + TOL["energy"]["rtol"] * e_scale
+    gap_f = np.abs(r32["force"] - r64["force"]).max()
+    gap_v = np.abs(r32["virial"] - r64["virial"]).max()
+    check_fv(out, r32, gap_f=gap_f, gap_v=gap_v)
+    check_fv(out, r64, gap_f=gap_f, gap_v=gap_v)
     return out
 
 
