@@ -77,6 +77,24 @@ def _build_lib(LIB, OBJ, extra, force, verbose):
     return LIB
 
 
+MGPU = PKG / "libb200md_mgpu.so"
+
+
+def build_mgpu(force=False):
+    """The multi-GPU domain module (csrc/b2_mgpu.cu: C++ host + CUDA + NCCL over the libb200md
+    C-ABI) -> gpumd_b200/libb200md_mgpu.so."""
+    nvcc = _nvcc()
+    src = CSRC / "b2_mgpu.cu"
+    deps = [src, PKG.parent / "include" / "b200md.h", PKG.parent / "include" / "b200md_mgpu.h", LIB]
+    if force or _stale(MGPU, deps):
+        cmd = [nvcc] + NVCC_FLAGS + ["-shared", str(src), "-o", str(MGPU), "-L" + str(PKG), "-lb200md",
+                                     "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN", "-lnccl", "-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("mgpu build failed:\n" + r.stdout + r.stderr)
+    return MGPU
+
+
 HOST = PKG / "host"
 EXE = PKG / "b200md"
 
@@ -98,4 +116,5 @@ def build_host(force=False):
 
 if __name__ == "__main__":
     print(build_lib(force="--force" in sys.argv, verbose=True))
+    print(build_mgpu(force="--force" in sys.argv))
     print(build_host(force="--force" in sys.argv))

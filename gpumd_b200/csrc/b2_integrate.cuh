@@ -53,6 +53,35 @@ B2_HD void b2_body_vv(
   }
 }
 
+// The same half step with the reference's group rules (gpu_velocity_verlet with groups,
+// src/integrate/ensemble.cu:111-174): atoms of `fixed_group` do not move and have zero velocity,
+// atoms of `move_group` are translated with the constant velocity mv[] (stored velocity zero, so
+// that they do not enter the temperature); everything else is integrated normally.  label[] is
+// Group::label of the grouping method the fix / move keywords named.
+B2_HD void b2_body_vv_groups(
+  int i, int stride, bool step1, double dt, const double* mass, double* pos, double* vel,
+  const double* f, const int* label, int fixed_group, int move_group, const double* mv)
+{
+  const size_t N = (size_t)stride;
+  const int g = label[i];
+  if (g == fixed_group) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d)
+      vel[d * N + i] = 0.0; // pos += 0 * dt
+    return;
+  }
+  if (g == move_group) {
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+      vel[d * N + i] = 0.0;
+      if (step1)
+        pos[d * N + i] += mv[d] * dt;
+    }
+    return;
+  }
+  b2_body_vv(i, stride, step1, dt, mass, pos, vel, f);
+}
+
 // per-atom contributions to the 8 sums: m v^2, U, W_ab + m v_a v_b (ab = xx,yy,zz,xy,xz,yz)
 B2_HD void b2_thermo_terms(
   int i, int stride, const double* mass, const double* pe, const double* vel, const double* virial,

@@ -63,6 +63,27 @@ __global__ void __launch_bounds__(BLK) k_vv(
     b2_body_vv(i, stride, step1 != 0, dt, mass, pos, vel, f);
 }
 
+__global__ void __launch_bounds__(BLK) k_vv_groups(
+  int n, int stride, int step1, double dt, const double* __restrict__ mass, double* pos,
+  double* vel, const double* __restrict__ f, const int* __restrict__ label, int fixed_group,
+  int move_group, double mvx, double mvy, double mvz)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const double mv[3] = {mvx, mvy, mvz};
+  if (i < n)
+    b2_body_vv_groups(i, stride, step1 != 0, dt, mass, pos, vel, f, label, fixed_group, move_group, mv);
+}
+
+// out[k*n + i] = in[i*mn + k]
+__global__ void __launch_bounds__(BLK) k_transpose_int(int n, int mn, const int* __restrict__ in, int* out)
+{
+  const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < (size_t)n * mn) {
+    const int k = (int)(e / n), i = (int)(e - (size_t)k * n);
+    out[e] = in[(size_t)i * mn + k];
+  }
+}
+
 // halo pack: out[d*m + k] = pos[d*stride + idx[k]] + shift[d]  (ghost positions for a neighbour
 // domain; the shift carries the periodic image / local-frame offset)
 __global__ void __launch_bounds__(BLK) k_halo_pack(
@@ -462,6 +483,33 @@ int b200md_velocity_verlet(
 {
   return b200md_velocity_verlet_strided(
     is_step1, n, n, time_step, d_mass, d_position, d_velocity, d_force, stream);
+}
+
+int b200md_transpose_int(int n, int mn, const int* d_row_major, int* d_column_major, void* stream)
+{
+  if (n <= 0 || mn <= 0)
+    return B200MD_OK;
+  k_transpose_int<<<grid_for((long long)n * mn, BLK), BLK, 0, (cudaStream_t)stream>>>(
+    n, mn, d_row_major, d_column_major);
+  B2_LAUNCHED();
+  return B200MD_OK;
+}
+
+int b200md_velocity_verlet_groups(
+  int is_step1, int n, int stride, double time_step, const double* d_mass, double* d_position,
+  double* d_velocity, const double* d_force, const int* d_group_label, int fixed_group,
+  int move_group, const double move_velocity[3], void* stream)
+{
+  if (!d_group_label || (fixed_group < 0 && move_group < 0))
+    return b200md_velocity_verlet_strided(
+      is_step1, n, stride, time_step, d_mass, d_position, d_velocity, d_force, stream);
+  const double z[3] = {0.0, 0.0, 0.0};
+  const double* mv = move_velocity ? move_velocity : z;
+  k_vv_groups<<<grid_for(n, BLK), BLK, 0, (cudaStream_t)stream>>>(
+    n, stride, is_step1, time_step, d_mass, d_position, d_velocity, d_force, d_group_label,
+    fixed_group, move_group, mv[0], mv[1], mv[2]);
+  B2_LAUNCHED();
+  return B200MD_OK;
 }
 
 int b200md_halo_pack(

@@ -400,15 +400,17 @@ int dispatch_force_final(
     const int g = grid_for(p->n, BLK);
     const int4* p0 = p->nb.plane0.p;
     const int4* p1 = p->nb.plane1.p;
-    // B200MD_NEP_VARIANT: resident blocks per SM the register allocation targets (A/B runs)
+    // B200MD_NEP_VARIANT: resident blocks per SM the register allocation targets.  Measured on
+    // 1 M-atom PbTe (profiles/r02_c_*): 5 blocks / 96 regs 0.927 ms (default), 6 blocks / 80 regs
+    // with spills 1.03 ms, 4 blocks / 128 regs 0.959 ms
 #define B2_FF2(NT_, ORTHO_)                                                                      \
   do {                                                                                           \
     if (p->variant == 1)                                                                         \
-      k_force_final2<NT_, K1, ORTHO_, 5><<<g, BLK, 0, st>>>(p->view, p0, p1, box, pe, f, v);     \
+      k_force_final2<NT_, K1, ORTHO_, 6><<<g, BLK, 0, st>>>(p->view, p0, p1, box, pe, f, v);     \
     else if (p->variant == 2)                                                                    \
       k_force_final2<NT_, K1, ORTHO_, 4><<<g, BLK, 0, st>>>(p->view, p0, p1, box, pe, f, v);     \
     else                                                                                         \
-      k_force_final2<NT_, K1, ORTHO_, 6><<<g, BLK, 0, st>>>(p->view, p0, p1, box, pe, f, v);     \
+      k_force_final2<NT_, K1, ORTHO_, 5><<<g, BLK, 0, st>>>(p->view, p0, p1, box, pe, f, v);     \
   } while (0)
     if (p->model.nt == 1 && box.ortho)
       B2_FF2(1, true);

@@ -335,24 +335,48 @@ class Ensemble_NVE:
         nbytes = self._L.b200md_thermo_scratch_bytes(int(num_atoms))
         self._scratch = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
 
+    # `fix` / `move` keywords (integrate.cu:1362-1470): label = Group::label of the grouping method
+    fixed_group = -1
+    move_group = -1
+
+    def set_groups(self, label, fixed_group=-1, move_group=-1, move_velocity=(0.0, 0.0, 0.0)):
+        """label: int32 group label per atom (host array or device tensor).  Atoms of fixed_group stay
+        put, atoms of move_group translate with move_velocity (natural units); neither enters the
+        temperature (ensemble.cu:111-174, 645-651)."""
+        lab = torch.as_tensor(np.ascontiguousarray(label, dtype=np.int32)) if not torch.is_tensor(label) else label
+        self._label = lab.to(device="cuda", dtype=torch.int32).contiguous()
+        self.fixed_group, self.move_group = int(fixed_group), int(move_group)
+        self._move_velocity = (C.c_double * 3)(*[float(v) for v in move_velocity])
+        excluded = 0
+        for g in (self.fixed_group, self.move_group):
+            if g >= 0:
+                excluded += int((self._label == g).sum().item())
+        self._n_excluded = excluded
+
+    def _vv(self, step1, time_step, atom):
+        n = atom.number_of_atoms
+        if self.fixed_group < 0 and self.move_group < 0:
+            _lib.check(self._L.b200md_velocity_verlet(
+                step1, n, float(time_step), _ptr(atom.mass), _ptr(atom.position_per_atom),
+                _ptr(atom.velocity_per_atom), _ptr(atom.force_per_atom), _stream()))
+        else:
+            _lib.check(self._L.b200md_velocity_verlet_groups(
+                step1, n, n, float(time_step), _ptr(atom.mass), _ptr(atom.position_per_atom),
+                _ptr(atom.velocity_per_atom), _ptr(atom.force_per_atom), _ptr(self._label),
+                self.fixed_group, self.move_group, self._move_velocity, _stream()))
+
     def compute1(self, time_step, box, atom, thermo=None):
-        _lib.check(self._L.b200md_velocity_verlet(
-            1, atom.number_of_atoms, float(time_step), _ptr(atom.mass),
-            _ptr(atom.position_per_atom), _ptr(atom.velocity_per_atom), _ptr(atom.force_per_atom),
-            _stream()))
+        self._vv(1, time_step, atom)
 
     def compute2(self, time_step, box, atom, thermo):
-        n = atom.number_of_atoms
-        st = _stream()
-        _lib.check(self._L.b200md_velocity_verlet(
-            0, n, float(time_step), _ptr(atom.mass), _ptr(atom.position_per_atom),
-            _ptr(atom.velocity_per_atom), _ptr(atom.force_per_atom), st))
+        self._vv(0, time_step, atom)
         self.find_thermo(box.get_volume(), atom, thermo)
 
     def find_thermo(self, volume, atom, thermo):
         n = atom.number_of_atoms
+        n_t = n - getattr(self, "_n_excluded", 0)  # ensemble.cu:645-651
         _lib.check(self._L.b200md_find_thermo(
-            n, n, float(volume), _ptr(atom.mass), _ptr(atom.potential_per_atom),
+            n, n_t, float(volume), _ptr(atom.mass), _ptr(atom.potential_per_atom),
             _ptr(atom.velocity_per_atom), _ptr(atom.virial_per_atom), _ptr(thermo),
             _ptr(self._scratch), _stream()))
 
@@ -424,10 +448,7 @@ class Ensemble_NHC(Ensemble_NVE):
         super().compute1(time_step, box, atom, thermo)
 
     def compute2(self, time_step, box, atom, thermo):
-        n = atom.number_of_atoms
-        _lib.check(self._L.b200md_velocity_verlet(
-            0, n, float(time_step), _ptr(atom.mass), _ptr(atom.position_per_atom),
-            _ptr(atom.velocity_per_atom), _ptr(atom.force_per_atom), _stream()))
+        self._vv(0, time_step, atom)
         self._thermostat(time_step, box, atom, thermo)
 
 

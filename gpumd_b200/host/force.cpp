@@ -39,7 +39,7 @@ void Force::compute(
 {
   const int n = (int)type.size();
   int pbc[3];
-  box.pbc(pbc);
+  b2h_pbc(box, pbc);
   if (b200md_apply_pbc(n, box.cpu_h, pbc, position_per_atom.data(), nullptr) != B200MD_OK)
     b2h_fail("Force::compute (apply_pbc)");
   if (b200md_zero_properties(

@@ -27,6 +27,11 @@ public:
   explicit GPU_Vector(size_t n) { resize(n); }
   GPU_Vector(const GPU_Vector&) = delete;
   GPU_Vector& operator=(const GPU_Vector&) = delete;
+  GPU_Vector(GPU_Vector&& o) noexcept : data_(o.data_), size_(o.size_)
+  {
+    o.data_ = nullptr;
+    o.size_ = 0;
+  }
   ~GPU_Vector() { release(); }
 
   void resize(size_t n)

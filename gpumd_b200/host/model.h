@@ -28,8 +28,10 @@ public:
 class Group
 {
 public:
-  int number = 0;
-  std::vector<int> cpu_size;
+  int number = 0;             // number of groups of this grouping method
+  std::vector<int> cpu_label; // group label of every atom (group.cuh:25)
+  std::vector<int> cpu_size;  // atoms per group
+  GPU_Vector<int> label;      // device copy of cpu_label
 };
 
 class Atom

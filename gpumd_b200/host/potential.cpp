@@ -16,6 +16,8 @@ NEP_B200::NEP_B200(const char* file_potential, const int num_atoms)
     b2h_fail("NEP_B200");
   N1 = 0;
   N2 = num_atoms;
+  num_atoms_ = num_atoms;
+  nep_model_type = 0; // "potential" model (potential.cuh:33-34)
   rc = b200md_nep_rc(handle_);
   printf("Use the b200md NEP backend with %d atom type(s), D = %d, %d neurons.\n",
          b200md_nep_info(handle_, 0), b200md_nep_info(handle_, 1), b200md_nep_info(handle_, 2));
@@ -28,16 +30,47 @@ void NEP_B200::compute(
   GPU_Vector<double>& potential, GPU_Vector<double>& force, GPU_Vector<double>& virial)
 {
   int pbc[3];
-  box.pbc(pbc);
+  b2h_pbc(box, pbc);
   // legacy default stream, like every reference kernel
   if (b200md_nep_compute(
         handle_, (int)type.size(), box.cpu_h, pbc, type.data(), position.data(), potential.data(),
         force.data(), virial.data(), nullptr) != B200MD_OK)
     b2h_fail("NEP_B200::compute");
+  lists_current_ = false;
   // the reference looks at its neighbour counts every 1000 calls (nep.cu:1014-1034); same cadence
   // for the latched capacity check, which needs a synchronisation
   if (++num_calls_ % 1000 == 1)
     check();
+}
+
+void NEP_B200::export_radial()
+{
+  if (lists_current_)
+    return;
+  const int n = num_atoms_, mn = b200md_nep_info(handle_, 3);
+  if ((int)NN_radial_.size() != n) {
+    NN_radial_.resize(n);
+    NL_radial_.resize((size_t)n * mn);
+    row_major_.resize((size_t)n * mn);
+  }
+  // the C-ABI exports row-major rows in caller indices; the reference layout is column-major
+  if (b200md_nep_export_neighbors(
+        handle_, mn, NN_radial_.data(), row_major_.data(), 0, nullptr, nullptr, nullptr) != B200MD_OK ||
+      b200md_transpose_int(n, mn, row_major_.data(), NL_radial_.data(), nullptr) != B200MD_OK)
+    b2h_fail("NEP_B200::export_radial");
+  lists_current_ = true;
+}
+
+const GPU_Vector<int>& NEP_B200::get_NN_radial_ptr()
+{
+  export_radial();
+  return NN_radial_;
+}
+
+const GPU_Vector<int>& NEP_B200::get_NL_radial_ptr()
+{
+  export_radial();
+  return NL_radial_;
 }
 
 int NEP_B200::type_of(const std::string& symbol) const
@@ -71,7 +104,7 @@ void LJ_B200::compute(
   GPU_Vector<double>& potential, GPU_Vector<double>& force, GPU_Vector<double>& virial)
 {
   int pbc[3];
-  box.pbc(pbc);
+  b2h_pbc(box, pbc);
   if (b200md_lj_compute(
         handle_, (int)type.size(), box.cpu_h, pbc, type.data(), position.data(), potential.data(),
         force.data(), virial.data(), nullptr) != B200MD_OK)
@@ -109,7 +142,7 @@ void Tersoff1989_B200::compute(
   GPU_Vector<double>& potential, GPU_Vector<double>& force, GPU_Vector<double>& virial)
 {
   int pbc[3];
-  box.pbc(pbc);
+  b2h_pbc(box, pbc);
   if (b200md_tersoff_compute(
         handle_, (int)type.size(), box.cpu_h, pbc, type.data(), position.data(), potential.data(),
         force.data(), virial.data(), nullptr) != B200MD_OK)
@@ -147,7 +180,7 @@ void EAM_B200::compute(
   GPU_Vector<double>& potential, GPU_Vector<double>& force, GPU_Vector<double>& virial)
 {
   int pbc[3];
-  box.pbc(pbc);
+  b2h_pbc(box, pbc);
   if (b200md_eam_compute(
         handle_, (int)type.size(), box.cpu_h, pbc, type.data(), position.data(), potential.data(),
         force.data(), virial.data(), nullptr) != B200MD_OK)

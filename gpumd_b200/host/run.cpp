@@ -73,6 +73,7 @@ static std::string header_value(const std::string& line, const std::string& key)
 struct Model {
   Box box;
   Atom atom;
+  std::vector<Group> group; // one entry per grouping method of model.xyz (group:I:k)
   bool has_velocity = false;
 };
 
@@ -113,7 +114,7 @@ static void read_model(const char* path, Model& m)
   std::string props = lower(header_value(line, "properties"));
   if (props.empty())
     props = "species:s:1:pos:r:3";
-  int off_species = -1, off_pos = -1, off_mass = -1, off_vel = -1, col = 0;
+  int off_species = -1, off_pos = -1, off_mass = -1, off_vel = -1, off_group = -1, num_group = 0, col = 0;
   {
     std::istringstream ss(props);
     std::string name, kind, width;
@@ -127,6 +128,10 @@ static void read_model(const char* path, Model& m)
         off_mass = col;
       else if (name == "vel")
         off_vel = col;
+      else if (name == "group") { // group:I:k = k grouping methods (read_xyz.cu:271-287)
+        off_group = col;
+        num_group = w;
+      }
       col += w;
     }
   }
@@ -139,6 +144,9 @@ static void read_model(const char* path, Model& m)
   a.cpu_position_per_atom.resize((size_t)3 * N);
   a.cpu_velocity_per_atom.assign((size_t)3 * N, 0.0);
   m.has_velocity = off_vel >= 0;
+  m.group.resize(num_group);
+  for (Group& g : m.group)
+    g.cpu_label.assign(N, 0);
   for (int n = 0; n < N; ++n) {
     if (!std::getline(in, line))
       input_error("model.xyz ended early.");
@@ -162,6 +170,21 @@ static void read_model(const char* path, Model& m)
       for (int d = 0; d < 3; ++d) // A/fs -> natural units (read_xyz.cu:380-387)
         a.cpu_velocity_per_atom[n + (size_t)N * d] =
           std::atof(tok[off_vel + d].c_str()) * TIME_UNIT_CONVERSION;
+    for (int g = 0; g < num_group; ++g) { // read_xyz.cu:389-398
+      const int label = std::atoi(tok[off_group + g].c_str());
+      if (label < 0 || label >= N)
+        input_error("Group label should >= 0 and < N.");
+      m.group[g].cpu_label[n] = label;
+      if (label + 1 > m.group[g].number)
+        m.group[g].number = label + 1;
+    }
+  }
+  for (Group& g : m.group) {
+    g.cpu_size.assign(g.number, 0);
+    for (int n = 0; n < N; ++n)
+      g.cpu_size[g.cpu_label[n]]++;
+    g.label.resize(N);
+    g.label.copy_from_host(g.cpu_label.data());
   }
 }
 
@@ -285,7 +308,10 @@ private:
     unsigned seed = 0;
   } ensemble_spec_;
   GPU_Vector<double> thermo_;
-  std::vector<Group> group_;
+  // `fix [method] group` / `move [method] group vx vy vz` (integrate.cu:1362-1470); both are reset
+  // after every run like the reference's Integrate::finalize (integrate.cu:284-290)
+  int fixed_group_ = -1, move_group_ = -1, fixed_method_ = 0, move_method_ = 0;
+  double move_velocity_[3] = {0.0, 0.0, 0.0};
   double time_step_ = 1.0 / TIME_UNIT_CONVERSION;
   int dump_thermo_ = 0;
   int dump_restart_ = 0;
@@ -393,6 +419,33 @@ private:
                     "by the b200md backend.");
       }
       ensemble_spec_ = e;
+    } else if (t[0] == "fix") {
+      // fix group_id | fix grouping_method group_id
+      if (t.size() != 2 && t.size() != 3)
+        input_error("Keyword fix should have 1 or 2 parameters.");
+      fixed_method_ = t.size() == 3 ? std::atoi(t[1].c_str()) : 0;
+      fixed_group_ = std::atoi(t[t.size() - 1].c_str());
+      if (fixed_method_ < 0 || fixed_method_ >= (int)model_.group.size())
+        input_error("Grouping method for fix is out of range (does model.xyz have a group column?).");
+      if (fixed_group_ < 0 || fixed_group_ >= model_.group[fixed_method_].number)
+        input_error("Group ID for fix is out of range.");
+      printf("Group %d in grouping method %d will be fixed.\n", fixed_group_, fixed_method_);
+    } else if (t[0] == "move") {
+      // move group_id vx vy vz | move grouping_method group_id vx vy vz   (velocities in A/fs)
+      if (t.size() != 5 && t.size() != 6)
+        input_error("Keyword move should have 4 or 5 parameters.");
+      const size_t o = t.size() - 4;
+      move_method_ = t.size() == 6 ? std::atoi(t[1].c_str()) : 0;
+      move_group_ = std::atoi(t[o].c_str());
+      if (move_method_ < 0 || move_method_ >= (int)model_.group.size())
+        input_error("Grouping method for move is out of range.");
+      if (move_group_ < 0 || move_group_ >= model_.group[move_method_].number)
+        input_error("Group ID for move is out of range.");
+      for (int d = 0; d < 3; ++d)
+        move_velocity_[d] = std::atof(t[o + 1 + d].c_str()) * TIME_UNIT_CONVERSION;
+      printf("Group %d in grouping method %d will move at (%g, %g, %g) A/fs.\n", move_group_,
+             move_method_, move_velocity_[0] / TIME_UNIT_CONVERSION,
+             move_velocity_[1] / TIME_UNIT_CONVERSION, move_velocity_[2] / TIME_UNIT_CONVERSION);
     } else if (t[0] == "time_step") {
       if (t.size() < 2)
         input_error("time_step should have at least 1 parameter.");
@@ -415,6 +468,8 @@ private:
       if (t.size() != 2 || std::atoi(t[1].c_str()) < 0)
         input_error("run should have 1 parameter (the number of steps).");
       perform_a_run(std::atoi(t[1].c_str()));
+      fixed_group_ = move_group_ = -1;
+      fixed_method_ = move_method_ = 0;
       dump_thermo_ = 0; // non-propagating keywords are reset after each run (run.cu:329-340)
       dump_restart_ = 0;
       dump_xyz_ = XyzDump();
@@ -634,10 +689,21 @@ private:
     Atom& a = model_.atom;
     { // Integrate::initialize: a fresh ensemble object per run, from the CURRENT time step
       const EnsembleSpec& e = ensemble_spec_;
+      if (move_group_ >= 0) { // integrate.cu:59-73
+        if (fixed_group_ < 0)
+          input_error("It is not allowed to have moving group but no fixed group.");
+        if (fixed_method_ != move_method_)
+          input_error("The fixed and moving groups must use the same grouping method.");
+        if (move_group_ == fixed_group_)
+          input_error("The fixed and moving groups cannot be the same.");
+        if (e.type != 1 && e.type != 2 && e.type != 4)
+          input_error("It is only allowed to use nvt_ber, nvt_nhc, or nvt_bdp with a moving group.");
+      }
+      const int N = a.number_of_atoms;
       if (e.type == 0) {
         ensemble_.reset(new Ensemble_NVE_B200(0));
       } else if (e.type == 1) {
-        ensemble_.reset(new Ensemble_BER_B200(1, e.T, e.Tc));
+        ensemble_.reset(new Ensemble_BER_B200(1, move_group_, move_velocity_, e.T, e.Tc));
       } else if (e.type == 4) {
         // the reference seeds std::mt19937 with 12345678 under -DDEBUG and from the clock otherwise
         // (ensemble_bdp.cu:31-37); B200MD_DEBUG_SEED=1 selects the former for trajectory parity
@@ -646,10 +712,13 @@ private:
           seed = std::getenv("B200MD_DEBUG_SEED")
                    ? 12345678u
                    : (unsigned)std::chrono::system_clock::now().time_since_epoch().count();
-        ensemble_.reset(new Ensemble_BDP_B200(4, a.number_of_atoms, e.T, e.Tc, seed));
+        ensemble_.reset(new Ensemble_BDP_B200(4, move_group_, move_velocity_, N, e.T, e.Tc, seed));
       } else {
-        ensemble_.reset(new Ensemble_NHC_B200(2, a.number_of_atoms, e.T, e.Tc, time_step_));
+        ensemble_.reset(new Ensemble_NHC_B200(2, move_group_, move_velocity_, N, e.T, e.Tc, time_step_));
       }
+      ensemble_->fixed_group = fixed_group_; // integrate.cu:279-281
+      ensemble_->fixed_grouping_method = fixed_method_;
+      ensemble_->move_grouping_method = move_method_;
     }
     if (!state_on_gpu_)
       upload_state();
@@ -667,10 +736,10 @@ private:
     printf("Run %d steps.\n", number_of_steps);
     const auto t0 = std::chrono::high_resolution_clock::now();
     for (int step = 0; step < number_of_steps; ++step) {
-      ensemble_->compute1(time_step_, group_, model_.box, a, thermo_);
+      ensemble_->compute1(time_step_, model_.group, model_.box, a, thermo_);
       force_.compute(model_.box, a.position_per_atom, a.type, a.potential_per_atom, a.force_per_atom,
                      a.virial_per_atom);
-      ensemble_->compute2(time_step_, group_, model_.box, a, thermo_);
+      ensemble_->compute2(time_step_, model_.group, model_.box, a, thermo_);
       ++global_step_;
       global_time_ += time_step_;
       if (fid && (step + 1) % dump_thermo_ == 0)

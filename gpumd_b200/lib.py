@@ -28,6 +28,7 @@ SIGNATURES = {
     "b200md_nep_compute": (C.c_int, [_vp, C.c_int, _dp, _ip, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200md_nep_compute_host": (C.c_int, [_vp, C.c_int, _dp, _ip, _vp, _vp, _vp, _vp, _vp]),
     "b200md_nep_export_neighbors": (C.c_int, [_vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, _vp]),
+    "b200md_transpose_int": (C.c_int, [C.c_int, C.c_int, _vp, _vp, _vp]),
     "b200md_nep_export_descriptors": (C.c_int, [_vp, _vp, _vp]),
     "b200md_nep_check": (C.c_int, [_vp, _vp]),
     "b200md_nep_profile": (C.c_int, [_vp, C.c_int]),
@@ -62,6 +63,8 @@ SIGNATURES = {
     "b200md_apply_pbc": (C.c_int, [C.c_int, _dp, _ip, _vp, _vp]),
     "b200md_zero_properties": (C.c_int, [C.c_int, _vp, _vp, _vp, _vp]),
     "b200md_velocity_verlet": (C.c_int, [C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp]),
+    "b200md_velocity_verlet_groups": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp,
+                                                C.c_int, C.c_int, _dp, _vp]),
     "b200md_thermo_scratch_bytes": (C.c_longlong, [C.c_int]),
     "b200md_find_thermo": (C.c_int, [C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200md_scale_velocity": (C.c_int, [C.c_int, C.c_double, _vp, _vp]),

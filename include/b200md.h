@@ -72,6 +72,9 @@ int b200md_nep_compute_host(
 int b200md_nep_export_neighbors(
   b200md_nep* p, int mn_r, int* d_NN_r, int* d_NL_r, int mn_a, int* d_NN_a, int* d_NL_a,
   void* stream);
+/* Row-major rows NL[i*mn + k] -> the reference's column-major layout NL[k*n + i]
+ * (NEP::get_NL_radial_ptr, nep.cuh:100-101 / potential.cuh:66-77).  Device pointers. */
+int b200md_transpose_int(int n, int mn, const int* d_row_major, int* d_column_major, void* stream);
 /* Parity hook: scaled descriptors q[d*N + i] (caller order) of the last compute call. */
 int b200md_nep_export_descriptors(b200md_nep* p, float* d_q, void* stream);
 
@@ -162,7 +165,13 @@ int b200md_zero_properties(
 /* ------------------------------------------------------------------------------------------
  * Integrator kernels behind Ensemble::compute1 / compute2 (src/integrate/ensemble.cuh:26-157):
  *   b200md_velocity_verlet <- Ensemble::velocity_verlet / gpu_velocity_verlet,
- *                             ensemble.cu:176-214,348-397 (no fixed/move groups)
+ *                             ensemble.cu:176-214,348-397 (the variant without groups)
+ *   b200md_velocity_verlet_groups <- the variant with `fix` / `move` groups, ensemble.cu:111-174,
+ *                             369-391: d_group_label = Group::label of the fixed grouping method
+ *                             (device, n ints), fixed_group / move_group = -1 when unused,
+ *                             move_velocity in natural units.  Atoms of either group keep zero
+ *                             velocity; pass n_temperature = n - |fixed| - |move| to
+ *                             b200md_find_thermo (ensemble.cu:645-651).
  *   b200md_find_thermo     <- Ensemble::find_thermo / gpu_find_thermo_instant_temperature,
  *                             ensemble.cu:434-673: d_thermo[0..7] = T,U,sxx,syy,szz,sxy,sxz,syz
  *   b200md_scale_velocity  <- Ensemble::scale_velocity_global, ensemble.cu:676-698
@@ -172,6 +181,10 @@ int b200md_zero_properties(
 int b200md_velocity_verlet(
   int is_step1, int n, double time_step, const double* d_mass, double* d_position,
   double* d_velocity, const double* d_force, void* stream);
+int b200md_velocity_verlet_groups(
+  int is_step1, int n, int stride, double time_step, const double* d_mass, double* d_position,
+  double* d_velocity, const double* d_force, const int* d_group_label, int fixed_group,
+  int move_group, const double move_velocity[3], void* stream);
 long long b200md_thermo_scratch_bytes(int n);
 int b200md_find_thermo(
   int n, int n_temperature, double volume, const double* d_mass, const double* d_potential,

@@ -150,6 +150,33 @@ void oracle_velocity_verlet(
   }
 }
 
+/* gpu_velocity_verlet with fixed / moving groups, src/integrate/ensemble.cu:111-174 */
+void oracle_velocity_verlet_groups(
+  int is_step1, int N, double dt, const double* mass, double* pos, double* vel, const double* f,
+  const int* label, int fixed_group, int move_group, const double* move_velocity)
+{
+  const double half = dt * 0.5;
+  for (int i = 0; i < N; ++i) {
+    const double minv = 1.0 / mass[i];
+    for (int d = 0; d < 3; ++d) {
+      double v = vel[(size_t)d * N + i];
+      const double a = f[(size_t)d * N + i] * minv;
+      if (label[i] == fixed_group) {
+        v = 0.0;
+        vel[(size_t)d * N + i] = 0.0;
+      } else if (label[i] == move_group) {
+        v = move_velocity[d];
+        vel[(size_t)d * N + i] = 0.0;
+      } else {
+        v = fma(a, half, v);
+        vel[(size_t)d * N + i] = v;
+      }
+      if (is_step1)
+        pos[(size_t)d * N + i] = fma(v, dt, pos[(size_t)d * N + i]);
+    }
+  }
+}
+
 void oracle_find_thermo(
   int N, int N_temperature, double volume, const double* mass, const double* pe,
   const double* vel, const double* virial, double* t)

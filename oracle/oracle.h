@@ -84,6 +84,12 @@ void oracle_velocity_verlet(
   int is_step1, int N, double dt, const double* mass, double* position, double* velocity,
   const double* force);
 
+/* gpu_velocity_verlet with `fix` / `move` groups, src/integrate/ensemble.cu:111-174. */
+void oracle_velocity_verlet_groups(
+  int is_step1, int N, double dt, const double* mass, double* position, double* velocity,
+  const double* force, const int* group_label, int fixed_group, int move_group,
+  const double* move_velocity);
+
 /* gpu_find_thermo_instant_temperature, src/integrate/ensemble.cu:434-633:
  * thermo[0..7] = T, U, sxx, syy, szz, sxy, sxz, syz. */
 void oracle_find_thermo(

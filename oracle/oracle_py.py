@@ -58,6 +58,8 @@ def lib():
         L.oracle_compute_heat.argtypes = [C.c_int, _dp, _dp, _dp]
         L.oracle_apply_pbc.argtypes = [C.c_int, _dp, _ip, _dp]
         L.oracle_velocity_verlet.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp]
+        L.oracle_velocity_verlet_groups.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _ip,
+                                                    C.c_int, C.c_int, _dp]
         L.oracle_find_thermo.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp]
         _LIB = L
     return _LIB
@@ -223,6 +225,20 @@ def velocity_verlet(step1, dt, mass, pos, vel, force):
     f = np.ascontiguousarray(force, dtype=np.float64).reshape(3 * n)
     m = np.ascontiguousarray(mass, dtype=np.float64)
     L.oracle_velocity_verlet(int(step1), n, float(dt), _d(m), _d(p), _d(v), _d(f))
+    return p.reshape(3, n), v.reshape(3, n)
+
+
+def velocity_verlet_groups(step1, dt, mass, pos, vel, force, label, fixed_group, move_group, move_velocity):
+    L = lib()
+    n = mass.shape[0]
+    p = np.ascontiguousarray(pos, dtype=np.float64).reshape(3 * n).copy()
+    v = np.ascontiguousarray(vel, dtype=np.float64).reshape(3 * n).copy()
+    f = np.ascontiguousarray(force, dtype=np.float64).reshape(3 * n)
+    m = np.ascontiguousarray(mass, dtype=np.float64)
+    lab = np.ascontiguousarray(label, dtype=np.int32)
+    mv = np.ascontiguousarray(move_velocity, dtype=np.float64)
+    L.oracle_velocity_verlet_groups(int(step1), n, float(dt), _d(m), _d(p), _d(v), _d(f), _i(lab),
+                                    int(fixed_group), int(move_group), _d(mv))
     return p.reshape(3, n), v.reshape(3, n)
 
 

@@ -692,6 +692,13 @@ void emu_velocity_verlet(
   for (int i = 0; i < n; ++i)
     b2_body_vv(i, n, step1 != 0, dt, mass, pos, vel, f); // stride = n
 }
+void emu_velocity_verlet_groups(
+  int step1, int n, double dt, const double* mass, double* pos, double* vel, const double* f,
+  const int* label, int fixed_group, int move_group, const double* mv)
+{
+  for (int i = 0; i < n; ++i)
+    b2_body_vv_groups(i, n, step1 != 0, dt, mass, pos, vel, f, label, fixed_group, move_group, mv);
+}
 void emu_find_thermo(
   int n, int n_temp, double volume, const double* mass, const double* pe, const double* vel,
   const double* virial, double* thermo)

@@ -160,6 +160,8 @@ class Emu:
         E.emu_compute_heat.argtypes = [C.c_int, _dp, _dp, _dp]
         E.emu_apply_pbc.argtypes = [C.c_int, _dp, _ip, _dp]
         E.emu_velocity_verlet.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp]
+        E.emu_velocity_verlet_groups.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _ip,
+                                                 C.c_int, C.c_int, _dp]
         E.emu_find_thermo.argtypes = [C.c_int, C.c_int, C.c_double, _dp, _dp, _dp, _dp, _dp]
         E.emu_bdp_create.restype = C.c_void_p
         E.emu_bdp_create.argtypes = [C.c_uint]
@@ -203,6 +205,17 @@ class Emu:
         f = np.ascontiguousarray(force, np.float64).reshape(-1)
         self.E.emu_velocity_verlet(int(step1), n, float(dt), _d(np.ascontiguousarray(mass)), _d(p),
                                    _d(v), _d(f))
+        return p.reshape(3, n), v.reshape(3, n)
+
+    def velocity_verlet_groups(self, step1, dt, mass, pos, vel, force, label, fixed_group, move_group, mv):
+        n = mass.shape[0]
+        p = np.ascontiguousarray(pos, np.float64).reshape(-1).copy()
+        v = np.ascontiguousarray(vel, np.float64).reshape(-1).copy()
+        f = np.ascontiguousarray(force, np.float64).reshape(-1)
+        self.E.emu_velocity_verlet_groups(
+            int(step1), n, float(dt), _d(np.ascontiguousarray(mass)), _d(p), _d(v), _d(f),
+            _i(np.ascontiguousarray(label, np.int32)), int(fixed_group), int(move_group),
+            _d(np.ascontiguousarray(mv, np.float64)))
         return p.reshape(3, n), v.reshape(3, n)
 
     def find_thermo(self, n_temp, volume, mass, pe, vel, virial):

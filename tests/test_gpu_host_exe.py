@@ -194,9 +194,19 @@ def test_b200md_reproduces_the_references_carbon_golden(tmp_path):
     # same thermodynamic state within finite-size fluctuations (1/sqrt(N) = 0.4 %).
     e_mine = mine[:, 1] + mine[:, 2]
     e_ref = ref[:, 1] + ref[:, 2]
-    assert np.all(np.abs(e_mine - e_ref) / n < 5e-6), np.abs(e_mine - e_ref).max() / n
-    assert np.all(np.abs(e_mine - e_mine[0]) / n < 5e-6)          # NVE conservation (the golden's own
-    #                                                               rows wander by 1.6e-6 eV/atom)
+    # NVE conservation.  The total energy does not drift here, it WANDERS by ~1e-6 eV/atom from
+    # output to output: FP32 force noise.  Measured on one B200 from identical positions and
+    # velocities (scripts/diag_r02.py, profiles/r02_diag_carbon.json), deviation from the first
+    # row in ueV/atom over the 10 rows: this library rms 0.85 / max 2.08 (bit-identical with the
+    # SIMT or the tensor-core hidden layer, with rsqrtf or the exact 1/sqrt, +-0.02 with the round-1
+    # kernels -- so neither 3xTF32 nor rsqrt is the cause); the unmodified reference gpumd rms 0.68 /
+    # max 1.29; the checked-in golden itself rms 0.93 / max 1.99.  Three samples of the same noise.
+    # Bounds: rms and extreme within 2x of the golden's own (3.98e-6 eV/atom; round 1 asserted 5e-6).
+    w_mine, w_ref = (e_mine - e_mine[0]) / n, (e_ref - e_ref[0]) / n
+    assert np.sqrt(np.mean(w_mine ** 2)) < 2.0 * np.sqrt(np.mean(w_ref ** 2)), (w_mine, w_ref)
+    assert np.abs(w_mine).max() < 2.0 * np.abs(w_ref).max(), (w_mine, w_ref)
+    # same conserved energy as the golden (same positions, KE scaled to exactly 300 K)
+    assert np.all(np.abs(e_mine - e_ref) / n < 4e-6), np.abs(e_mine - e_ref).max() / n
     assert np.all(np.abs(mine[:, 0] - ref[:, 0]) < 1.5)            # T, K
     assert np.all(np.abs(mine[:, 2] - ref[:, 2]) / n < 3e-4)       # PE, eV/atom
     assert np.allclose(mine[:, 3:6], ref[:, 3:6], rtol=0, atol=0.3)   # diagonal stress, GPa (row noise 0.1)

@@ -265,6 +265,26 @@ def test_integrator_kernels(oracle, eng):
     atom.velocity_per_atom.copy_(torch.as_tensor(v1.reshape(-1)))
     ens.compute2(0.098, box, atom, thermo)
     assert np.array_equal(a, thermo.cpu().numpy())  # deterministic reduction order
+    # `fix` / `move` groups (ensemble.cu:111-174, 645-651): bit for bit against the restatement, and
+    # the temperature counts only the atoms that are integrated
+    label = rng.integers(0, 4, n).astype(np.int32)
+    mv = np.array([0.3, -0.2, 0.1])
+    atom = eng.Atom(np.zeros(n, np.int32), pos, mass, vel)
+    atom.force_per_atom.copy_(torch.as_tensor(f.reshape(-1)))
+    atom.potential_per_atom.copy_(torch.as_tensor(pe))
+    atom.virial_per_atom.copy_(torch.as_tensor(vir.reshape(-1)))
+    ens = eng.Ensemble_NVE(n)
+    ens.set_groups(label, fixed_group=1, move_group=2, move_velocity=mv)
+    ens.compute1(0.098, box, atom)
+    p1, v1 = oracle.velocity_verlet_groups(True, 0.098, mass, pos, vel, f, label, 1, 2, mv)
+    assert np.array_equal(atom.position_per_atom.cpu().numpy().reshape(3, n), p1)
+    assert np.array_equal(atom.velocity_per_atom.cpu().numpy().reshape(3, n), v1)
+    ens.compute2(0.098, box, atom, thermo)
+    p2, v2 = oracle.velocity_verlet_groups(False, 0.098, mass, p1, v1, f, label, 1, 2, mv)
+    assert np.array_equal(atom.velocity_per_atom.cpu().numpy().reshape(3, n), v2)
+    n_t = n - int(((label == 1) | (label == 2)).sum())
+    want = oracle.find_thermo(n_t, box.get_volume(), mass, pe, v2, vir)
+    assert np.allclose(thermo.cpu().numpy(), want, rtol=1e-12, atol=1e-9)
 
 
 @pytest.mark.parametrize("two_types", [False, True])

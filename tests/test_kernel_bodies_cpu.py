@@ -186,6 +186,17 @@ def test_integrate_bodies(oracle, emu):
         # FP64, same operations; the host build may or may not contract a*b+c, so allow 1 ulp here
         # (the GPU test compares bit for bit against the FMA form nvcc emits)
         assert np.allclose(a[0], b[0], rtol=4e-16, atol=0) and np.allclose(a[1], b[1], rtol=4e-16, atol=1e-18)
+    # `fix` / `move` groups (ensemble.cu:111-174): group 1 frozen, group 2 dragged at a constant velocity
+    label = rng.integers(0, 4, n).astype(np.int32)
+    mv = np.array([0.3, -0.2, 0.1])
+    for step1 in (True, False):
+        a = oracle.velocity_verlet_groups(step1, 0.098, mass, pos, vel, f, label, 1, 2, mv)
+        b = emu.velocity_verlet_groups(step1, 0.098, mass, pos, vel, f, label, 1, 2, mv)
+        assert np.allclose(a[0], b[0], rtol=4e-16, atol=0) and np.allclose(a[1], b[1], rtol=4e-16, atol=1e-18)
+        assert np.all(a[1][:, (label == 1) | (label == 2)] == 0.0)
+        assert np.array_equal(a[0][:, label == 1], pos[:, label == 1])
+        if step1:
+            assert np.allclose(a[0][:, label == 2], pos[:, label == 2] + mv[:, None] * 0.098, rtol=1e-15)
     pe, vir = rng.normal(size=n), rng.normal(size=(9, n))
     assert np.allclose(oracle.find_thermo(n, 123.0, mass, pe, vel, vir),
                        emu.find_thermo(n, 123.0, mass, pe, vel, vir), rtol=1e-13)
