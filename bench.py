@@ -293,47 +293,61 @@ def side_bench(args, rank, world, local, torch, dist, engine):
         check = pot.check
         rebuilds = lambda: pot.num_rebuilds
     else:
-        from gpumd_b200.domain import DomainMD, SlabDomain
-        pot_rc = {"lj": 10.0, "unep": 6.0, "si": 3.0}[args.workload]
-        dom = SlabDomain(s["h"], s["pbc"], pot_rc, rank, world, "cuda", skin=DOMAIN_SKIN)
-        dom.distribute(s["type"], s["pos"], s["mass"], s["vel"])
-        md = DomainMD(dom, GOLDEN / potfile, ensemble=ensemble, temperature=T0, temperature_coupling=100.0,
-                      time_step=dt)
+        # libb200md_mgpu: C++ / CUDA / NCCL domains (slabs along x by default, --grid for blocks)
+        from gpumd_b200 import build, mgpu
+        if rank == 0:
+            build.build_mgpu()
+        dist.barrier()
+        grid = parse_grid(args.grid, world)
+        g = mgpu.DomainGroup(s["h"], s["pbc"], grid, GOLDEN / potfile, ensemble=ensemble, temperature=T0,
+                             temperature_coupling=100.0, time_step=dt, skin=DOMAIN_SKIN, distributed=True,
+                             cuda_graph=not args.no_graph)
+        g.distribute(s["type"], s["pos"], s["mass"], s["vel"])
         count = [0]
 
         def step():
-            md.maybe_exchange(5)
-            md.step(dt)
+            g.run(1, 5)
             count[0] += 1
             if heat_every and count[0] % heat_every == 0:
-                heat[0] = md.heat_current()
+                heat[0] = torch.as_tensor(g.heat_current())
 
-        md.compute_force()
-        get_thermo = lambda: md.read_thermo()
-        check = md.pot.check
-        rebuilds = lambda: md.pot.num_rebuilds
+        get_thermo = lambda: g.thermo()
+        check = g.check
+        rebuilds = lambda: g.info(4, 0)
     del s
     check()
     for _ in range(max(args.warmup, 3)):
         step()
-    if world > 1:
-        for _ in range(2):  # warm the displacement check (torch ops + all-reduce MAX) as well
-            dom.needs_exchange()
-        if heat_every:
-            md.heat_current()
+    if world > 1 and heat_every:
+        g.heat_current()
     check()
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
         torch.cuda.synchronize()
     r0 = rebuilds()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(args.steps):
-        step()
-    e1.record()
-    torch.cuda.synchronize()
-    ms_t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
+    if world == 1:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_dev = e0.elapsed_time(e1)
+    else:
+        # the module owns its stream: device time from its own CUDA events, heat-current samples
+        # (host reads) between the timed chunks
+        ms_dev, done = 0.0, 0
+        chunk = heat_every if heat_every else args.steps
+        while done < args.steps:
+            k = min(chunk, args.steps - done)
+            ms_dev += g.run_timed(k, 5)
+            done += k
+            if heat_every and done % heat_every == 0:
+                t0 = time.time()
+                heat[0] = torch.as_tensor(g.heat_current())
+                ms_dev += (time.time() - t0) * 1e3
+    ms_t = torch.tensor([ms_dev], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.barrier()
         dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
@@ -347,8 +361,21 @@ def side_bench(args, rank, world, local, torch, dist, engine):
             step()
         stage_ms = {k: round(v[0] / max(v[1], 1), 4) for k, v in pot.profile_read().items()}
         pot.profile(False)
+    ref_gpu = None
+    if rank == 0 and not args.no_reference_gpu:
+        from gpumd_b200.structures import nep_type_order
+        if world == 1:
+            del atom, force, pot, ens
+            torch.cuda.empty_cache()
+        s_ref = side_structure(args.workload, world, args.cells)
+        sym = {"lj": ["Ar"], "si": ["Si"]}.get(args.workload) or nep_type_order(GOLDEN / potfile)
+        ens_line = "nve" if ensemble == "nve" else f"{ensemble} {T0:g} {T0:g} 100"
+        ref_gpu = reference_gpu(s_ref, s_ref["vel"], world, args.steps, potential=GOLDEN / potfile,
+                                symbols=sym, ensemble=ens_line, dt_fs=dt_fs)
+        del s_ref
     if rank == 0:
         print(json.dumps({
+            "reference_gpu": ref_gpu,
             "metric": f"atom-steps/sec ({args.workload}, secondary config)", "value": n_global * args.steps / (ms * 1e-3),
             "unit": "atom-steps/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -359,98 +386,82 @@ def side_bench(args, rank, world, local, torch, dist, engine):
                        "final_T_K": float(th[0]), "nep_stage_ms": stage_ms,
                        "heat_current": None if heat[0] is None else [float(v) for v in heat[0].cpu().numpy()]}}))
     if world > 1:
-        dist.barrier()
+        dist.barrier(group=args.cpu_group)
+
+
+def parse_grid(spec, world):
+    """--grid PxxPyxPz (default: slabs along x, which is also how the weak-scaling crystal grows)."""
+    if not spec:
+        return (world, 1, 1)
+    g = tuple(int(v) for v in spec.lower().split("x"))
+    if len(g) != 3 or g[0] * g[1] * g[2] != world:
+        raise SystemExit(f"--grid {spec}: need PxxPyxPz with product {world}")
+    return g
 
 
 def ours_multi(args, rank, world, local, torch, dist, engine):
-    """N > 1: weak scaling, one slab of cells^3 conventional cells (1 M atoms) per GPU, owned-atom
-    integration, NCCL ghost-position halo per force evaluation, 8-double thermo all-reduce per
-    step, displacement-triggered migration / ghost-list exchange (gpumd_b200/domain.py)."""
-    from gpumd_b200.domain import DomainMD, SlabDomain
+    """N > 1: weak scaling, cells^3 conventional cells (1 M atoms) per GPU.  The whole multi-GPU step
+    is libb200md_mgpu (C++ / CUDA / NCCL, include/b200md_mgpu.h): owned-atom integration, staged
+    ncclSend/Recv of FP64 ghost positions per force evaluation, 8-double thermo all-reduce, device-side
+    displacement-triggered migration; one CUDA graph replay per step."""
+    from gpumd_b200 import build, mgpu
     from gpumd_b200.structures import TIME_UNIT_CONVERSION, init_velocities, rocksalt_pbte
-    s = rocksalt_pbte((args.cells * world, args.cells, args.cells), rattle=0.02, seed=1)
+    if rank == 0:
+        build.build_mgpu()
+    dist.barrier()
+    grid = parse_grid(args.grid, world)
+    cells = tuple(args.cells * g for g in grid)
+    s = rocksalt_pbte(cells, rattle=0.02, seed=1)
     vel = init_velocities(s["mass"], 300.0, seed=42)
     n_global = s["type"].shape[0]
-    # domain skin 3 A: ghost lists stay valid until some atom has moved 1.05 A (0.7 * skin / 2), which a
-    # solid at 300 K never does -- migrations are for diffusing systems; costs ~1 % more ghosts than 1 A
-    dom = SlabDomain(s["h"], s["pbc"], 8.0, rank, world, "cuda", skin=DOMAIN_SKIN)
-    dom.distribute(s["type"], s["pos"], s["mass"], vel)
-    del s, vel
-    md = DomainMD(dom, MODEL)
     dt = 1.0 / TIME_UNIT_CONVERSION
-    cadence = 5  # displacement check (all-reduce MAX + host read) every 5 steps
-    exchanges = [0]
-
-    exchange_s = [0.0]
-
-    def step():
-        t0 = time.time()
-        if md.maybe_exchange(cadence):
-            torch.cuda.synchronize()
-            exchanges[0] += 1
-            exchange_s[0] += time.time() - t0
-        md.step(dt)
-
-    md.compute_force()
-    md.pot.check()
-    for _ in range(max(args.warmup, 3)):
-        step()
-    for _ in range(2):  # the displacement check (torch ops + all-reduce MAX) is part of the loop: warm it too
-        dom.needs_exchange()
-    md.pot.check()
+    cadence = 5  # displacement check (max displacement, all-reduce MAX, one host read) every 5 steps
+    # ghost skin 3 A: ghost lists stay valid until some atom has moved 1.05 A (0.7 * skin / 2), which a
+    # solid at 300 K never does -- migrations are for diffusing systems; costs ~1 % more ghosts than 1 A
+    g = mgpu.DomainGroup(s["h"], s["pbc"], grid, MODEL, time_step=dt, skin=DOMAIN_SKIN, distributed=True,
+                         cuda_graph=not args.no_graph)
+    g.distribute(s["type"], s["pos"], s["mass"], vel)
+    del s, vel
+    g.run(max(args.warmup, 3), cadence)
+    g.check()
     sampler = ClockSampler(local) if rank == 0 and not os.environ.get("BENCH_NO_SAMPLER") else None
     torch.cuda.synchronize()
     dist.barrier()
     torch.cuda.synchronize()
-    launches0 = engine.launch_count()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mig0 = g.migrations
     w0 = time.time()
-    e0.record()
-    marks = []
-    for k in range(args.steps):
-        step()
-        if os.environ.get("BENCH_MARKS") and k % 10 == 9:
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            marks.append(ev)
-    e1.record()
-    torch.cuda.synchronize()
+    ms = g.run_timed(args.steps, cadence)  # CUDA events on the launching stream, synchronised
     dist.barrier()
     torch.cuda.synchronize()
     w1 = time.time()
-    # phase breakdown (untimed extra steps with CUDA events between the phases of DomainMD.step)
-    md.enable_profile(True)
-    h0 = time.time()
-    for _ in range(10):
-        md.step(dt)
-    host_issue_ms = (time.time() - h0) * 100.0  # host time to ISSUE one step (no sync inside)
-    phase_ms = md.profile_read()
-    phase_ms["host_issue"] = host_issue_ms
-    md.enable_profile(False)
-    ms_t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device="cuda")
-    if marks:
-        seq = [e0] + marks
-        print(f"rank {rank}: ms per 10 steps:", [round(a.elapsed_time(b), 2) for a, b in zip(seq[:-1], seq[1:])],
-              file=sys.stderr, flush=True)
+    g.check()
+    ms_t = torch.tensor([ms], dtype=torch.float64, device="cuda")
     dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
     ms = float(ms_t.item())
-    launches = engine.launch_count() - launches0
-    md.pot.check()
     clocks = sampler.stop(w0, w1) if sampler else None
-    th = md.read_thermo()
-    loc = torch.tensor([dom.n_own, dom.n_loc], dtype=torch.float64, device="cuda")
+    launches = g.launches_per_step * args.steps
+    th = g.thermo()
+    # phase breakdown: untimed extra steps, eager launches with CUDA events between the phases
+    g.profile(True)
+    h0 = time.time()
+    g.run(10, cadence)
+    host_ms = (time.time() - h0) * 100.0
+    phase_ms = g.profile(False)
+    phase_ms["host_per_step_eager"] = host_ms
+    loc = torch.tensor([g.info(1, 0), g.info(2, 0)], dtype=torch.float64, device="cuda")
     loc_max = loc.clone()
     dist.all_reduce(loc_max, op=dist.ReduceOp.MAX)
 
-    # end to end: every rank pushes its own local system through the host-buffer entry point
-    n = dom.n_loc
-    h_type = dom.type.cpu().pin_memory()
-    h_pos = dom.pos.cpu().pin_memory()
+    # end to end: every rank pushes its own local (owned + ghost) system through the host-buffer entry
+    ls = g.local_system(0)
+    n = ls["type"].shape[0]
+    h_type = torch.from_numpy(ls["type"]).pin_memory()
+    h_pos = torch.from_numpy(ls["pos"]).pin_memory()
     h_pe = torch.zeros(n, dtype=torch.float64).pin_memory()
     h_f = torch.zeros(3 * n, dtype=torch.float64).pin_memory()
     h_v = torch.zeros(9 * n, dtype=torch.float64).pin_memory()
     pot2 = engine.NEP(MODEL, n)
-    box = engine.Box(dom.local_h, dom.local_pbc)
+    box = engine.Box(ls["h"], ls["pbc"])
     for _ in range(2):
         pot2.compute_host(box, h_type, h_pos, h_pe, h_f, h_v)
     torch.cuda.synchronize()
@@ -465,7 +476,7 @@ def ours_multi(args, rank, world, local, torch, dist, engine):
     ref_gpu = None
     torch.cuda.synchronize()
     if rank == 0 and not args.no_reference_gpu:
-        s_ref = rocksalt_pbte((args.cells * world, args.cells, args.cells), rattle=0.02, seed=1)
+        s_ref = rocksalt_pbte(cells, rattle=0.02, seed=1)
         ref_gpu = reference_gpu(s_ref, init_velocities(s_ref["mass"], 300.0, seed=42), world, args.steps)
         del s_ref
     if rank == 0:
@@ -475,20 +486,22 @@ def ours_multi(args, rank, world, local, torch, dist, engine):
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {
-                "workload": f"C3 x {world}: rocksalt PbTe {args.cells * world}x{args.cells}x{args.cells} cells = "
+                "workload": f"C3 x {world}: rocksalt PbTe {cells[0]}x{cells[1]}x{cells[2]} cells = "
                             f"{n_global} atoms, NEP (nep_PbTe.txt), NVE dt 1 fs, 300 K",
                 "atoms_per_gpu": n_global // world,
-                "parallelism": f"{world} slab domains along x, owned-atom integration, NCCL halo of "
-                               f"FP64 ghost positions (2*rc+skin = {16 + DOMAIN_SKIN:g} A) per force call, thermo "
-                               f"all-reduce per step, displacement-triggered migration (checked every "
-                               f"{cadence} steps; {exchanges[0]} exchanges taking {exchange_s[0] * 1e3:.1f} ms "
-                               f"in warm-up + timed region)",
+                "parallelism": f"{grid[0]}x{grid[1]}x{grid[2]} block domains (libb200md_mgpu: C++ host, "
+                               f"device-side migration, NCCL), owned-atom integration, staged ncclSend/Recv of "
+                               f"FP64 ghost positions (halo 2*rc+skin = {16 + DOMAIN_SKIN:g} A) per force call; "
+                               f"descriptor work only for ghosts within rc+skin of the owned block; thermo "
+                               f"all-reduce per step; displacement check every {cadence} steps "
+                               f"({g.migrations - mig0} migrations in the timed region); "
+                               f"{'one CUDA-graph replay per step' if not args.no_graph else 'eager launches'}",
                 "max_owned": int(loc_max[0].item()), "max_local_with_ghosts": int(loc_max[1].item()),
                 "phase_ms_rank0": {k: round(v, 4) for k, v in (phase_ms or {}).items()},
                 "cache": "inputs larger than L2; no flush needed",
                 "final_T_K": float(th[0]), "final_U_eV_per_atom": float(th[1]) / n_global},
             "clocks": clocks,
-            "e2e": {"value": dom.n_own * world * e2e_steps / float(e2e_t.item()), "unit": "atom-steps/s",
+            "e2e": {"value": g.info(1, 0) * world * e2e_steps / float(e2e_t.item()), "unit": "atom-steps/s",
                     "h2d_bytes_per_step": int(28 * n), "d2h_bytes_per_step": int(104 * n),
                     "steps": e2e_steps,
                     "what": "per rank: b200md_nep_compute_host on its local (owned+ghost) system, pinned "
@@ -710,6 +723,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--cells", type=int, default=50, help="conventional cells per edge (50 -> 1M atoms)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--grid", default="", help="multi-GPU block grid PxxPyxPz (default: Nx1x1 slabs)")
+    ap.add_argument("--no-graph", action="store_true", help="multi-GPU: eager launches instead of a CUDA graph per step")
     ap.add_argument("--no-reference-gpu", action="store_true",
                     help="skip the run of oracle/_ref/gpumd_ref (the reference on the same GPU) after the bench")
     ap.add_argument("--workload", default="pbte", choices=["pbte", "lj", "unep", "si"],

@@ -92,6 +92,8 @@ struct DBuf {
 
 constexpr int BLK = 256;
 inline int grid_for(long long n, int b) { return (int)((n + b - 1) / b); }
+long long g_own_launches = 0; // kernels launched by this module (libb200md counts its own)
+#define MG_COUNT() (++g_own_launches)
 
 // ---------------------------------------------------------------------------------------------
 // kernels
@@ -273,6 +275,12 @@ struct Pot {
       MG_B2(b200md_nep_set_owned((b200md_nep*)h, n)); // the others compute ghost outputs, unused
     return B200MD_OK;
   }
+  int set_active(const double lo[3], const double hi[3])
+  {
+    if (kind == 0)
+      MG_B2(b200md_nep_set_active_region((b200md_nep*)h, lo, hi));
+    return B200MD_OK;
+  }
   int check(cudaStream_t st)
   {
     switch (kind) {
@@ -373,6 +381,8 @@ struct b200md_mgpu {
   // CUDA graph of one step
   cudaGraphExec_t graph = nullptr;
   double graph_dt = 0.0;
+  long long launches_per_step = 0; // kernels of one step (this module's + libb200md's)
+  cudaEvent_t t0 = nullptr, t1 = nullptr;
 
   ~b200md_mgpu()
   {
@@ -382,6 +392,10 @@ struct b200md_mgpu {
     for (auto& e : ev)
       if (e)
         cudaEventDestroy(e);
+    if (t0)
+      cudaEventDestroy(t0);
+    if (t1)
+      cudaEventDestroy(t1);
     if (comm)
       ncclCommDestroy(comm);
     if (stream)
@@ -533,8 +547,8 @@ int sync_owned(Group& G, Domain& D)
   }
   MG_CUDA(cudaMemcpyAsync(D.own_d.p + (size_t)9 * n, D.mass.p, sizeof(double) * n,
                           cudaMemcpyDeviceToDevice, st));
-  k_int_to_double<<<grid_for(n, BLK), BLK, 0, st>>>(n, D.type.p, D.own_d.p + (size_t)10 * n);
-  k_ll_to_double<<<grid_for(n, BLK), BLK, 0, st>>>(n, D.id.p, D.own_d.p + (size_t)11 * n);
+  k_int_to_double<<<grid_for(n, BLK), BLK, 0, st>>>(n, D.type.p, D.own_d.p + (size_t)10 * n); MG_COUNT();
+  k_ll_to_double<<<grid_for(n, BLK), BLK, 0, st>>>(n, D.id.p, D.own_d.p + (size_t)11 * n); MG_COUNT();
   return B200MD_OK;
 }
 
@@ -556,9 +570,10 @@ int migrate_stage(Group& G, int d)
     MG_CUDA(D.st[d].idx_lo.reserve(D.cap));
     MG_CUDA(D.st[d].idx_hi.reserve(D.cap));
     MG_CUDA(idx_stay[k]->reserve(D.cap));
-    if (n > 0)
+    if (n > 0) {
       k_flag_faces<<<grid_for(n, BLK), BLK, 0, st>>>(
-        n, D.own_d.p + (size_t)d * n, G.halo, G.halo + G.w[d], D.flag_lo.p, D.flag_hi.p, D.flag_stay.p);
+        n, D.own_d.p + (size_t)d * n, G.halo, G.halo + G.w[d], D.flag_lo.p, D.flag_hi.p, D.flag_stay.p); MG_COUNT();
+    }
     MG_TRY(select(D, n, D.flag_lo.p, D.st[d].idx_lo.p, &n_lo[k], st));
     MG_TRY(select(D, n, D.flag_hi.p, D.st[d].idx_hi.p, &n_hi[k], st));
     MG_TRY(select(D, n, D.flag_stay.p, idx_stay[k]->p, &n_stay[k], st));
@@ -573,12 +588,14 @@ int migrate_stage(Group& G, int d)
     msg[k].recv_hi = (size_t)MIG_ROWS * from_hi[k];
     msg[k].recv_lo = (size_t)MIG_ROWS * from_lo[k];
     MG_TRY(reserve_msg(D, msg[k].send_lo, msg[k].send_hi, msg[k].recv_hi, msg[k].recv_lo, st));
-    if (n_lo[k])
+    if (n_lo[k]) {
       k_gather_rows<<<grid_for((long long)n_lo[k] * MIG_ROWS, BLK), BLK, 0, st>>>(
-        n_lo[k], MIG_ROWS, D.st[d].idx_lo.p, n, D.own_d.p, d, +G.w[d], D.send_lo.p);
-    if (n_hi[k])
+        n_lo[k], MIG_ROWS, D.st[d].idx_lo.p, n, D.own_d.p, d, +G.w[d], D.send_lo.p); MG_COUNT();
+    }
+    if (n_hi[k]) {
       k_gather_rows<<<grid_for((long long)n_hi[k] * MIG_ROWS, BLK), BLK, 0, st>>>(
-        n_hi[k], MIG_ROWS, D.st[d].idx_hi.p, n, D.own_d.p, d, -G.w[d], D.send_hi.p);
+        n_hi[k], MIG_ROWS, D.st[d].idx_hi.p, n, D.own_d.p, d, -G.w[d], D.send_hi.p); MG_COUNT();
+    }
   }
   MG_TRY(exchange_payload(G, d, msg));
   for (size_t k = 0; k < K; ++k) {
@@ -588,18 +605,22 @@ int migrate_stage(Group& G, int d)
     if (n_new > D.cap)
       return fail(B200MD_ERR_OVERFLOW, "a domain's atom count exceeds its capacity (raise capacity_factor)");
     // own_d2 = [stay | from_hi | from_lo] with stride n_new
-    if (n_stay[k])
+    if (n_stay[k]) {
       k_gather_rows<<<grid_for((long long)n_stay[k] * MIG_ROWS, BLK), BLK, 0, st>>>(
-        n_stay[k], MIG_ROWS, idx_stay[k]->p, n, D.own_d.p, -1, 0.0, D.cand.p); // cand as scratch
-    if (n_stay[k])
+        n_stay[k], MIG_ROWS, idx_stay[k]->p, n, D.own_d.p, -1, 0.0, D.cand.p); MG_COUNT(); // cand as scratch
+    }
+    if (n_stay[k]) {
       k_scatter_rows<<<grid_for((long long)n_stay[k] * MIG_ROWS, BLK), BLK, 0, st>>>(
-        n_stay[k], MIG_ROWS, D.cand.p, n_new, 0, D.own_d2.p);
-    if (from_hi[k])
+        n_stay[k], MIG_ROWS, D.cand.p, n_new, 0, D.own_d2.p); MG_COUNT();
+    }
+    if (from_hi[k]) {
       k_scatter_rows<<<grid_for((long long)from_hi[k] * MIG_ROWS, BLK), BLK, 0, st>>>(
-        from_hi[k], MIG_ROWS, D.recv_hi.p, n_new, n_stay[k], D.own_d2.p);
-    if (from_lo[k])
+        from_hi[k], MIG_ROWS, D.recv_hi.p, n_new, n_stay[k], D.own_d2.p); MG_COUNT();
+    }
+    if (from_lo[k]) {
       k_scatter_rows<<<grid_for((long long)from_lo[k] * MIG_ROWS, BLK), BLK, 0, st>>>(
-        from_lo[k], MIG_ROWS, D.recv_lo.p, n_new, n_stay[k] + from_hi[k], D.own_d2.p);
+        from_lo[k], MIG_ROWS, D.recv_lo.p, n_new, n_stay[k] + from_hi[k], D.own_d2.p); MG_COUNT();
+    }
     std::swap(D.own_d.p, D.own_d2.p);
     std::swap(D.own_d.n, D.own_d2.n);
     D.n_own = n_new;
@@ -620,9 +641,10 @@ int ghost_stage(Group& G, int d, std::vector<int>& m_now)
     S.m_cand = m_now[k];
     const int m = S.m_cand;
     // within `halo` of the lower face: coordinate < 2 halo; of the upper face: >= w
-    if (m > 0)
+    if (m > 0) {
       k_flag_faces<<<grid_for(m, BLK), BLK, 0, st>>>(
-        m, D.cand.p + (size_t)d * D.cap, 2.0 * G.halo, G.w[d], D.flag_lo.p, D.flag_hi.p, nullptr);
+        m, D.cand.p + (size_t)d * D.cap, 2.0 * G.halo, G.w[d], D.flag_lo.p, D.flag_hi.p, nullptr); MG_COUNT();
+    }
     MG_TRY(select(D, m, D.flag_lo.p, S.idx_lo.p, &S.n_lo, st));
     MG_TRY(select(D, m, D.flag_hi.p, S.idx_hi.p, &S.n_hi, st));
     n_lo[k] = S.n_lo;
@@ -643,23 +665,27 @@ int ghost_stage(Group& G, int d, std::vector<int>& m_now)
     msg[k].recv_hi = (size_t)GHOST_ROWS * from_hi[k];
     msg[k].recv_lo = (size_t)GHOST_ROWS * from_lo[k];
     MG_TRY(reserve_msg(D, msg[k].send_lo, msg[k].send_hi, msg[k].recv_hi, msg[k].recv_lo, st));
-    if (S.n_lo)
+    if (S.n_lo) {
       k_gather_rows<<<grid_for((long long)S.n_lo * GHOST_ROWS, BLK), BLK, 0, st>>>(
-        S.n_lo, GHOST_ROWS, S.idx_lo.p, D.cap, D.cand.p, d, +G.w[d], D.send_lo.p);
-    if (S.n_hi)
+        S.n_lo, GHOST_ROWS, S.idx_lo.p, D.cap, D.cand.p, d, +G.w[d], D.send_lo.p); MG_COUNT();
+    }
+    if (S.n_hi) {
       k_gather_rows<<<grid_for((long long)S.n_hi * GHOST_ROWS, BLK), BLK, 0, st>>>(
-        S.n_hi, GHOST_ROWS, S.idx_hi.p, D.cap, D.cand.p, d, -G.w[d], D.send_hi.p);
+        S.n_hi, GHOST_ROWS, S.idx_hi.p, D.cap, D.cand.p, d, -G.w[d], D.send_hi.p); MG_COUNT();
+    }
   }
   MG_TRY(exchange_payload(G, d, msg));
   for (size_t k = 0; k < K; ++k) {
     Domain& D = *G.dom[k];
     Stage& S = D.st[d];
-    if (S.n_from_hi)
+    if (S.n_from_hi) {
       k_scatter_rows<<<grid_for((long long)S.n_from_hi * GHOST_ROWS, BLK), BLK, 0, st>>>(
-        S.n_from_hi, GHOST_ROWS, D.recv_hi.p, D.cap, S.ghost_start, D.cand.p);
-    if (S.n_from_lo)
+        S.n_from_hi, GHOST_ROWS, D.recv_hi.p, D.cap, S.ghost_start, D.cand.p); MG_COUNT();
+    }
+    if (S.n_from_lo) {
       k_scatter_rows<<<grid_for((long long)S.n_from_lo * GHOST_ROWS, BLK), BLK, 0, st>>>(
-        S.n_from_lo, GHOST_ROWS, D.recv_lo.p, D.cap, S.ghost_start + S.n_from_hi, D.cand.p);
+        S.n_from_lo, GHOST_ROWS, D.recv_lo.p, D.cap, S.ghost_start + S.n_from_hi, D.cand.p); MG_COUNT();
+    }
     m_now[k] += S.n_from_hi + S.n_from_lo;
   }
   return B200MD_OK;
@@ -710,10 +736,12 @@ int rebuild_local(Group& G)
     }
     MG_CUDA(cudaMemcpyAsync(D.mass.p, D.cand.p + (size_t)4 * D.cap, sizeof(double) * s,
                             cudaMemcpyDeviceToDevice, st));
-    if (s > 0)
-      k_double_to_int<<<grid_for(s, BLK), BLK, 0, st>>>(s, D.cand.p + (size_t)3 * D.cap, D.type.p);
-    if (n > 0)
-      k_double_to_ll<<<grid_for(n, BLK), BLK, 0, st>>>(n, D.own_d.p + (size_t)11 * n, D.id.p);
+    if (s > 0) {
+      k_double_to_int<<<grid_for(s, BLK), BLK, 0, st>>>(s, D.cand.p + (size_t)3 * D.cap, D.type.p); MG_COUNT();
+    }
+    if (n > 0) {
+      k_double_to_ll<<<grid_for(n, BLK), BLK, 0, st>>>(n, D.own_d.p + (size_t)11 * n, D.id.p); MG_COUNT();
+    }
     MG_TRY(D.pot.invalidate(s, st));
     MG_TRY(D.pot.set_owned(n));
   }
@@ -743,23 +771,27 @@ int halo_update(Group& G)
       msg[k].send_hi = (size_t)3 * S.n_hi;
       msg[k].recv_hi = (size_t)3 * S.n_from_hi;
       msg[k].recv_lo = (size_t)3 * S.n_from_lo;
-      if (S.n_lo)
+      if (S.n_lo) {
         k_gather_rows<<<grid_for((long long)S.n_lo * 3, BLK), BLK, 0, st>>>(
-          S.n_lo, 3, S.idx_lo.p, D.n_loc, D.pos.p, d, +G.w[d], D.send_lo.p);
-      if (S.n_hi)
+          S.n_lo, 3, S.idx_lo.p, D.n_loc, D.pos.p, d, +G.w[d], D.send_lo.p); MG_COUNT();
+      }
+      if (S.n_hi) {
         k_gather_rows<<<grid_for((long long)S.n_hi * 3, BLK), BLK, 0, st>>>(
-          S.n_hi, 3, S.idx_hi.p, D.n_loc, D.pos.p, d, -G.w[d], D.send_hi.p);
+          S.n_hi, 3, S.idx_hi.p, D.n_loc, D.pos.p, d, -G.w[d], D.send_hi.p); MG_COUNT();
+      }
     }
     MG_TRY(exchange_payload(G, d, msg));
     for (size_t k = 0; k < K; ++k) {
       Domain& D = *G.dom[k];
       const Stage& S = D.st[d];
-      if (S.n_from_hi)
+      if (S.n_from_hi) {
         k_scatter_rows<<<grid_for((long long)S.n_from_hi * 3, BLK), BLK, 0, st>>>(
-          S.n_from_hi, 3, D.recv_hi.p, D.n_loc, S.ghost_start, D.pos.p);
-      if (S.n_from_lo)
+          S.n_from_hi, 3, D.recv_hi.p, D.n_loc, S.ghost_start, D.pos.p); MG_COUNT();
+      }
+      if (S.n_from_lo) {
         k_scatter_rows<<<grid_for((long long)S.n_from_lo * 3, BLK), BLK, 0, st>>>(
-          S.n_from_lo, 3, D.recv_lo.p, D.n_loc, S.ghost_start + S.n_from_hi, D.pos.p);
+          S.n_from_lo, 3, D.recv_lo.p, D.n_loc, S.ghost_start + S.n_from_hi, D.pos.p); MG_COUNT();
+      }
     }
   }
   return B200MD_OK;
@@ -791,7 +823,7 @@ int find_thermo(Group& G)
   } else if (G.dom.size() > 1) {
     MG_CUDA(cudaMemsetAsync(G.thermo_sum.p, 0, 8 * sizeof(double), st));
     for (auto& dp : G.dom)
-      k_add8<<<1, 32, 0, st>>>(G.thermo_sum.p, dp->thermo.p, 8);
+      k_add8<<<1, 32, 0, st>>>(G.thermo_sum.p, dp->thermo.p, 8); MG_COUNT();
     for (auto& dp : G.dom)
       MG_CUDA(cudaMemcpyAsync(dp->thermo.p, G.thermo_sum.p, 8 * sizeof(double), cudaMemcpyDeviceToDevice, st));
   }
@@ -818,6 +850,12 @@ int one_step(Group& G, double dt)
 {
   cudaStream_t st = G.stream;
   const int ens = G.cfg.ensemble;
+  const long long l0 = g_own_launches + b200md_launch_count();
+  struct Tally {
+    Group& G;
+    long long l0;
+    ~Tally() { G.launches_per_step = g_own_launches + b200md_launch_count() - l0; }
+  } tally{G, l0};
   mark(G, 0);
   if (ens == 2)
     MG_TRY(nhc_half(G, dt));
@@ -863,10 +901,11 @@ int needs_exchange(Group& G, bool* out)
   for (auto& dp : G.dom) {
     Domain& D = *dp;
     MG_CUDA(cudaMemsetAsync(D.disp_bits.p, 0, sizeof(unsigned int), st));
-    if (D.n_own > 0)
+    if (D.n_own > 0) {
       k_max_disp2<<<grid_for(D.n_own, BLK), BLK, 0, st>>>(
         D.n_own, D.n_loc, D.pos.p, D.ref.p, D.lpbc[0] ? G.L[0] : 0.0, D.lpbc[1] ? G.L[1] : 0.0,
-        D.lpbc[2] ? G.L[2] : 0.0, D.disp_bits.p);
+        D.lpbc[2] ? G.L[2] : 0.0, D.disp_bits.p); MG_COUNT();
+    }
   }
   if (G.distributed)
     MG_NCCL(ncclAllReduce(G.dom[0]->disp_bits.p, G.dom[0]->disp_bits.p, 1, ncclUint32, ncclMax, G.comm, st));
@@ -1068,6 +1107,17 @@ int b200md_mgpu_distribute(
     MG_CUDA(cudaMemsetAsync(D.thermo_scratch.p, 0, (size_t)sb, st));
     MG_CUDA(cudaMemsetAsync(D.thermo.p, 0, 8 * sizeof(double), st));
     MG_TRY(D.pot.create(G.potential_file.c_str(), D.cap));
+    { // ghosts beyond rc + skin of the owned block cannot be a neighbour of an owned atom: no
+      // descriptor work for them (they still serve as neighbours)
+      double lo[3], hi[3];
+      const double reach = D.pot.rc + G.cfg.skin;
+      for (int d = 0; d < 3; ++d) {
+        const bool cut = G.cfg.grid[d] > 1;
+        lo[d] = cut ? G.halo - reach : -1.0e300;
+        hi[d] = cut ? G.halo + G.w[d] + reach : 1.0e300;
+      }
+      MG_TRY(D.pot.set_active(lo, hi));
+    }
     if (G.cfg.ensemble == 2)
       MG_B2(b200md_nhc_create(n_global, G.cfg.temperature, G.cfg.temperature_coupling, G.cfg.time_step, &D.nhc));
     else if (G.cfg.ensemble == 4)
@@ -1153,6 +1203,25 @@ int b200md_mgpu_run(b200md_mgpu* g, int nsteps, int check_every)
   return B200MD_OK;
 }
 
+int b200md_mgpu_run_timed(b200md_mgpu* g, int nsteps, int check_every, double* ms_out)
+{
+  Group& G = *g;
+  if (!G.t0) {
+    MG_CUDA(cudaEventCreate(&G.t0));
+    MG_CUDA(cudaEventCreate(&G.t1));
+  }
+  MG_CUDA(cudaStreamSynchronize(G.stream));
+  MG_CUDA(cudaEventRecord(G.t0, G.stream));
+  MG_TRY(b200md_mgpu_run(g, nsteps, check_every));
+  MG_CUDA(cudaEventRecord(G.t1, G.stream));
+  MG_CUDA(cudaStreamSynchronize(G.stream));
+  float ms = 0.0f;
+  MG_CUDA(cudaEventElapsedTime(&ms, G.t0, G.t1));
+  if (ms_out)
+    *ms_out = ms;
+  return B200MD_OK;
+}
+
 int b200md_mgpu_thermo(b200md_mgpu* g, double out8[8])
 {
   Group& G = *g;
@@ -1204,6 +1273,8 @@ long long b200md_mgpu_info(b200md_mgpu* g, int what, int k)
     return (long long)G.dom.size();
   if (what == 3)
     return G.migrations;
+  if (what == 6)
+    return G.launches_per_step;
   if (k < 0 || k >= (int)G.dom.size())
     return -1;
   Domain& D = *G.dom[k];
@@ -1252,6 +1323,26 @@ int b200md_mgpu_get_owned(
         }
         position[d * n + i] = x;
       }
+  return B200MD_OK;
+}
+
+int b200md_mgpu_get_local(
+  b200md_mgpu* g, int k, int* type, double* position, double h_out[9], int pbc_out[3])
+{
+  Group& G = *g;
+  if (k < 0 || k >= (int)G.dom.size())
+    return fail(B200MD_ERR_ARG, "b200md_mgpu_get_local: bad domain index");
+  Domain& D = *G.dom[k];
+  const size_t s = (size_t)D.n_loc;
+  if (type)
+    MG_CUDA(cudaMemcpyAsync(type, D.type.p, sizeof(int) * s, cudaMemcpyDeviceToHost, G.stream));
+  if (position)
+    MG_CUDA(cudaMemcpyAsync(position, D.pos.p, sizeof(double) * 3 * s, cudaMemcpyDeviceToHost, G.stream));
+  MG_CUDA(cudaStreamSynchronize(G.stream));
+  if (h_out)
+    std::memcpy(h_out, D.lh, sizeof D.lh);
+  if (pbc_out)
+    std::memcpy(pbc_out, D.lpbc, sizeof D.lpbc);
   return B200MD_OK;
 }
 

@@ -347,6 +347,11 @@ int dispatch_desc_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
     A.nn_r = P.nn_r; A.nl_r = P.nl_r; A.nn_a = P.nn_a; A.nl_a = P.nl_a;
     A.q = P.q; A.flags = P.flags;
     A.rc_r = P.rc_r; A.rcinv_r = P.rcinv_r; A.rc2_r = P.rc2_r; A.rc2_a = P.rc2_a; A.c_r = P.c_r;
+    A.use_active = P.use_active;
+    for (int d = 0; d < 3; ++d) {
+      A.act_lo[d] = P.act_lo[d];
+      A.act_hi[d] = P.act_hi[d];
+    }
     const int g = grid_for(p->n, BLK);
     if (p->model.nt == 1 && box.ortho)
       k_desc_radial2<1, K1, true><<<g, BLK, 0, st>>>(A, box);
@@ -902,6 +907,22 @@ int b200md_nep_set_owned(b200md_nep* p, int n_owned)
     return B200MD_ERR_ARG;
   }
   p->view.n_own = n_owned;
+  return B200MD_OK;
+}
+
+int b200md_nep_set_active_region(b200md_nep* p, const double lo[3], const double hi[3])
+{
+  // nep_setup (supercell path) rewrites the view: keep the request in the view only, which is what the
+  // domain module needs (its local boxes are never small boxes)
+  if (!lo || !hi) {
+    p->view.use_active = 0;
+    return B200MD_OK;
+  }
+  p->view.use_active = 1;
+  for (int d = 0; d < 3; ++d) {
+    p->view.act_lo[d] = lo[d];
+    p->view.act_hi[d] = hi[d];
+  }
   return B200MD_OK;
 }
 

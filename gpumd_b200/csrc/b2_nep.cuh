@@ -101,6 +101,9 @@ struct B2NepView {
                            //    lane teams), 0: AoS rows of UST floats (many-type path, tests/emu)
   int n_own;               // > 0: only caller indices < n_own get outputs (domain decomposition:
                            // the rest are ghosts whose forces the caller discards)
+  int use_active;          // 1: atoms outside [act_lo, act_hi) get empty neighbour sets, i.e. no
+  double act_lo[3];        //    descriptor / MLP-gradient / partial-force work: ghosts further than
+  double act_hi[3];        //    rc from every owned atom only serve as neighbours (b200md_nep_set_active_region)
   // ---- tensor-core hidden layer (k_mlp_tc; null / 0 when the SIMT k_mlp is used) ----
   const float* tc_img;  // [nt][tc_img_floats] shared-memory images, see NepModel::tc_img
   int tc_img_floats, HN, DK, DN;
@@ -110,6 +113,15 @@ struct B2NepView {
   const int* tile_meta;
 };
 
+// inside the region whose atoms need descriptors (always true without a region)
+B2_HD bool b2_is_active(const B2NepView& P, double x, double y, double z)
+{
+  if (!P.use_active)
+    return true;
+  return x >= P.act_lo[0] && x < P.act_hi[0] && y >= P.act_lo[1] && y < P.act_hi[1] &&
+         z >= P.act_lo[2] && z < P.act_hi[2];
+}
+
 // ---------------------------------------------------------------------------------------------
 // neighbour-set split: find_neighbor_list_large_box, nep.cu:436-486
 // ---------------------------------------------------------------------------------------------
@@ -118,6 +130,11 @@ B2_HD void b2_body_split(int i, const B2NepView& P, const B2Box& box)
   const B2Geo geo = b2_geo(box);
   const size_t N = (size_t)P.n;
   const B2Atom a1 = P.atoms[i];
+  if (!b2_is_active(P, a1.x, a1.y, a1.z)) {
+    P.nn_r[i] = 0;
+    P.nn_a[i] = 0;
+    return;
+  }
   const int nn = P.nn_skin[i];
   const int row = a1.type * P.nt;
   int cr = 0, ca = 0;
@@ -237,6 +254,13 @@ B2_HD void b2_body_desc_radial(
   const B2Geo geo = b2_geo(box);
   const B2Atom a1 = P.atoms[i];
   const int t1 = a1.type;
+  if (SPLIT && !b2_is_active(P, a1.x, a1.y, a1.z)) {
+    P.nn_r[i] = 0;
+    P.nn_a[i] = 0;
+    for (int n = 0; n < P.nr1; ++n)
+      P.q[(size_t)n * P.n + i] = 0.0f;
+    return;
+  }
   const int nn = SPLIT ? P.nn_skin[i] : P.nn_r[i];
   const int* list = SPLIT ? P.nl_skin : P.nl_r;
   int cr = 0, ca = 0;

@@ -398,6 +398,100 @@ class Ensemble_BER(Ensemble_NVE):
             _ptr(atom.velocity_per_atom), _stream()))
 
 
+K_B = 8.617343e-5  # common.cuh:21
+PRESSURE_UNIT_CONVERSION = 1.602177e+2  # common.cuh:25
+
+
+class Ensemble_NPT_BER(Ensemble_BER):
+    """npt_ber, src/integrate/ensemble_ber.cu:38-64,88-172,237-285: Berendsen thermostat + barostat.
+    target_pressure / elastic_modulus in GPa (1, 3 or 6 values, Voigt order for 6), tau_p in steps, as
+    on the `ensemble npt_ber` line; converted like integrate.cu:690-700,1150-1153.  The box is updated
+    in place on the host (Box.h), positions are rescaled on the device."""
+
+    def __init__(self, num_atoms, temperature, temperature_coupling, target_pressure, elastic_modulus, tau_p):
+        super().__init__(num_atoms, temperature, temperature_coupling)
+        p = np.atleast_1d(np.asarray(target_pressure, dtype=np.float64))
+        c = np.atleast_1d(np.asarray(elastic_modulus, dtype=np.float64))
+        if p.shape[0] not in (1, 3, 6) or c.shape != p.shape:
+            raise ValueError("npt_ber takes 1, 3 or 6 pressure components and as many elastic moduli")
+        self.num_p = int(p.shape[0])
+        pc = np.ones(6)
+        pc[:self.num_p] = c
+        coupling = np.where(pc > 2.0e3, 0.0, 1.0 / (float(tau_p) * 3.0 * pc))
+        p6 = np.zeros(6)
+        p6[:self.num_p] = p
+        self._p0 = (C.c_double * 6)(*(p6 / PRESSURE_UNIT_CONVERSION))
+        self._pc = (C.c_double * 6)(*(coupling * PRESSURE_UNIT_CONVERSION))
+        self._zero3i = (C.c_int * 3)(0, 0, 0)
+        self._zero3d = (C.c_double * 3)(0.0, 0.0, 0.0)
+
+    def compute2(self, time_step, box, atom, thermo):
+        super().compute2(time_step, box, atom, thermo)
+        n = atom.number_of_atoms
+        # box.cpu_h is updated in place (the next force call sees the new box)
+        _lib.check(self._L.b200md_berendsen_pressure(
+            n, n, self.num_p, self._p0, self._pc, self._zero3i, self._zero3d, box._p, box._h, _ptr(thermo),
+            _ptr(atom.position_per_atom), _stream()))
+
+
+class Ensemble_LAN(Ensemble_NVE):
+    """nvt_lan, src/integrate/ensemble_lan.cu:29-41,92-124,190-269: half Langevin kick (c1 =
+    exp(-0.5/Tc)) + momentum correction, velocity-Verlet, half kick.  cuRAND XORWOW per atom, seeded
+    like the reference (seed 1804289383 = glibc's first rand(), what its -DDEBUG build passes)."""
+    C1_EXPONENT = -0.5
+
+    def __init__(self, num_atoms, temperature, temperature_coupling, seed=1804289383):
+        super().__init__(num_atoms)
+        self.temperature = float(temperature)
+        self.c1 = float(np.exp(self.C1_EXPONENT / float(temperature_coupling)))
+        h = C.c_void_p()
+        _lib.check(self._L.b200md_langevin_create(int(num_atoms), int(seed), C.byref(h)))
+        self._lan = h
+
+    def __del__(self):
+        if getattr(self, "_lan", None):
+            self._L.b200md_langevin_destroy(self._lan)
+            self._lan = None
+
+    def _kick(self, atom):
+        n = atom.number_of_atoms
+        c2 = float(np.sqrt((1.0 - self.c1 * self.c1) * K_B * self.temperature))
+        _lib.check(self._L.b200md_langevin_apply(self._lan, n, n, self.c1, c2, _ptr(atom.mass),
+                                                 _ptr(atom.velocity_per_atom), _stream()))
+
+    def compute1(self, time_step, box, atom, thermo=None):
+        self._kick(atom)
+        self._vv(1, time_step, atom)
+
+    def compute2(self, time_step, box, atom, thermo):
+        self._vv(0, time_step, atom)
+        self._kick(atom)
+        self.find_thermo(box.get_volume(), atom, thermo)
+
+
+class Ensemble_BAO(Ensemble_LAN):
+    """nvt_bao, src/integrate/ensemble_bao.cu:29-41,91-120,190-470: B A O A | force | B with the full
+    Ornstein-Uhlenbeck step O (c1 = exp(-1/Tc))."""
+    C1_EXPONENT = -1.0
+
+    def _op(self, which, time_step, atom):
+        n = atom.number_of_atoms
+        label = _ptr(self._label) if self.fixed_group >= 0 else None
+        _lib.check(self._L.b200md_baoab_operator(
+            which, n, n, float(time_step), _ptr(atom.mass), _ptr(atom.position_per_atom),
+            _ptr(atom.velocity_per_atom), _ptr(atom.force_per_atom), label, self.fixed_group, _stream()))
+
+    def compute1(self, time_step, box, atom, thermo=None):
+        self._op(1, time_step, atom)
+        self._op(0, time_step, atom)
+        self._kick(atom)
+        self._op(0, time_step, atom)
+
+    def compute2(self, time_step, box, atom, thermo):
+        self._op(1, time_step, atom)
+        self.find_thermo(box.get_volume(), atom, thermo)
+
+
 class Ensemble_BDP(Ensemble_NVE):
     """nvt_bdp, src/integrate/ensemble_bdp.cu:69-101: velocity-Verlet, thermo, then the stochastic
     rescaling of Bussi et al.; generator and factor live on the device (seed 12345678 = the

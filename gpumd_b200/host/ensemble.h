@@ -5,6 +5,9 @@
 //   Ensemble_BER_B200  replaces Ensemble_BER (type 1, nvt_ber), ensemble_ber.cu:178-233
 //   Ensemble_NHC_B200  replaces Ensemble_NHC (type 2, nvt_nhc), ensemble_nhc.cu:173-237
 //   Ensemble_BDP_B200  replaces Ensemble_BDP (type 4, nvt_bdp), ensemble_bdp.cu:69-101,151-196
+//   Ensemble_LAN_B200  replaces Ensemble_LAN (type 3, nvt_lan), ensemble_lan.cu:29-41,92-124,190-269
+//   Ensemble_BAO_B200  replaces Ensemble_BAO (type 5, nvt_bao), ensemble_bao.cu:29-41,91-120,419-470
+//   Ensemble_BER_B200 with a target pressure = npt_ber (type 11), ensemble_ber.cu:38-64,88-172,237-285
 // Inside the reference tree (B200MD_IN_GPUMD, oracle/Makefile.gpumd_b200) they derive from the
 // reference's own class Ensemble; the standalone driver uses a same-shaped base.
 #pragma once
@@ -71,12 +74,57 @@ class Ensemble_BER_B200 : public Ensemble, protected B200_Integrator
 {
 public:
   Ensemble_BER_B200(int t, int mg, const double mv[3], double T, double Tc);
+  // npt_ber: target pressure / coupling in natural units (integrate.cu:1150-1153), 1, 3 or 6 components
+  Ensemble_BER_B200(
+    int t, double T, double Tc, const double target_p[6], int num_target_p, const double pc[6], int dx,
+    int dy, int dz, const double rate[3]);
   void compute1(
     const double time_step, const std::vector<Group>& group, Box& box, Atom& atom,
     GPU_Vector<double>& thermo) override;
   void compute2(
     const double time_step, const std::vector<Group>& group, Box& box, Atom& atom,
     GPU_Vector<double>& thermo) override;
+
+private:
+  double b2_target_p_[6] = {0, 0, 0, 0, 0, 0}, b2_pc_[6] = {0, 0, 0, 0, 0, 0}, b2_rate_[3] = {0, 0, 0};
+  int b2_num_p_ = 0, b2_deform_[3] = {0, 0, 0};
+};
+
+// cuRAND XORWOW state per atom on the device, seeded like the reference (rand())
+class Ensemble_LAN_B200 : public Ensemble, protected B200_Integrator
+{
+public:
+  Ensemble_LAN_B200(int t, int N, double T, double Tc, unsigned long long seed);
+  ~Ensemble_LAN_B200() override;
+  void compute1(
+    const double time_step, const std::vector<Group>& group, Box& box, Atom& atom,
+    GPU_Vector<double>& thermo) override;
+  void compute2(
+    const double time_step, const std::vector<Group>& group, Box& box, Atom& atom,
+    GPU_Vector<double>& thermo) override;
+
+private:
+  void half(Atom& atom);
+  b200md_langevin* lan_ = nullptr;
+  double c1_ = 0.0;
+};
+
+class Ensemble_BAO_B200 : public Ensemble, protected B200_Integrator
+{
+public:
+  Ensemble_BAO_B200(int t, int N, double T, double Tc, unsigned long long seed);
+  ~Ensemble_BAO_B200() override;
+  void compute1(
+    const double time_step, const std::vector<Group>& group, Box& box, Atom& atom,
+    GPU_Vector<double>& thermo) override;
+  void compute2(
+    const double time_step, const std::vector<Group>& group, Box& box, Atom& atom,
+    GPU_Vector<double>& thermo) override;
+
+private:
+  void op(int which, const double time_step, const std::vector<Group>& group, Atom& atom);
+  b200md_langevin* lan_ = nullptr;
+  double c1_ = 0.0;
 };
 
 // the generator lives on the device; seed 12345678 follows the reference's -DDEBUG stream

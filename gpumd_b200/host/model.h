@@ -17,6 +17,23 @@ public:
                      h[2] * (h[3] * h[7] - h[4] * h[6]);
     return v < 0 ? -v : v;
   }
+  // Box::get_inverse, src/model/box.cu:26-60: cpu_h[9..17] = inverse of cpu_h[0..8]
+  void get_inverse()
+  {
+    double* h = cpu_h;
+    h[9] = h[4] * h[8] - h[5] * h[7];
+    h[10] = h[2] * h[7] - h[1] * h[8];
+    h[11] = h[1] * h[5] - h[2] * h[4];
+    h[12] = h[5] * h[6] - h[3] * h[8];
+    h[13] = h[0] * h[8] - h[2] * h[6];
+    h[14] = h[2] * h[3] - h[0] * h[5];
+    h[15] = h[3] * h[7] - h[4] * h[6];
+    h[16] = h[1] * h[6] - h[0] * h[7];
+    h[17] = h[0] * h[4] - h[1] * h[3];
+    const double det = h[0] * h[9] + h[1] * h[12] + h[2] * h[15];
+    for (int k = 9; k < 18; ++k)
+      h[k] /= det;
+  }
   void pbc(int out[3]) const
   {
     out[0] = pbc_x;

@@ -302,8 +302,11 @@ private:
   // what the `ensemble` keyword asked for; the object itself is built at `run` from the time step
   // and atom count in force THEN, and rebuilt for every run (Integrate::initialize, integrate.cu:76-280)
   struct EnsembleSpec {
-    int type = -1; // 0 nve, 1 nvt_ber, 2 nvt_nhc, 4 nvt_bdp (the reference's type codes)
+    int type = -1; // 0 nve, 1 nvt_ber, 2 nvt_nhc, 3 nvt_lan, 4 nvt_bdp, 5 nvt_bao, 11 npt_ber
     double T = 0.0, Tc = 0.0;
+    // npt_ber: natural units, as integrate.cu:1150-1153 leaves them
+    double target_p[6] = {0, 0, 0, 0, 0, 0}, p_coupling[6] = {0, 0, 0, 0, 0, 0};
+    int num_p = 0;
     bool has_seed = false;
     unsigned seed = 0;
   } ensemble_spec_;
@@ -414,9 +417,49 @@ private:
           e.has_seed = true;
           e.seed = (unsigned)std::strtoul(t[6].c_str(), nullptr, 10);
         }
+      } else if (t.size() == 5 && (t[1] == "nvt_lan" || t[1] == "nvt_bao")) {
+        e.T = std::atof(t[2].c_str());
+        e.Tc = std::atof(t[4].c_str());
+        if (e.T <= 0.0 || std::atof(t[3].c_str()) != e.T)
+          input_error("Temperatures should > 0 and equal (no ramps in the b200md backend).");
+        if (e.Tc < 1.0)
+          input_error("Temperature coupling should >= 1.");
+        e.type = t[1] == "nvt_lan" ? 3 : 5;
+      } else if (t[1] == "npt_ber" && (t.size() == 8 || t.size() == 12 || t.size() == 18)) {
+        // npt_ber T1 T2 Tc p(1|3|6, GPa) C(1|3|6 elastic moduli, GPa) tau_p  (integrate.cu:630-700)
+        e.T = std::atof(t[2].c_str());
+        e.Tc = std::atof(t[4].c_str());
+        if (e.T <= 0.0 || std::atof(t[3].c_str()) != e.T)
+          input_error("Temperatures should > 0 and equal (no ramps in the b200md backend).");
+        if (e.Tc < 1.0)
+          input_error("Temperature coupling should >= 1.");
+        e.num_p = t.size() == 8 ? 1 : (t.size() == 12 ? 3 : 6);
+        const Box& b = model_.box;
+        const bool tri = b.cpu_h[1] != 0 || b.cpu_h[2] != 0 || b.cpu_h[3] != 0 || b.cpu_h[5] != 0 ||
+                         b.cpu_h[6] != 0 || b.cpu_h[7] != 0;
+        if (e.num_p < 6 && tri)
+          input_error("Cannot use triclinic box with only 1 or 3 target pressure components.");
+        if (e.num_p != 3 && !(b.pbc_x && b.pbc_y && b.pbc_z))
+          input_error("Cannot use isotropic / 6-component pressure with a non-periodic direction.");
+        double modulus[6] = {1, 1, 1, 1, 1, 1};
+        for (int k = 0; k < e.num_p; ++k) {
+          e.target_p[k] = std::atof(t[5 + k].c_str());
+          modulus[k] = std::atof(t[5 + e.num_p + k].c_str());
+          if (modulus[k] <= 0)
+            input_error("elastic modulus should > 0.");
+        }
+        const double tau_p = std::atof(t[5 + 2 * e.num_p].c_str());
+        if (tau_p < 1)
+          input_error("Pressure coupling should >= 1.");
+        for (int k = 0; k < 6; ++k) {
+          e.p_coupling[k] = modulus[k] > 2.0e3 ? 0.0 : 1.0 / (tau_p * 3.0 * modulus[k]);
+          e.target_p[k] /= PRESSURE_UNIT_CONVERSION;
+          e.p_coupling[k] *= PRESSURE_UNIT_CONVERSION;
+        }
+        e.type = 11;
       } else {
-        input_error("only 'ensemble nve', 'nvt_ber|nvt_nhc|nvt_bdp T T tau' are supported "
-                    "by the b200md backend.");
+        input_error("supported by the b200md backend: ensemble nve | nvt_ber|nvt_nhc|nvt_bdp|nvt_lan|"
+                    "nvt_bao T T tau | npt_ber T T tau p.. C.. tau_p");
       }
       ensemble_spec_ = e;
     } else if (t[0] == "fix") {
@@ -713,6 +756,13 @@ private:
                    ? 12345678u
                    : (unsigned)std::chrono::system_clock::now().time_since_epoch().count();
         ensemble_.reset(new Ensemble_BDP_B200(4, move_group_, move_velocity_, N, e.T, e.Tc, seed));
+      } else if (e.type == 3) {
+        ensemble_.reset(new Ensemble_LAN_B200(3, N, e.T, e.Tc, (unsigned long long)rand())); // ensemble_lan.cu:39
+      } else if (e.type == 5) {
+        ensemble_.reset(new Ensemble_BAO_B200(5, N, e.T, e.Tc, (unsigned long long)rand())); // ensemble_bao.cu:39
+      } else if (e.type == 11) {
+        const double no_rate[3] = {0, 0, 0};
+        ensemble_.reset(new Ensemble_BER_B200(11, e.T, e.Tc, e.target_p, e.num_p, e.p_coupling, 0, 0, 0, no_rate));
       } else {
         ensemble_.reset(new Ensemble_NHC_B200(2, move_group_, move_velocity_, N, e.T, e.Tc, time_step_));
       }

@@ -75,12 +75,20 @@ SIGNATURES = {
     "b200md_bdp_create": (C.c_int, [C.c_longlong, C.c_double, C.c_double, C.c_uint, C.POINTER(_vp)]),
     "b200md_bdp_destroy": (None, [_vp]),
     "b200md_bdp_step": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "b200md_langevin_create": (C.c_int, [C.c_int, C.c_ulonglong, C.POINTER(_vp)]),
+    "b200md_langevin_destroy": (None, [_vp]),
+    "b200md_langevin_apply": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp]),
+    "b200md_baoab_operator": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp,
+                                        C.c_int, _vp]),
+    "b200md_berendsen_pressure": (C.c_int, [C.c_int, C.c_int, C.c_int, _dp, _dp, _ip, _dp, _ip, _dp, _vp,
+                                            _vp, _vp]),
     "b200md_apply_pbc_strided": (C.c_int, [C.c_int, C.c_int, _dp, _ip, _vp, _vp]),
     "b200md_velocity_verlet_strided": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp]),
     "b200md_find_thermo_strided": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_double, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "b200md_halo_pack": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _dp, _vp, _vp]),
     "b200md_nep_invalidate": (C.c_int, [_vp, C.c_int, _vp]),
     "b200md_nep_set_owned": (C.c_int, [_vp, C.c_int]),
+    "b200md_nep_set_active_region": (C.c_int, [_vp, _dp, _dp]),
     "b200md_tc_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
 }
 

@@ -41,7 +41,9 @@ bool b200md_make_potential(
 bool b200md_make_ensemble(
   const int type, const int move_group, const double* move_velocity, const int number_of_atoms,
   const double temperature, const double temperature_coupling, const double time_step,
-  std::unique_ptr<Ensemble>& ensemble)
+  const double* target_pressure, const int num_target_pressure_components,
+  const double* pressure_coupling, const int deform_x, const int deform_y, const int deform_z,
+  const double* deform_rate, std::unique_ptr<Ensemble>& ensemble)
 {
   if (!b200md_enabled())
     return false;
@@ -65,6 +67,19 @@ bool b200md_make_ensemble(
         type, move_group, move_velocity, number_of_atoms, temperature, temperature_coupling, seed));
       break;
     }
+    case 3: // the reference seeds cuRAND with rand() (ensemble_lan.cu:39): same call, same stream
+      ensemble.reset(new Ensemble_LAN_B200(
+        type, number_of_atoms, temperature, temperature_coupling, (unsigned long long)rand()));
+      break;
+    case 5:
+      ensemble.reset(new Ensemble_BAO_B200(
+        type, number_of_atoms, temperature, temperature_coupling, (unsigned long long)rand()));
+      break;
+    case 11:
+      ensemble.reset(new Ensemble_BER_B200(
+        type, temperature, temperature_coupling, target_pressure, num_target_pressure_components,
+        pressure_coupling, deform_x, deform_y, deform_z, deform_rate));
+      break;
     default: return false; // every other ensemble stays with the reference's own class
   }
   printf("Use the b200md integrator for ensemble type %d.\n", type);

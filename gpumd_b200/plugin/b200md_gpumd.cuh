@@ -19,7 +19,11 @@ bool b200md_make_potential(
   const char* potential_name, const char* potential_file, const int number_of_atoms,
   std::unique_ptr<Potential>& potential);
 
+// target_pressure / pressure_coupling / deform*: the npt_ber parameters as Integrate holds them at
+// initialize() (natural units); ignored for the other types
 bool b200md_make_ensemble(
   const int type, const int move_group, const double* move_velocity, const int number_of_atoms,
   const double temperature, const double temperature_coupling, const double time_step,
-  std::unique_ptr<Ensemble>& ensemble);
+  const double* target_pressure, const int num_target_pressure_components,
+  const double* pressure_coupling, const int deform_x, const int deform_y, const int deform_z,
+  const double* deform_rate, std::unique_ptr<Ensemble>& ensemble);

@@ -226,6 +226,37 @@ void b200md_bdp_destroy(b200md_bdp* p);
 int b200md_bdp_step(
   b200md_bdp* p, int n, int stride, const double* d_thermo, double* d_velocity, void* stream);
 
+/* Langevin thermostats and the Berendsen barostat:
+ *   b200md_langevin_*         <- curand states + gpu_langevin + momentum correction,
+ *                                src/integrate/langevin_utilities.cuh:26-127; one apply() = one
+ *                                Ensemble_LAN::integrate_nvt_lan_half (ensemble_lan.cu:92-124, c1 =
+ *                                exp(-0.5/Tc)) or Ensemble_BAO::integrate_nvt_lan (ensemble_bao.cu:91-120,
+ *                                c1 = exp(-1/Tc)); c2 = sqrt((1-c1^2) k_B T).  cuRAND XORWOW,
+ *                                curand_init(seed, atom, 0): seed 1804289383 (glibc's first rand())
+ *                                reproduces the stream of the reference's -DDEBUG build when model.xyz
+ *                                carries the velocities.
+ *   b200md_baoab_operator     <- gpu_operator_A (which = 0) / gpu_operator_B (which = 1),
+ *                                ensemble_bao.cu:190-300; d_group_label may be NULL (fixed_group -1)
+ *   b200md_berendsen_pressure <- Ensemble_BER::compute2, NPT branch (ensemble_ber.cu:88-172,237-285):
+ *                                num_components 1 (isotropic), 3 (orthogonal, optional deform) or 6
+ *                                (triclinic, Voigt order); target_pressure / pressure_coupling in
+ *                                natural units as integrate.cu:1150-1153 leaves them; h[9] (HOST) is
+ *                                updated in place, positions are scaled on the device.  Reads
+ *                                d_thermo[2..7] back, i.e. synchronises the stream, as the reference. */
+typedef struct b200md_langevin b200md_langevin;
+int b200md_langevin_create(int n, unsigned long long seed, b200md_langevin** out);
+void b200md_langevin_destroy(b200md_langevin* p);
+int b200md_langevin_apply(
+  b200md_langevin* p, int n, int stride, double c1, double c2, const double* d_mass,
+  double* d_velocity, void* stream);
+int b200md_baoab_operator(
+  int which, int n, int stride, double time_step, const double* d_mass, double* d_position,
+  double* d_velocity, const double* d_force, const int* d_group_label, int fixed_group, void* stream);
+int b200md_berendsen_pressure(
+  int n, int stride, int num_components, const double target_pressure[6],
+  const double pressure_coupling[6], const int deform[3], const double deform_rate[3],
+  const int pbc[3], double h[9], const double* d_thermo, double* d_position, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Spatial-domain sharding (replaces the hub-and-spoke scatter/gather of NEP_MULTIGPU,
  * src/force/nep_multigpu.cu:1249-1310,1552-1582,1764-1802).  A rank keeps ONE set of local SoA
@@ -255,6 +286,13 @@ int b200md_nep_invalidate(b200md_nep* p, int n_new, void* stream);
  * whose results the owner rank computes and the local rank would discard
  * (cf. nep_multigpu.cu:1764-1802, which copies back the owned range only). */
 int b200md_nep_set_owned(b200md_nep* p, int n_owned);
+/* Atoms whose position (in the coordinates passed to b200md_nep_compute) lies outside [lo, hi) get
+ * EMPTY radial / angular neighbour sets from the following calls: no descriptor, dU/dq or partial-
+ * force work is spent on them, they only serve as neighbours of the others.  A spatial domain sets
+ * this to its owned region grown by rc + skin: ghosts further away cannot be a neighbour of an owned
+ * atom, so nothing an owned atom's force depends on is skipped (the reference recomputes descriptors
+ * for its whole ghost layer, nep_multigpu.cu:1476-1545).  lo = hi = NULL switches it off. */
+int b200md_nep_set_active_region(b200md_nep* p, const double lo[3], const double hi[3]);
 
 /* ---------------------------------------------------------------------------------------------
  * Tensor-core self-test (no reference counterpart): one CTA computes D[128 x N] = A[128 x K] .

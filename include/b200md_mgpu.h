@@ -64,19 +64,28 @@ int b200md_mgpu_distribute(
  * included.  Asynchronous apart from the displacement check every `check_every` steps. */
 int b200md_mgpu_run(b200md_mgpu* g, int nsteps, int check_every);
 
+/* the same, bracketed by CUDA events on the module's stream: *ms_out = device time of the nsteps
+ * (synchronises before and after) */
+int b200md_mgpu_run_timed(b200md_mgpu* g, int nsteps, int check_every, double* ms_out);
+
 /* global thermo[0..7] = T, U, sxx, syy, szz, sxy, sxz, syz (synchronises) */
 int b200md_mgpu_thermo(b200md_mgpu* g, double out8[8]);
 /* global heat current jx_in, jx_out, jy_in, jy_out, jz (compute_heat.cu:32-90 summed, hac.cu:51,106) */
 int b200md_mgpu_heat_current(b200md_mgpu* g, double out5[5]);
 
 /* counters: what = 0 local domains, 1 owned atoms of domain k, 2 local (owned+ghost) atoms of
- * domain k, 3 migrations so far, 4 neighbour rebuilds of domain k, 5 global rank of domain k */
+ * domain k, 3 migrations so far, 4 neighbour rebuilds of domain k, 5 global rank of domain k,
+ * 6 kernels launched per step (this module's + libb200md's, counted on the last eager step) */
 long long b200md_mgpu_info(b200md_mgpu* g, int what, int k);
 /* owned atoms of local domain k in GLOBAL coordinates: id[n], position[3n], velocity[3n],
  * force[3n], potential[n], virial[9n] (host arrays; any may be NULL) */
 int b200md_mgpu_get_owned(
   b200md_mgpu* g, int k, long long* id, double* position, double* velocity, double* force,
   double* potential, double* virial);
+/* the LOCAL system of domain k as the potential sees it: type[n_loc], position[3*n_loc] in the local
+ * frame (owned atoms first), local box h[9] and pbc[3] (host arrays; any may be NULL) */
+int b200md_mgpu_get_local(
+  b200md_mgpu* g, int k, int* type, double* position, double h_out[9], int pbc_out[3]);
 /* per-phase device time of the last b200md_mgpu_run when profiling was on (ms per step):
  * 0 vv1+wrap, 1 halo, 2 force, 3 vv2+thermo; returns the number of phases written */
 int b200md_mgpu_profile(b200md_mgpu* g, int enable, double* ms_out, int max_out);

@@ -457,3 +457,44 @@ class RefNepCpu:
         pe, f, v = np.zeros(n), np.zeros(3 * n), np.zeros(9 * n)
         self.R.refnep_compute(self.h, n, _i(type_), _d(h), _d(pos), _d(pe), _d(f), _d(v))
         return dict(pe=pe, force=f.reshape(3, n), virial=v.reshape(9, n))
+
+
+# ---- BAOAB operators and the Berendsen barostat (test infrastructure) ----------
+def baoab_operator(which, dt, mass, pos, vel, force, label=None, fixed_group=-1):
+    """gpu_operator_A (which = 0: x += v dt/2) / gpu_operator_B (which = 1: v += f/m dt/2) with the fixed
+    group frozen, src/integrate/ensemble_bao.cu:190-300."""
+    p, v = np.array(pos, dtype=np.float64), np.array(vel, dtype=np.float64)
+    fixed = np.zeros(p.shape[1], bool) if label is None or fixed_group < 0 else (np.asarray(label) == fixed_group)
+    if which == 0:
+        p += np.where(fixed, 0.0, v) * (dt * 0.5)
+    else:
+        v = np.where(fixed, 0.0, v + np.asarray(force) / np.asarray(mass)[None, :] * (dt * 0.5))
+    return p, v
+
+
+def berendsen_pressure(h, pbc, thermo, target_p, p_coupling, num_components):
+    """cpu_pressure_isotropic / _orthogonal / _triclinic, src/integrate/ensemble_ber.cu:88-172 (no
+    deformation): returns (new h[9], mu[9]); positions transform as r <- mu r.  thermo[2..7] = sxx syy szz
+    sxy sxz syz; target_p / p_coupling in natural units, Voigt order xx yy zz yz xz xy for 6 components."""
+    h = np.array(h, dtype=np.float64).reshape(9)
+    p = np.asarray(thermo, dtype=np.float64)[2:8]
+    p0, pc = np.asarray(target_p, dtype=np.float64), np.asarray(p_coupling, dtype=np.float64)
+    mu = np.eye(3).reshape(9)
+    if num_components == 1:
+        sfac = 1.0 - pc[0] * (p0[0] - (p[0] + p[1] + p[2]) * 0.3333333333333333)
+        mu[[0, 4, 8]] = sfac
+        h[[0, 4, 8]] *= sfac
+    elif num_components == 3:
+        for d in range(3):
+            sfac = 1.0 - pc[d] * (p0[d] - p[d]) if pbc[d] else 1.0
+            mu[4 * d] = sfac
+            h[4 * d] *= sfac
+    else:
+        mu[0] = 1.0 - pc[0] * (p0[0] - p[0])
+        mu[4] = 1.0 - pc[1] * (p0[1] - p[1])
+        mu[8] = 1.0 - pc[2] * (p0[2] - p[2])
+        mu[3] = mu[1] = -pc[5] * (p0[5] - p[3])
+        mu[6] = mu[2] = -pc[4] * (p0[4] - p[4])
+        mu[7] = mu[5] = -pc[3] * (p0[3] - p[5])
+        h = (mu.reshape(3, 3) @ h.reshape(3, 3)).reshape(9)
+    return h, mu

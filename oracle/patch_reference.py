@@ -44,7 +44,8 @@ def main():
         g, "  switch (type) {\n    case 0: // NVE\n",
         "  if (!b200md_make_ensemble(\n"
         "        type, move_group, move_velocity, number_of_atoms, temperature, temperature_coupling,\n"
-        "        time_step, ensemble))\n", "Integrate::initialize hook")
+        "        time_step, target_pressure, num_target_pressure_components, pressure_coupling,\n"
+        "        deform_x, deform_y, deform_z, deform_rate, ensemble))\n", "Integrate::initialize hook")
     (out / "integrate").mkdir(parents=True, exist_ok=True)
     (out / "integrate" / "integrate.cu").write_text(g)
     print("patched copies written to", out)

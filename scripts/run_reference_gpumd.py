@@ -36,9 +36,23 @@ def write_model(path, s, symbols, vel=None):
 ONLY = None  # --only REGEX: run just the matching cases
 
 
-def run_case(name, s, symbols, potential, run_in, vel=None, timeout=900):
+def run_case(name, s, symbols, potential, run_in, vel=None, timeout=900, gpus=1):
+    """gpus > 1: that many visible devices -> the reference takes its NEP_MULTIGPU path
+    (src/force/force.cu:139-160); skipped when the box has fewer."""
     if ONLY and not re.search(ONLY, name):
         return None, None
+    import os
+    env = dict(os.environ)
+    if gpus > 1:
+        try:
+            import torch
+            have = torch.cuda.device_count()
+        except Exception:
+            have = 1
+        if have < gpus:
+            print(f"skip {name}: needs {gpus} GPUs, box has {have}")
+            return None, None
+    env["CUDA_VISIBLE_DEVICES"] = ",".join(str(k) for k in range(gpus))
     d = OUT / name
     shutil.rmtree(d, ignore_errors=True)
     d.mkdir(parents=True)
@@ -46,7 +60,7 @@ def run_case(name, s, symbols, potential, run_in, vel=None, timeout=900):
     write_model(d / "model.xyz", s, symbols, vel)
     (d / "run.in").write_text("potential potential.txt\n" + run_in)
     t0 = time.time()
-    r = subprocess.run([str(BIN)], cwd=d, capture_output=True, text=True, timeout=timeout)
+    r = subprocess.run([str(BIN)], cwd=d, capture_output=True, text=True, timeout=timeout, env=env)
     wall = time.time() - t0
     (d / "stdout.txt").write_text(r.stdout[-20000:] + "\n--- stderr ---\n" + r.stderr[-5000:])
     speed = re.findall(r"Speed of this run = ([0-9.eE+-]+) atom\*step/second", r.stdout)
@@ -110,6 +124,9 @@ def main():
     vel = init_velocities(s["mass"], 300.0, seed=42)
     d, i = run_case("md_pbte", s, pbte_sym, GOLDEN / "nep_PbTe.txt", md.format(dt=1, steps=200), vel)
     infos.append(i)
+    # the same start through the reference's multi-GPU path (2 visible devices)
+    d, i = run_case("md_pbte_2gpu", s, pbte_sym, GOLDEN / "nep_PbTe.txt", md.format(dt=1, steps=200), vel, gpus=2)
+    infos.append(i)
     s = fcc(25, 5.30, rattle=0.0, seed=1)  # 62 500 atoms
     vel = init_velocities(s["mass"], 80.0, seed=42)
     d, i = run_case("md_lj", s, ["Ar"], GOLDEN / "lj_Ar_10A.txt", md.format(dt=5, steps=200), vel)
@@ -124,8 +141,11 @@ def main():
     s = rocksalt_pbte(20, rattle=0.02, seed=1)
     vel = init_velocities(s["mass"], 300.0, seed=42)
     # ... and Bussi-Donadio-Parrinello: the reference binary is built -DDEBUG, i.e. std::mt19937(12345678)
+    # Langevin / BAOAB: cuRAND seeded with rand(), which is glibc's first value (1804289383) in a -DDEBUG
+    # build when model.xyz carries the velocities; npt_ber: isotropic, 0 GPa, 50 GPa modulus, tau_p 1000
     for name, ens in (("md_pbte_nhc", "nvt_nhc 300 300 100"), ("md_pbte_ber", "nvt_ber 300 300 100"),
-                      ("md_pbte_bdp", "nvt_bdp 300 300 100")):
+                      ("md_pbte_bdp", "nvt_bdp 300 300 100"), ("md_pbte_lan", "nvt_lan 300 300 100"),
+                      ("md_pbte_bao", "nvt_bao 300 300 100"), ("md_pbte_npt", "npt_ber 300 300 100 0 50 1000")):
         d, i = run_case(name, s, pbte_sym, GOLDEN / "nep_PbTe.txt",
                         f"ensemble {ens}\ntime_step 1\ndump_thermo 10\nrun 200\n", vel)
         infos.append(i)

@@ -11,7 +11,7 @@ from test_kernel_bodies_cpu import check_fv
 pytestmark = pytest.mark.gpu
 
 
-def run_nve(eng, s, pot_file, steps, dt_fs, temperature, seed=42, every=None, ensemble="nve"):
+def run_nve(eng, s, pot_file, steps, dt_fs, temperature, seed=42, every=None, ensemble="nve", T_target=300.0):
     import torch
     n = s["type"].shape[0]
     vel = init_velocities(s["mass"], temperature, seed)
@@ -20,13 +20,19 @@ def run_nve(eng, s, pot_file, steps, dt_fs, temperature, seed=42, every=None, en
     force = eng.Force()
     pot = force.parse_potential(pot_file, n)
     if ensemble == "nvt_ber":
-        ens = eng.Ensemble_BER(n, 300.0, 100.0)
+        ens = eng.Ensemble_BER(n, T_target, 100.0)
     elif ensemble == "nvt_nhc":
-        ens = eng.Ensemble_NHC(n, 300.0, 100.0, dt_fs / TIME_UNIT_CONVERSION)
+        ens = eng.Ensemble_NHC(n, T_target, 100.0, dt_fs / TIME_UNIT_CONVERSION)
     elif ensemble == "nvt_nhc_dt1":  # chain masses from a 1 fs step whatever dt is (a former driver bug)
-        ens = eng.Ensemble_NHC(n, 300.0, 100.0, 1.0 / TIME_UNIT_CONVERSION)
+        ens = eng.Ensemble_NHC(n, T_target, 100.0, 1.0 / TIME_UNIT_CONVERSION)
+    elif ensemble == "nvt_lan":
+        ens = eng.Ensemble_LAN(n, T_target, 100.0)
+    elif ensemble == "nvt_bao":
+        ens = eng.Ensemble_BAO(n, T_target, 100.0)
+    elif ensemble == "npt_ber":  # `ensemble npt_ber 300 300 100 0 50 1000` (isotropic, 50 GPa modulus)
+        ens = eng.Ensemble_NPT_BER(n, T_target, 100.0, [0.0], [50.0], 1000.0)
     elif ensemble == "nvt_bdp":
-        ens = eng.Ensemble_BDP(n, 300.0, 100.0)
+        ens = eng.Ensemble_BDP(n, T_target, 100.0)
     else:
         ens = eng.Ensemble_NVE(n)
     thermo = torch.zeros(8, dtype=torch.float64, device="cuda")
@@ -93,7 +99,8 @@ def read_thermo(path):
     return np.array(rows, dtype=np.float64)
 
 
-@pytest.mark.parametrize("case", ["md_pbte", "md_lj", "md_si", "md_pbte_nhc", "md_pbte_ber", "md_pbte_bdp"])
+@pytest.mark.parametrize("case", ["md_pbte", "md_lj", "md_si", "md_pbte_nhc", "md_pbte_ber", "md_pbte_bdp",
+                                  "md_pbte_lan", "md_pbte_bao", "md_pbte_npt"])
 def test_nve_trajectory_matches_reference_gpu(eng_mod, case):
     """tests/golden/refgpu_md_*_thermo.out: thermo.out (every 10 steps, 200 steps) written by the
     unmodified reference gpumd on a B200 from the same positions and velocities
@@ -106,7 +113,9 @@ def test_nve_trajectory_matches_reference_gpu(eng_mod, case):
     ensemble = "nve"
     if case.startswith("md_pbte"):
         s, pot_file, dt, T0 = rocksalt_pbte(20, rattle=0.02, seed=1), GOLDEN / "nep_PbTe.txt", 1.0, 300.0
-        if case != "md_pbte":
+        if case == "md_pbte_npt":
+            ensemble = "npt_ber"
+        elif case != "md_pbte":
             ensemble = "nvt_" + case.split("_")[-1]
     elif case == "md_si":
         s, pot_file, dt, T0 = diamond(20, a=5.431, rattle=0.0, seed=1), GOLDEN / "tersoff_Si_1989.txt", 1.0, 300.0

@@ -1,0 +1,201 @@
+"""libb200md_mgpu (C++ / CUDA / NCCL block decomposition, include/b200md_mgpu.h).
+
+Local mode runs ALL domains of a Px x Py x Pz grid on one GPU in lock step through exactly the entry
+points, kernels, ghost lists and message layout of the distributed run (device copies stand in for
+ncclSend/Recv), so the decomposition is checked against the ORACLE on the driver's single-GPU box;
+the NCCL transport itself is covered by the 2-process test below (needs 2 GPUs)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT
+from gpumd_b200.structures import TIME_UNIT_CONVERSION, diamond, fcc, init_velocities, rocksalt_pbte
+from test_kernel_bodies_cpu import check_fv
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mg():
+    import torch
+    from gpumd_b200 import build
+    build.build_lib()
+    build.build_mgpu()
+    assert torch.cuda.is_available()
+    from gpumd_b200 import mgpu
+    return mgpu
+
+
+@pytest.mark.parametrize("grid", [(2, 1, 1), (2, 2, 1), (2, 2, 2), (3, 1, 2)])
+def test_blocks_match_the_oracle_single_point(oracle, mg, grid):
+    """Forces / energies / virials of every owned atom of every block against the FP32 oracle evaluated
+    on the WHOLE periodic system (same tolerances as the single-domain parity tests)."""
+    s = rocksalt_pbte(14, rattle=0.05, seed=3)  # 21 952 atoms, 92 A: three 30.7 A blocks > 17 A halo
+    n = s["type"].shape[0]
+    g = mg.DomainGroup(s["h"], s["pbc"], grid, GOLDEN / "nep_PbTe.txt")
+    g.distribute(s["type"], s["pos"], s["mass"])
+    assert g.num_local_domains == grid[0] * grid[1] * grid[2]
+    out = g.gather_local()
+    assert np.array_equal(out["id"], np.arange(n))
+    orc = oracle.NepOracle(GOLDEN / "nep_PbTe.txt")
+    r = orc.compute(s["type"], s["h"], s["pbc"], s["pos"], precision=32)
+    r64 = orc.compute(s["type"], s["h"], s["pbc"], s["pos"], precision=64)
+    # atol + the FP32 restatement's own distance from FP64 on this input, as in check_nep
+    check_fv(out, r, gap_f=np.abs(r["force"] - r64["force"]).max(), gap_v=np.abs(r["virial"] - r64["virial"]).max())
+    assert abs(out["pe"].sum() - r["pe"].sum()) / n < 1e-6
+    # thermo of the decomposed system = sum over blocks
+    th = g.thermo()
+    assert abs(th[1] - r["pe"].sum()) < 1e-6 * n
+
+
+@pytest.mark.parametrize("ensemble", ["nve", "nvt_nhc"])
+def test_blocks_follow_the_single_domain_trajectory(oracle, mg, ensemble):
+    """200 steps on 2x2x2 blocks vs one domain (same library, no decomposition), then the state against
+    the oracle.  Hot enough (900 K, skin 1 A) that atoms cross block faces: migrations must happen."""
+    from gpumd_b200 import engine
+    from test_gpu_md import run_nve
+    s = rocksalt_pbte(12, rattle=0.02, seed=1)  # 13 824 atoms, 78.8 A -> 39.4 A blocks
+    n = s["type"].shape[0]
+    dt = 1.0 / TIME_UNIT_CONVERSION
+    vel = init_velocities(s["mass"], 900.0, seed=42)
+    g = mg.DomainGroup(s["h"], s["pbc"], (2, 2, 2), GOLDEN / "nep_PbTe.txt", ensemble=ensemble,
+                       temperature=900.0, temperature_coupling=100.0, time_step=dt, skin=1.0)
+    g.distribute(s["type"], s["pos"], s["mass"], vel)
+    g.run(200, check_every=5)
+    g.check()
+    assert g.migrations >= 1
+    th = g.thermo()
+    out = g.gather_local()
+    assert np.array_equal(out["id"], np.arange(n))
+    # single domain, same start
+    import test_gpu_md
+    atom, pot, rows = test_gpu_md.run_nve(engine, s, GOLDEN / "nep_PbTe.txt", 200, 1.0, 900.0, seed=42,
+                                          ensemble=ensemble, T_target=900.0)
+    ref = rows[-1]
+    assert abs(th[0] - ref[0]) < 0.05 and abs(th[1] - ref[1]) < 2e-6 * n
+    # and the decomposed state is self-consistent with the oracle at its own positions
+    orc = oracle.NepOracle(GOLDEN / "nep_PbTe.txt")
+    r = orc.compute(s["type"], s["h"], s["pbc"], out["pos"], precision=32)
+    r64 = orc.compute(s["type"], s["h"], s["pbc"], out["pos"], precision=64)
+    check_fv(out, r, gap_f=np.abs(r["force"] - r64["force"]).max(), gap_v=np.abs(r["virial"] - r64["virial"]).max())
+
+
+def read_thermo(path):
+    return np.array([ln.split()[:18] for ln in open(path) if not ln.startswith("#")], dtype=np.float64)
+
+
+@pytest.mark.parametrize("fixture,grid", [("refgpu_md_pbte_2gpu_thermo.out", (2, 1, 1)),
+                                          ("refgpu_md_pbte_thermo.out", (2, 2, 2))])
+def test_blocks_track_the_reference_gpu_trajectory(mg, fixture, grid):
+    """thermo.out of the UNMODIFIED reference for 64 000 PbTe atoms, NVE, 200 steps from given
+    velocities: written by its NEP_MULTIGPU path on 2 GPUs (refgpu_md_pbte_2gpu_thermo.out) and by its
+    single-GPU path (refgpu_md_pbte_thermo.out), scripts/run_reference_gpumd.py.  Our decomposed run must
+    track both like the single-domain run does (test_gpu_md.py)."""
+    if not (GOLDEN / fixture).exists():
+        pytest.skip(f"{fixture} not generated yet (needs a 2-GPU box)")
+    s = rocksalt_pbte(20, rattle=0.02, seed=1)
+    n = s["type"].shape[0]
+    ref = read_thermo(GOLDEN / fixture)
+    g = mg.DomainGroup(s["h"], s["pbc"], grid, GOLDEN / "nep_PbTe.txt", time_step=1.0 / TIME_UNIT_CONVERSION, skin=1.0)
+    g.distribute(s["type"], s["pos"], s["mass"], init_velocities(s["mass"], 300.0, seed=42))
+    rows = []
+    for _ in range(20):
+        g.run(10, check_every=5)
+        rows.append(g.thermo())
+    g.check()
+    mine = np.array(rows)
+    for k in range(20):
+        tol = 2e-5 * (1 + k)
+        assert abs(mine[k, 0] - ref[k, 0]) < tol * 3000, (k, mine[k, 0], ref[k, 0])
+        assert abs(mine[k, 1] - ref[k, 2]) < tol * abs(ref[k, 2]), (k, mine[k, 1], ref[k, 2])
+        for c in range(3):
+            assert abs(mine[k, 2 + c] * 1.602177e+2 - ref[k, 3 + c]) < 2e-3 + 1e-3 * abs(ref[k, 3 + c])
+    assert abs(mine[0, 0] - ref[0, 0]) < 2e-3 and abs(mine[0, 1] - ref[0, 2]) / n < 2e-7
+
+
+@pytest.mark.parametrize("case", ["lj", "si"])
+def test_blocks_other_potentials(oracle, mg, case):
+    """Pair (halo rc + skin) and FP64 many-body (halo 2 rc + skin) potentials through the same blocks."""
+    if case == "lj":
+        s = fcc(12, 5.30, rattle=0.1, seed=5)  # 6912 atoms, 63.6 A
+        g = mg.DomainGroup(s["h"], s["pbc"], (2, 2, 1), GOLDEN / "lj_Ar_10A.txt")
+        g.distribute(s["type"], s["pos"], s["mass"])
+        out = g.gather_local()
+        r = oracle.lj_compute(np.array([[[1.032e-2, 3.405, 10.0]]]), s["type"], s["h"], s["pbc"], s["pos"])
+        check_fv(out, r)
+    else:
+        s = diamond(8, a=5.431, rattle=0.08, seed=6)  # 4096 atoms, 43.4 A
+        g = mg.DomainGroup(s["h"], s["pbc"], (2, 2, 2), GOLDEN / "tersoff_Si_1989.txt")
+        g.distribute(s["type"], s["pos"], s["mass"], init_velocities(s["mass"], 300.0, seed=1))
+        out = g.gather_local()
+        nt, p0 = oracle.tersoff_parameters(GOLDEN / "tersoff_Si_1989.txt")
+        r = oracle.tersoff_compute(nt, p0, s["type"], s["h"], s["pbc"], s["pos"])
+        assert np.allclose(out["force"], r["force"], rtol=1e-9, atol=1e-10)
+        assert np.allclose(out["pe"], r["pe"], rtol=1e-10, atol=1e-12)
+        j = g.heat_current()
+        assert np.isfinite(j).all()
+
+
+def test_cuda_graph_replay_is_bit_identical(mg):
+    """The per-step CUDA graph (all launches + the staged halo copies of one step) replays to the same
+    trajectory as eager launches."""
+    s = rocksalt_pbte(12, rattle=0.02, seed=1)
+    dt = 1.0 / TIME_UNIT_CONVERSION
+    vel = init_velocities(s["mass"], 300.0, seed=42)
+    res = []
+    for graph in (False, True):
+        g = mg.DomainGroup(s["h"], s["pbc"], (2, 1, 1), GOLDEN / "nep_PbTe.txt", time_step=dt, skin=3.0,
+                           cuda_graph=graph)
+        g.distribute(s["type"], s["pos"], s["mass"], vel)
+        g.run(50, check_every=5)
+        g.check()
+        res.append(g.gather_local())
+    assert np.array_equal(res[0]["pos"], res[1]["pos"]) and np.array_equal(res[0]["vel"], res[1]["vel"])
+
+
+WORKER = r"""
+import os, sys, json
+import numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, os.environ["B2_ROOT"]); sys.path.insert(0, os.path.join(os.environ["B2_ROOT"], "tests"))
+from gpumd_b200 import mgpu
+from gpumd_b200.structures import TIME_UNIT_CONVERSION, init_velocities, rocksalt_pbte
+rank = int(os.environ["RANK"]); torch.cuda.set_device(int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl")
+s = rocksalt_pbte(12, rattle=0.02, seed=1)
+vel = init_velocities(s["mass"], 300.0, seed=42)
+g = mgpu.DomainGroup(s["h"], s["pbc"], (2, 1, 1), os.environ["B2_MODEL"], time_step=1.0 / TIME_UNIT_CONVERSION,
+                     skin=1.0, distributed=True)
+g.distribute(s["type"], s["pos"], s["mass"], vel)
+g.run(100, check_every=5); g.check()
+o = g.owned(0)
+np.savez(os.path.join(os.environ["B2_OUT"], f"rank{rank}.npz"), thermo=g.thermo(), **o)
+dist.barrier(); dist.destroy_process_group()
+"""
+
+
+def test_two_ranks_over_nccl_match_the_local_run(mg, tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    (tmp_path / "worker.py").write_text(WORKER)
+    env = dict(os.environ, B2_ROOT=str(ROOT), B2_MODEL=str(GOLDEN / "nep_PbTe.txt"), B2_OUT=str(tmp_path))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29533", str(tmp_path / "worker.py")],
+                       env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-3000:]
+    parts = [np.load(tmp_path / f"rank{k}.npz") for k in range(2)]
+    ids = np.concatenate([p["id"] for p in parts])
+    order = np.argsort(ids)
+    pos = np.concatenate([p["pos"] for p in parts], axis=1)[:, order]
+    s = rocksalt_pbte(12, rattle=0.02, seed=1)
+    g = mg.DomainGroup(s["h"], s["pbc"], (2, 1, 1), GOLDEN / "nep_PbTe.txt", time_step=1.0 / TIME_UNIT_CONVERSION,
+                       skin=1.0)
+    g.distribute(s["type"], s["pos"], s["mass"], init_velocities(s["mass"], 300.0, seed=42))
+    g.run(100, check_every=5)
+    loc = g.gather_local()
+    assert np.array_equal(np.sort(ids), np.arange(s["type"].shape[0]))
+    assert np.array_equal(pos, loc["pos"])  # same kernels, same message order: bit-identical
+    assert np.allclose(parts[0]["thermo"], g.thermo(), rtol=1e-13)
