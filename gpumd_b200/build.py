@@ -18,7 +18,7 @@ LIB = PKG / "libb200md.so"
 OBJ = PKG / "build"
 
 CU_SOURCES = ["b2_host.cu", "b2_neighbor.cu", "b2_nep.cu", "b2_md.cu", "b2_tersoff.cu", "b2_eam.cu",
-              "b2_tc_test.cu", "b2_stochastic.cu"]
+              "b2_tc_test.cu", "b2_stochastic.cu", "b2_measure.cu"]
 CPP_SOURCES = ["b2_nep_model.cpp"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -234,7 +234,7 @@ __global__ void k_export_q(B2NepView P, int n_cell, float* out)
   if (a >= n_cell)
     return;
   for (int d = 0; d < P.dim; ++d)
-    out[(size_t)d * n_cell + a] = P.q[(size_t)d * P.n + i] * P.q_scaler[d];
+    out[(size_t)d * n_cell + a] = P.q[(size_t)i * P.qs + d] * P.q_scaler[d];
 }
 
 // ---- small periodic boxes: evaluate a supercell, keep the first replica -----------------------
@@ -341,7 +341,7 @@ int dispatch_desc_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
   } else if (p->radial_v2) {
     const B2NepView& P = p->view;
     B2RadialDescArgs A;
-    A.n = P.n; A.nt = P.nt; A.nr1 = P.nr1; A.mn_r = P.mn_r; A.mn_a = P.mn_a;
+    A.n = P.n; A.nt = P.nt; A.nr1 = P.nr1; A.mn_r = P.mn_r; A.mn_a = P.mn_a; A.qs = P.qs;
     A.plane0 = p->nb.plane0.p; A.plane1 = p->nb.plane1.p;
     A.nn_skin = P.nn_skin; A.nl_skin = P.nl_skin;
     A.nn_r = P.nn_r; A.nl_r = P.nl_r; A.nn_a = P.nn_a; A.nl_a = P.nl_a;
@@ -610,10 +610,10 @@ int nep_setup(b200md_nep* p, int num_atoms)
   B2_CUDA(p->nl_r.reserve(N * (size_t)pitch_r));
   B2_CUDA(p->nn_a.reserve(N));
   B2_CUDA(p->nl_a.reserve(N * m.MN_angular));
-  B2_CUDA(p->q.reserve(N * m.dim));
+  B2_CUDA(p->q.reserve(N * ((m.dim + 3) / 4 * 4)));
   B2_CUDA(p->sfx.reserve(N * m.na1 * B2_NABC));
   B2_CUDA(p->FpR.reserve(N * m.nr1));
-  B2_CUDA(p->FpA.reserve(N * m.dim_angular));
+  B2_CUDA(p->FpA.reserve(N * ((m.dim_angular + 3) / 4 * 4) + 4));
   B2_CUDA(p->U.reserve(N * m.UST));
   B2_CUDA(p->f12.reserve(N * 3 * m.MN_angular));
   B2_CUDA(p->acc.reserve(N)); // site energies from the MLP pass
@@ -633,6 +633,8 @@ int nep_setup(b200md_nep* p, int num_atoms)
   P.has1111 = m.has1111;
   P.num_L = m.num_L;
   P.dim = m.dim;
+  P.qs = (m.dim + 3) / 4 * 4;
+  P.fas = (m.dim_angular + 3) / 4 * 4;
   P.dim_ang = m.dim_angular;
   P.nneu = m.nneu;
   P.DIMP = m.DIMP;

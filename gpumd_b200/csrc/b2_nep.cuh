@@ -85,10 +85,15 @@ struct B2NepView {
   int* nl_r; // [mn_r * n]
   int* nn_a;
   int* nl_a; // [mn_a * n]
-  float* q;   // [dim * n]   unscaled descriptors
+  // descriptors and dU/dq(angular) are AoS ROWS per atom: the tensor-core hidden layer gathers /
+  // scatters rows by type tile, and a row is one run of full sectors whichever atom it belongs to
+  // (SoA columns made that kernel move 2.3x (PbTe) to 4x (16 types) its algorithmic bytes)
+  int qs;       // row stride of q   (dim rounded up to a multiple of 4)
+  int fas;      // row stride of FpA (dim_ang rounded up to a multiple of 4)
+  float* q;   // [n * qs]   unscaled descriptors, q[i*qs + d]
   float* sfx; // [na1*24 * n] angular sums s[n][abc]
   float* FpR; // [nr1 * n]     dU/dq, radial part (input of k_utable)
-  float* FpA; // [dim_ang * n] dU/dq (already multiplied by q_scaler), angular part
+  float* FpA; // [n * fas] dU/dq (already multiplied by q_scaler), angular part, FpA[i*fas + d]
   float* U;   // [n * UST]   pre-contracted radial table
   float* f12; // [3 * mn_a * n]
   double* acc; // [13 * n]: pe, fx,fy,fz, virial xx,yy,zz,xy,xz,yz,yx,zx,zy (sorted order)
@@ -258,7 +263,7 @@ B2_HD void b2_body_desc_radial(
     P.nn_r[i] = 0;
     P.nn_a[i] = 0;
     for (int n = 0; n < P.nr1; ++n)
-      P.q[(size_t)n * P.n + i] = 0.0f;
+      P.q[(size_t)i * P.qs + n] = 0.0f;
     return;
   }
   const int nn = SPLIT ? P.nn_skin[i] : P.nn_r[i];
@@ -357,7 +362,7 @@ B2_HD void b2_body_desc_radial(
           q = fmaf(B2_LDG(&c[k]), a[(size_t)k * stride], q);
       }
     }
-    P.q[(size_t)n * P.n + i] = q;
+    P.q[(size_t)i * P.qs + n] = q;
   }
 }
 
@@ -499,7 +504,7 @@ B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
     for (int c = 0; c < NCH; ++c) {
       const int n = n0 + c;
       if (n < P.na1) {
-        float* qa = P.q + (size_t)P.nr1 * P.n + i; // q[(nr1 + L*na1 + n) * N + i]
+        float* qa = P.q + (size_t)i * P.qs + P.nr1; // q[i*qs + nr1 + L*na1 + n]
         // 3-body invariants, L = 1..4
         int st = 0;
 #pragma unroll
@@ -509,7 +514,7 @@ B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
           for (int k = 1; k < 2 * L + 1; ++k)
             v = fmaf(C3B[st + k] * s[c][st + k], s[c][st + k], v);
           v = 2.0f * v + C3B[st] * s[c][st] * s[c][st];
-          qa[(size_t)((L - 1) * P.na1 + n) * P.n] = v;
+          qa[(L - 1) * P.na1 + n] = v;
           st += 2 * L + 1;
         }
         int Lidx = 4;
@@ -518,12 +523,12 @@ B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
           const float v = B2_C4B0 * t[0] * t[0] * t[0] + B2_C4B1 * t[0] * (t[1] * t[1] + t[2] * t[2]) +
                           B2_C4B2 * t[0] * (t[3] * t[3] + t[4] * t[4]) +
                           B2_C4B3 * t[3] * (t[2] * t[2] - t[1] * t[1]) + B2_C4B4 * t[1] * t[2] * t[4];
-          qa[(size_t)(Lidx * P.na1 + n) * P.n] = v;
+          qa[Lidx * P.na1 + n] = v;
           ++Lidx;
         }
         if (P.has1111) {
           const float s0 = s[c][0] * s[c][0], tt = s[c][1] * s[c][1] + s[c][2] * s[c][2];
-          qa[(size_t)(Lidx * P.na1 + n) * P.n] = B2_C5B0 * s0 * s0 + B2_C5B1 * s0 * tt + B2_C5B2 * tt * tt;
+          qa[Lidx * P.na1 + n] = B2_C5B0 * s0 * s0 + B2_C5B1 * s0 * tt + B2_C5B2 * tt * tt;
           ++Lidx;
         }
 #pragma unroll
@@ -548,7 +553,7 @@ B2_HD void b2_body_mlp(
   float q[DIMP], Fp[DIMP];
 #pragma unroll
   for (int d = 0; d < DIMP; ++d) {
-    q[d] = (d < P.dim) ? P.q[(size_t)d * P.n + i] * B2_LDG(&P.q_scaler[d]) : 0.0f;
+    q[d] = (d < P.dim) ? P.q[(size_t)i * P.qs + d] * B2_LDG(&P.q_scaler[d]) : 0.0f;
     Fp[d] = 0.0f;
   }
   const float4* w0 = reinterpret_cast<const float4*>(w0_all + (size_t)t * P.nneu * DIMP);
@@ -592,7 +597,7 @@ B2_HD void b2_body_mlp(
     if (d < P.nr1)
       P.FpR[(size_t)d * P.n + i] = Fp[d];
     else if (d < P.dim)
-      P.FpA[(size_t)(d - P.nr1) * P.n + i] = Fp[d];
+      P.FpA[(size_t)i * P.fas + (d - P.nr1)] = Fp[d];
   }
 }
 
@@ -833,7 +838,7 @@ B2_HD void b2_body_force_angular(int i, const B2NepView& P, const B2Box& box, fl
     int st = 0;
 #pragma unroll
     for (int L = 1; L <= 4; ++L) {
-      const float F = P.FpA[(size_t)((L - 1) * P.na1 + n) * N + i];
+      const float F = P.FpA[(size_t)i * P.fas + (L - 1) * P.na1 + n];
       wv[st] = 2.0f * F * C3B[st] * s[st];
 #pragma unroll
       for (int k = 1; k < 2 * L + 1; ++k)
@@ -842,7 +847,7 @@ B2_HD void b2_body_force_angular(int i, const B2NepView& P, const B2Box& box, fl
     }
     int Lidx = 4;
     if (P.has222) {
-      const float F = P.FpA[(size_t)(Lidx * P.na1 + n) * N + i];
+      const float F = P.FpA[(size_t)i * P.fas + Lidx * P.na1 + n];
       const float* t = &s[3];
       wv[3] += F * (3.0f * B2_C4B0 * t[0] * t[0] + B2_C4B1 * (t[1] * t[1] + t[2] * t[2]) +
                     B2_C4B2 * (t[3] * t[3] + t[4] * t[4]));
@@ -853,7 +858,7 @@ B2_HD void b2_body_force_angular(int i, const B2NepView& P, const B2Box& box, fl
       ++Lidx;
     }
     if (P.has1111) {
-      const float F = P.FpA[(size_t)(Lidx * P.na1 + n) * N + i];
+      const float F = P.FpA[(size_t)i * P.fas + Lidx * P.na1 + n];
       const float tt = s[1] * s[1] + s[2] * s[2];
       wv[0] += F * (4.0f * B2_C5B0 * s[0] * s[0] * s[0] + 2.0f * B2_C5B1 * tt * s[0]);
       wv[1] += F * (2.0f * B2_C5B1 * s[0] * s[0] * s[1] + 4.0f * B2_C5B2 * tt * s[1]);
@@ -1257,7 +1262,7 @@ B2_HD void b2_team_desc_radial(int i, int l, const B2NepView& P, const B2Box& bo
           q = fmaf(B2_LDG(&c[k]), S[t][k], q);
       }
     }
-    P.q[(size_t)n * N + i] = q;
+    P.q[(size_t)i * P.qs + n] = q;
   }
 }
 

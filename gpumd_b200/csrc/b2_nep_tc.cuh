@@ -92,12 +92,24 @@ __global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
     cur_type = t;
     // ---- stage Q (scaled descriptors) as the A operand: row tid, four columns per store.
     //      16 columns are fetched at a time so that their (strided) loads are all in flight ----
+    // this thread's row q[i*qs .. +dim) is one contiguous run (qs is a multiple of 4: float4 loads)
+    const float4* qrow = reinterpret_cast<const float4*>(P.q + (size_t)(i >= 0 ? i : 0) * P.qs);
     for (int c0 = 0; c0 < DK; c0 += 16) {
       float v[16];
 #pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float4 t = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (i >= 0 && c0 + 4 * g < P.qs)
+          t = qrow[c0 / 4 + g];
+        v[4 * g] = t.x;
+        v[4 * g + 1] = t.y;
+        v[4 * g + 2] = t.z;
+        v[4 * g + 3] = t.w;
+      }
+#pragma unroll
       for (int c = 0; c < 16; ++c) {
         const int d = c0 + c;
-        v[c] = (i >= 0 && d < P.dim) ? P.q[(size_t)d * N + i] * __ldg(&P.q_scaler[d]) : 0.0f;
+        v[c] = (i >= 0 && d < P.dim) ? v[c] * __ldg(&P.q_scaler[d]) : 0.0f;
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -200,7 +212,7 @@ __global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
           const int d = c0 + c;
           if (d < P.dim) {
             if (d >= P.nr1)
-              P.FpA[(size_t)(d - P.nr1) * N + i] = f[c];
+              P.FpA[(size_t)i * P.fas + (d - P.nr1)] = f[c];
             else if (N3 == 0)
               P.FpR[(size_t)d * N + i] = f[c];
           }

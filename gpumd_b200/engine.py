@@ -295,6 +295,42 @@ def compute_heat(atom, heat=None):
     return heat
 
 
+class HAC:
+    """compute_hac, src/measure/hac.cu:32-280: sample the total heat current every sample_interval steps,
+    then the autocorrelation hac[5, Nc] and the running thermal conductivity rtc[5, Nc] (W/mK)."""
+
+    def __init__(self, number_of_steps, sample_interval, Nc):
+        _require_cuda()
+        self._L = _lib.load()
+        self.Nc, self.Nd = int(Nc), int(number_of_steps) // int(sample_interval)
+        self.sample_interval = int(sample_interval)
+        h = C.c_void_p()
+        _lib.check(self._L.b200md_hac_create(int(number_of_steps), int(sample_interval), int(Nc), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.b200md_hac_destroy(self._h)
+            self._h = None
+
+    def process(self, step, atom):
+        n = atom.number_of_atoms
+        _lib.check(self._L.b200md_hac_sample(self._h, int(step), n, n, _ptr(atom.virial_per_atom),
+                                             _ptr(atom.velocity_per_atom), _stream()))
+
+    def series(self):
+        out = np.zeros(5 * self.Nd)
+        _lib.check(self._L.b200md_hac_series(self._h, out.ctypes.data_as(C.POINTER(C.c_double)), _stream()))
+        return out.reshape(5, self.Nd)
+
+    def postprocess(self, time_step, temperature, volume):
+        hac, rtc = np.zeros(5 * self.Nc), np.zeros(5 * self.Nc)
+        dp = C.POINTER(C.c_double)
+        _lib.check(self._L.b200md_hac_finish(self._h, float(time_step), float(temperature), float(volume),
+                                             hac.ctypes.data_as(dp), rtc.ctypes.data_as(dp), _stream()))
+        return hac.reshape(5, self.Nc), rtc.reshape(5, self.Nc)
+
+
 class Force:
     """Force driver, src/force/force.cu: parse_potential (75-218) and compute (771-985)."""
 

@@ -326,6 +326,12 @@ private:
     int precision = 2;
     bool mass = false, velocity = false, force = false, potential = false, virial = false;
   } dump_xyz_;
+  // compute_hac sample_interval Nc output_interval (measure/hac.cu:262-300); reset after each run
+  double hac_temperature_ = 300.0; // the temperature of the last thermostatted ensemble line (run.cu passes
+                                   // integrate.temperature2 to the measurements; an nve line leaves it)
+  struct HacSpec {
+    int interval = 0, Nc = 0, output_interval = 1;
+  } hac_spec_;
   double global_time_ = 0.0; // natural units, as Run::global_time (run.cu:316)
   bool state_on_gpu_ = false;
   bool has_potential_ = false;
@@ -462,6 +468,8 @@ private:
                     "nvt_bao T T tau | npt_ber T T tau p.. C.. tau_p");
       }
       ensemble_spec_ = e;
+      if (e.type != 0)
+        hac_temperature_ = e.T;
     } else if (t[0] == "fix") {
       // fix group_id | fix grouping_method group_id
       if (t.size() != 2 && t.size() != 3)
@@ -497,6 +505,16 @@ private:
       if (t.size() != 2 || std::atoi(t[1].c_str()) <= 0)
         input_error("dump_thermo should have 1 positive parameter (the interval).");
       dump_thermo_ = std::atoi(t[1].c_str());
+    } else if (t[0] == "compute_hac") {
+      if (t.size() != 4)
+        input_error("compute_hac should have 3 parameters.");
+      hac_spec_.interval = std::atoi(t[1].c_str());
+      hac_spec_.Nc = std::atoi(t[2].c_str());
+      hac_spec_.output_interval = std::atoi(t[3].c_str());
+      if (hac_spec_.interval <= 0 || hac_spec_.Nc <= 0 || hac_spec_.output_interval <= 0)
+        input_error("compute_hac parameters should be positive integers.");
+      printf("Compute HAC.\n    sample interval is %d.\n    Nc is %d\n    output_interval is %d\n",
+             hac_spec_.interval, hac_spec_.Nc, hac_spec_.output_interval);
     } else if (t[0] == "dump_restart") {
       if (t.size() != 2 || std::atoi(t[1].c_str()) <= 0)
         input_error("dump_restart should have 1 positive parameter (the interval).");
@@ -513,6 +531,7 @@ private:
       perform_a_run(std::atoi(t[1].c_str()));
       fixed_group_ = move_group_ = -1;
       fixed_method_ = move_method_ = 0;
+      hac_spec_ = HacSpec();
       dump_thermo_ = 0; // non-propagating keywords are reset after each run (run.cu:329-340)
       dump_restart_ = 0;
       dump_xyz_ = XyzDump();
@@ -783,6 +802,11 @@ private:
     force_.compute(model_.box, a.position_per_atom, a.type, a.potential_per_atom, a.force_per_atom,
                    a.virial_per_atom);
     force_.potentials[0]->check();
+    b200md_hac* hac = nullptr;
+    if (hac_spec_.interval > 0) {
+      if (b200md_hac_create(number_of_steps, hac_spec_.interval, hac_spec_.Nc, &hac) != B200MD_OK)
+        input_error(std::string("compute_hac: ") + b200md_last_error());
+    }
     printf("Run %d steps.\n", number_of_steps);
     const auto t0 = std::chrono::high_resolution_clock::now();
     for (int step = 0; step < number_of_steps; ++step) {
@@ -790,6 +814,9 @@ private:
       force_.compute(model_.box, a.position_per_atom, a.type, a.potential_per_atom, a.force_per_atom,
                      a.virial_per_atom);
       ensemble_->compute2(time_step_, model_.group, model_.box, a, thermo_);
+      if (hac && b200md_hac_sample(hac, step, a.number_of_atoms, a.number_of_atoms,
+                                   a.virial_per_atom.data(), a.velocity_per_atom.data(), nullptr) != B200MD_OK)
+        b2h_fail("compute_hac");
       ++global_step_;
       global_time_ += time_step_;
       if (fid && (step + 1) % dump_thermo_ == 0)
@@ -807,6 +834,29 @@ private:
     printf("Speed of this run = %g atom*step/second.\n", a.number_of_atoms * (double)number_of_steps / sec);
     if (fid)
       fclose(fid);
+    if (hac) { // HAC::postprocess, hac.cu:186-258: hac.out = t(ps), 5 hac averages, 5 rtc averages
+      const int Nc = hac_spec_.Nc, oi = hac_spec_.output_interval;
+      std::vector<double> h((size_t)5 * Nc), r((size_t)5 * Nc);
+      if (b200md_hac_finish(hac, time_step_, ensemble_spec_.type == 0 ? hac_temperature_ : ensemble_spec_.T,
+                            model_.box.get_volume(), h.data(), r.data(), nullptr) != B200MD_OK)
+        b2h_fail("compute_hac");
+      const double dt_in_ps = time_step_ * hac_spec_.interval * TIME_UNIT_CONVERSION / 1000.0;
+      FILE* fh = fopen("hac.out", "a");
+      for (int nd = 0; nd < Nc / oi; ++nd) {
+        const int nc = nd * oi;
+        fprintf(fh, "%25.15e", (nc + oi * 0.5) * dt_in_ps);
+        for (int pass = 0; pass < 2; ++pass)
+          for (int k = 0; k < 5; ++k) {
+            double ave = 0.0;
+            for (int m = 0; m < oi; ++m)
+              ave += (pass == 0 ? h : r)[(size_t)Nc * k + nc + m];
+            fprintf(fh, "%25.15e", ave / oi);
+          }
+        fprintf(fh, "\n");
+      }
+      fclose(fh);
+      b200md_hac_destroy(hac);
+    }
   }
 };
 

@@ -75,6 +75,11 @@ SIGNATURES = {
     "b200md_bdp_create": (C.c_int, [C.c_longlong, C.c_double, C.c_double, C.c_uint, C.POINTER(_vp)]),
     "b200md_bdp_destroy": (None, [_vp]),
     "b200md_bdp_step": (C.c_int, [_vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "b200md_hac_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.POINTER(_vp)]),
+    "b200md_hac_destroy": (None, [_vp]),
+    "b200md_hac_sample": (C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "b200md_hac_finish": (C.c_int, [_vp, C.c_double, C.c_double, C.c_double, _dp, _dp, _vp]),
+    "b200md_hac_series": (C.c_int, [_vp, _dp, _vp]),
     "b200md_langevin_create": (C.c_int, [C.c_int, C.c_ulonglong, C.POINTER(_vp)]),
     "b200md_langevin_destroy": (None, [_vp]),
     "b200md_langevin_apply": (C.c_int, [_vp, C.c_int, C.c_int, C.c_double, C.c_double, _vp, _vp, _vp]),

@@ -226,6 +226,26 @@ void b200md_bdp_destroy(b200md_bdp* p);
 int b200md_bdp_step(
   b200md_bdp* p, int n, int stride, const double* d_thermo, double* d_velocity, void* stream);
 
+/* Heat-current autocorrelation, SURVEY.md 8f rank 4.  Replaces HAC::preprocess / process /
+ * postprocess (src/measure/hac.cu:32-280):
+ *   b200md_hac_create  <- preprocess: Nd = number_of_steps / sample_interval records of 5 components
+ *   b200md_hac_sample  <- process: call every step; on (step+1) % sample_interval == 0 it runs
+ *                         compute_heat (compute_heat.cu:32-90) and sums jx_in jx_out jy_in jy_out jz
+ *   b200md_hac_finish  <- postprocess: hac[nc + Nc*k] (gpu_find_hac, :111-170) and the running thermal
+ *                         conductivity rtc[nc + Nc*k] in W/mK (find_rtc, :173-181; factor dt/2/(kB T^2 V)
+ *                         * 1.573769e5); host output arrays of 5*Nc doubles; time_step in natural units
+ *   b200md_hac_series  <- the recorded heat-current series [nd + Nd*k] (5*Nd doubles, host) */
+typedef struct b200md_hac b200md_hac;
+int b200md_hac_create(int number_of_steps, int sample_interval, int Nc, b200md_hac** out);
+void b200md_hac_destroy(b200md_hac* p);
+int b200md_hac_sample(
+  b200md_hac* p, int step, int n, int stride, const double* d_virial, const double* d_velocity,
+  void* stream);
+int b200md_hac_finish(
+  b200md_hac* p, double time_step, double temperature, double volume, double* hac_out,
+  double* rtc_out, void* stream);
+int b200md_hac_series(b200md_hac* p, double* out, void* stream);
+
 /* Langevin thermostats and the Berendsen barostat:
  *   b200md_langevin_*         <- curand states + gpu_langevin + momentum correction,
  *                                src/integrate/langevin_utilities.cuh:26-127; one apply() = one

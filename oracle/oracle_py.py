@@ -498,3 +498,26 @@ def berendsen_pressure(h, pbc, thermo, target_p, p_coupling, num_components):
         mu[7] = mu[5] = -pc[3] * (p0[3] - p[5])
         h = (mu.reshape(3, 3) @ h.reshape(3, 3)).reshape(9)
     return h, mu
+
+
+# ---- heat-current autocorrelation (test infrastructure) -------------------------
+def find_hac(heat_all, Nc, dt_sample, temperature, volume):
+    """gpu_find_hac + find_rtc, src/measure/hac.cu:111-181.  heat_all[5, Nd] = jx_in jx_out jy_in jy_out jz;
+    returns hac[5, Nc], rtc[5, Nc] (W/mK).  dt_sample = time_step * sample_interval, natural units."""
+    K_B, KAPPA = 8.617343e-5, 1.573769e+5
+    h = np.asarray(heat_all, dtype=np.float64)
+    Nd = h.shape[1]
+    hac = np.zeros((5, Nc))
+    for nc in range(Nc):
+        a, b = slice(0, Nd - nc), slice(nc, Nd)
+        hac[0, nc] = np.sum(h[0, a] * h[0, b] + h[0, a] * h[1, b])
+        hac[1, nc] = np.sum(h[1, a] * h[1, b] + h[1, a] * h[0, b])
+        hac[2, nc] = np.sum(h[2, a] * h[2, b] + h[2, a] * h[3, b])
+        hac[3, nc] = np.sum(h[3, a] * h[3, b] + h[3, a] * h[2, b])
+        hac[4, nc] = np.sum(h[4, a] * h[4, b])
+        hac[:, nc] /= Nd - nc
+    factor = dt_sample * 0.5 / (K_B * temperature * temperature * volume) * KAPPA
+    rtc = np.zeros((5, Nc))
+    for nc in range(1, Nc):
+        rtc[:, nc] = rtc[:, nc - 1] + (hac[:, nc - 1] + hac[:, nc]) * factor
+    return hac, rtc

@@ -5,11 +5,13 @@ T=${TAG:-r02_two}
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=index,name --format=csv > gpurun_out/${T}_gpus.txt 2>&1
 echo "== reference gpumd, 2 GPUs (NEP_MULTIGPU) fixture"
-timeout 900 python scripts/run_reference_gpumd.py --skip-speed --only 'md_pbte_2gpu' 2>&1 | tail -15
-cp gpurun_out/refgpu/md_pbte_2gpu/thermo.out gpurun_out/${T}_refgpu_md_pbte_2gpu_thermo.out 2>/dev/null
-cp gpurun_out/refgpu/md_pbte_2gpu/thermo.out tests/golden/refgpu_md_pbte_2gpu_thermo.out 2>/dev/null
+timeout 900 python scripts/run_reference_gpumd.py --skip-speed --only 'md_pbte_(2gpu|lan|bao|npt)' 2>&1 | tail -40
+for c in 2gpu lan bao npt; do
+  cp gpurun_out/refgpu/md_pbte_$c/thermo.out gpurun_out/${T}_refgpu_md_pbte_${c}_thermo.out 2>/dev/null
+  cp gpurun_out/refgpu/md_pbte_$c/thermo.out tests/golden/refgpu_md_pbte_${c}_thermo.out 2>/dev/null
+done
 echo "== pytest (multi-GPU tests)"
-timeout 1500 python -m pytest tests/test_gpu_mgpu.py tests/test_gpu_domain.py -m gpu -q 2>&1 | tail -25 | tee gpurun_out/${T}_pytest.txt
+timeout 1500 python -m pytest tests/test_gpu_mgpu.py tests/test_gpu_domain.py tests/test_gpu_stochastic.py tests/test_gpu_md.py -m gpu -q 2>&1 | tail -45 | tee gpurun_out/${T}_pytest.txt
 for g in ${BENCH_GPUS:-1 2}; do
   echo "== bench N=$g"
   if [ "$g" = "1" ]; then

@@ -150,6 +150,14 @@ def main():
                         f"ensemble {ens}\ntime_step 1\ndump_thermo 10\nrun 200\n", vel)
         infos.append(i)
 
+    # heat-current autocorrelation: FP64 Tersoff, short run
+    s = diamond(10, a=5.431, rattle=0.08, seed=24)
+    vel = init_velocities(s["mass"], 300.0, seed=42)
+    d, i = run_case("hac_si", s, ["Si"], GOLDEN / "tersoff_Si_1989.txt",
+                    "ensemble nvt_ber 300 300 100\ntime_step 1\nrun 100\nensemble nve\ncompute_hac 2 50 1\nrun 400\n",
+                    vel)
+    infos.append(i)
+
     # ---- (3) throughput at the BASELINE sizes ----
     if not args.skip_speed:
         s = rocksalt_pbte(50, rattle=0.02, seed=1)  # C3: 1 000 000 atoms

@@ -93,6 +93,33 @@ def test_b200md_ensemble_is_built_at_run_with_the_final_time_step(tmp_path):
     assert abs(wrong[-2, 0] - ref[-1, 0]) > 1e-5 * ref[-1, 0]
 
 
+def test_b200md_compute_hac_matches_reference(tmp_path):
+    """compute_hac through the C++ driver against hac.out of the unmodified reference gpumd for the same
+    run.in / model.xyz (8000 Si atoms, Tersoff-1989 FP64, nvt_ber 100 steps then NVE 400 steps with
+    `compute_hac 2 50 1`; tests/golden/refgpu_hac_si.out, scripts/run_reference_gpumd.py)."""
+    from gpumd_b200 import build
+    if not (GOLDEN / "refgpu_hac_si.out").exists():
+        pytest.skip("refgpu_hac_si.out not generated yet")
+    exe = build.build_host()
+    s = diamond(10, a=5.431, rattle=0.08, seed=24)
+    vel = init_velocities(s["mass"], 300.0, seed=42)
+    write_xyz(tmp_path / "model.xyz", s, ["Si"], vel)
+    shutil.copyfile(GOLDEN / "tersoff_Si_1989.txt", tmp_path / "potential.txt")
+    (tmp_path / "run.in").write_text(
+        "potential potential.txt\nensemble nvt_ber 300 300 100\ntime_step 1\nrun 100\n"
+        "ensemble nve\ncompute_hac 2 50 1\nrun 400\n")
+    r = subprocess.run([str(exe)], cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    mine = np.loadtxt(tmp_path / "hac.out")
+    ref = np.loadtxt(GOLDEN / "refgpu_hac_si.out")
+    assert mine.shape == ref.shape == (50, 11)
+    assert np.array_equal(mine[:, 0], ref[:, 0])  # correlation times
+    # FP64 force field, same integrator: 500 steps of chaotic divergence from 1e-13 stay far below this
+    scale = np.abs(ref[:, 1:6]).max()
+    assert np.allclose(mine[:, 1:6], ref[:, 1:6], rtol=1e-5, atol=1e-6 * scale)
+    assert np.allclose(mine[:, 6:], ref[:, 6:], rtol=1e-5, atol=1e-6 * np.abs(ref[:, 6:]).max())
+
+
 def test_b200md_rejects_unknown_keyword(tmp_path):
     from gpumd_b200 import build
     exe = build.build_host()

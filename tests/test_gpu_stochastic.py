@@ -116,3 +116,27 @@ def test_langevin_ensembles_thermalise_to_the_target(eng, ensemble):
     _, _, rows = run_nve(eng, s, GOLDEN / "nep_PbTe.txt", 1500, 1.0, 50.0, seed=42, every=100, ensemble=ensemble)
     T = rows[8:-1, 0]
     assert abs(T.mean() - 300.0) < 6.0, T
+
+
+def test_hac_matches_restatement(oracle, eng):
+    """compute_hac (hac.cu:32-280): the sampled heat-current series against compute_heat's restatement
+    summed on the host, then hac / rtc against the numpy restatement of gpu_find_hac + find_rtc."""
+    import torch
+    rng = np.random.default_rng(5)
+    n, steps, interval, Nc = 20_011, 120, 3, 25
+    atom = eng.Atom(np.zeros(n, np.int32), np.zeros((3, n)), np.ones(n), np.zeros((3, n)))
+    hac = eng.HAC(steps, interval, Nc)
+    want = np.zeros((5, steps // interval))
+    for step in range(steps):
+        if (step + 1) % interval == 0:
+            v, w = rng.normal(size=(3, n)), rng.normal(size=(9, n))
+            atom.velocity_per_atom.copy_(torch.as_tensor(v.reshape(-1)))
+            atom.virial_per_atom.copy_(torch.as_tensor(w.reshape(-1)))
+            want[:, (step + 1) // interval - 1] = oracle.compute_heat(w, v).sum(axis=1)
+        hac.process(step, atom)
+    got = hac.series()
+    assert np.allclose(got, want, rtol=1e-12, atol=1e-9)
+    dt, T, V = 0.0982, 300.0, 5.0e4
+    h, r = hac.postprocess(dt, T, V)
+    h0, r0 = oracle.find_hac(got, Nc, dt * interval, T, V)
+    assert np.allclose(h, h0, rtol=1e-12, atol=1e-9) and np.allclose(r, r0, rtol=1e-12, atol=1e-9)
