@@ -215,6 +215,7 @@ struct Pot {
     if (name.rfind("nep", 0) == 0) {
       kind = 0;
       MG_B2(b200md_nep_create(file, cap, (b200md_nep**)&h));
+      MG_B2(b200md_nep_set_accumulate((b200md_nep*)h, 0));
       rc = b200md_nep_rc((b200md_nep*)h);
     } else if (name == "lj") {
       kind = 1;
@@ -801,7 +802,8 @@ int compute_force(Group& G)
 {
   for (auto& dp : G.dom) {
     Domain& D = *dp;
-    MG_B2(b200md_zero_properties(D.n_loc, D.pe.p, D.force.p, D.virial.p, G.stream));
+    if (D.pot.kind != 0) // NEP stores its outputs (set_accumulate(0) at creation): no zeroing pass
+      MG_B2(b200md_zero_properties(D.n_loc, D.pe.p, D.force.p, D.virial.p, G.stream));
     MG_TRY(D.pot.compute(D.n_loc, D.lh, D.lpbc, D.type.p, D.pos.p, D.pe.p, D.force.p, D.virial.p, G.stream));
   }
   return B200MD_OK;

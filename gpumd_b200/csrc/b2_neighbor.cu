@@ -326,6 +326,8 @@ B2NeighborView Neighbor::view() const
   v.atoms_tmp = atoms_tmp.p;
   v.plane0 = planes ? plane0.p : nullptr;
   v.plane1 = planes ? plane1.p : nullptr;
+  v.planez = planes ? planez.p : nullptr;
+  v.tag_types = tag_types ? 1 : 0;
   v.snap = snap.p;
   v.perm = perm.p;
   v.perm_tmp = perm_tmp.p;
@@ -433,6 +435,7 @@ int Neighbor::enable_planes()
 {
   B2_CUDA(plane0.reserve(capacity));
   B2_CUDA(plane1.reserve(capacity));
+  B2_CUDA(planez.reserve(capacity));
   planes = true;
   return B200MD_OK;
 }

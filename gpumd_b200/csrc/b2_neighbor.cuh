@@ -34,6 +34,11 @@ struct B2NeighborView {
   // many 128-byte lines as with the 32-byte records (8 atoms per line instead of 4); null = off
   int4* plane0 = nullptr;
   int4* plane1 = nullptr;
+  double* planez = nullptr; // z alone (8 bytes, 16 atoms per line) for consumers that get the type elsewhere
+  // 1: skin-list entries carry the neighbour's type in bits 30+ (entry = j | type << 30; needs
+  //    n < 2^30 and <= 2 types).  The type of an atom is constant between rebuilds, and a consumer that
+  //    reads it from the entry saves a gather.  Only the few-type NEP kernels ask for this.
+  int tag_types = 0;
   double* snap;      // [3n] positions at the last rebuild, sorted order (x0,y0,z0 SoA)
   int* perm;         // [n] sorted index -> caller index
   int* perm_tmp;     // [n]
@@ -76,6 +81,7 @@ B2_HD void b2_store_planes(const B2NeighborView& v, int i, const B2Atom& a)
     hi.w = 0;
     v.plane0[i] = lo;
     v.plane1[i] = hi;
+    v.planez[i] = a.z;
   }
 #else
   (void)v;
@@ -221,10 +227,12 @@ B2_HD void b2_body_skin_list(
           if (j == i)
             continue;
           float x12, y12, z12;
-          b2_r12(geo, box, a1, v.atoms[j], x12, y12, z12);
+          const B2Atom a2 = v.atoms[j];
+          b2_r12(geo, box, a1, a2, x12, y12, z12);
           if (b2_d2(x12, y12, z12) < cutoff2) {
             if (count < v.mn_skin)
-              v.nl_skin[(size_t)i * v.skin_si + (size_t)count * v.skin_sk] = j;
+              v.nl_skin[(size_t)i * v.skin_si + (size_t)count * v.skin_sk] =
+                v.tag_types ? (j | (a2.type << 30)) : j;
             ++count;
           }
         }

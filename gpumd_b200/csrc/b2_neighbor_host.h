@@ -22,7 +22,9 @@ public:
 
   DevBuf<B2Atom> atoms, atoms_tmp;
   DevBuf<int4> plane0, plane1; // see B2NeighborView::plane0 (enable_planes)
+  DevBuf<double> planez;
   bool planes = false;
+  bool tag_types = false; // see B2NeighborView::tag_types (set before the first update)
   DevBuf<double> snap;
   DevBuf<int> perm, perm_tmp, cell_of, order_tmp, cell_count, cell_fill, cell_start, nn_skin,
     nl_skin, flags;

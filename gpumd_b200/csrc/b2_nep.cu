@@ -132,6 +132,32 @@ __global__ void __launch_bounds__(BLK) k_utable(B2NepView P)
   __shared__ float tile[BLK][KP + 1];
   const int base = blockIdx.x * BLK;
   const int i = base + threadIdx.x;
+  if (P.u_planes == 2) { // compact planes of the few-type kernels (b2_nep_radial.cuh)
+    if (i < P.n) {
+      constexpr int KQ = (K1 - 1) / 4;
+      const int t = P.atoms[i].type;
+      float4* U4 = reinterpret_cast<float4*>(P.U);
+      float* Uf = P.U + (size_t)P.nt * KQ * 4 * P.n;
+      for (int t2 = 0; t2 < P.nt; ++t2) {
+        const float* c = P.c_r + (size_t)(t * P.nt + t2) * P.nr1 * K1;
+        float u[K1];
+#pragma unroll
+        for (int k = 0; k < K1; ++k)
+          u[k] = 0.0f;
+        for (int n = 0; n < P.nr1; ++n) {
+          const float f = P.FpR[(size_t)n * P.n + i];
+#pragma unroll
+          for (int k = 0; k < K1; ++k)
+            u[k] = fmaf(f, __ldg(&c[n * K1 + k]), u[k]);
+        }
+#pragma unroll
+        for (int q = 0; q < KQ; ++q)
+          U4[(size_t)(t2 * KQ + q) * P.n + i] = make_float4(u[4 * q], u[4 * q + 1], u[4 * q + 2], u[4 * q + 3]);
+        Uf[(size_t)t2 * P.n + i] = u[K1 - 1];
+      }
+    }
+    return;
+  }
   if (P.u_planes) {
     if (i < P.n)
       b2_body_utable_planes<K1>(i, P);
@@ -196,7 +222,7 @@ __global__ void __launch_bounds__(NTHR) k_force_angular(B2NepView P, B2Box box)
 // parity hooks ---------------------------------------------------------------------------------
 __global__ void k_export_list(
   int n, int n_cell, const int* perm, const int* nn, const int* nl, size_t si, size_t sk,
-  int mn_out, int* NN_out, int* NL_out, int* flags)
+  int mn_out, int* NN_out, int* NL_out, int* flags, int mask)
 {
   // n_cell < n: a supercell was evaluated; report the first replica with neighbour indices folded
   // back into the caller's cell (an atom then appears once per periodic image, like in the
@@ -214,7 +240,7 @@ __global__ void k_export_list(
   }
   int* row = NL_out + (size_t)a * mn_out;
   for (int k = 0; k < cnt; ++k) { // insertion sort into ascending caller index
-    const int v = perm[nl[(size_t)i * si + (size_t)k * sk]] % n_cell;
+    const int v = perm[nl[(size_t)i * si + (size_t)k * sk] & mask] % n_cell;
     int q = k - 1;
     while (q >= 0 && row[q] > v) {
       row[q + 1] = row[q];
@@ -234,7 +260,7 @@ __global__ void k_export_q(B2NepView P, int n_cell, float* out)
   if (a >= n_cell)
     return;
   for (int d = 0; d < P.dim; ++d)
-    out[(size_t)d * n_cell + a] = P.q[(size_t)i * P.qs + d] * P.q_scaler[d];
+    out[(size_t)d * n_cell + a] = P.q[(size_t)d * P.n + i] * P.q_scaler[d];
 }
 
 // ---- small periodic boxes: evaluate a supercell, keep the first replica -----------------------
@@ -258,16 +284,18 @@ __global__ void __launch_bounds__(BLK) k_replicate(
 
 // outputs of the first replica are the outputs of the original cell (+= convention)
 __global__ void __launch_bounds__(BLK) k_fold_replica(
-  int n, size_t nR, const double* __restrict__ acc, double* pe, double* force, double* virial)
+  int n, size_t nR, const double* __restrict__ acc, double* pe, double* force, double* virial,
+  int overwrite)
 {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n)
     return;
-  pe[i] += acc[i];
+  pe[i] = (overwrite ? 0.0 : pe[i]) + acc[i];
   for (int k = 0; k < 3; ++k)
-    force[(size_t)k * n + i] += acc[nR + (size_t)k * nR + i];
+    force[(size_t)k * n + i] = (overwrite ? 0.0 : force[(size_t)k * n + i]) + acc[nR + (size_t)k * nR + i];
   for (int k = 0; k < 9; ++k)
-    virial[(size_t)k * n + i] += acc[4 * nR + (size_t)k * nR + i];
+    virial[(size_t)k * n + i] =
+      (overwrite ? 0.0 : virial[(size_t)k * n + i]) + acc[4 * nR + (size_t)k * nR + i];
 }
 
 template <typename T>
@@ -341,8 +369,8 @@ int dispatch_desc_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
   } else if (p->radial_v2) {
     const B2NepView& P = p->view;
     B2RadialDescArgs A;
-    A.n = P.n; A.nt = P.nt; A.nr1 = P.nr1; A.mn_r = P.mn_r; A.mn_a = P.mn_a; A.qs = P.qs;
-    A.plane0 = p->nb.plane0.p; A.plane1 = p->nb.plane1.p;
+    A.n = P.n; A.nt = P.nt; A.nr1 = P.nr1; A.mn_r = P.mn_r; A.mn_a = P.mn_a;
+    A.plane0 = p->nb.plane0.p; A.plane1 = p->nb.plane1.p; A.planez = p->nb.planez.p;
     A.nn_skin = P.nn_skin; A.nl_skin = P.nl_skin;
     A.nn_r = P.nn_r; A.nl_r = P.nl_r; A.nn_a = P.nn_a; A.nl_a = P.nl_a;
     A.q = P.q; A.flags = P.flags;
@@ -405,17 +433,18 @@ int dispatch_force_final(
     const int g = grid_for(p->n, BLK);
     const int4* p0 = p->nb.plane0.p;
     const int4* p1 = p->nb.plane1.p;
+    const double* pz = p->nb.planez.p;
     // B200MD_NEP_VARIANT: resident blocks per SM the register allocation targets.  Measured on
     // 1 M-atom PbTe (profiles/r02_c_*): 5 blocks / 96 regs 0.927 ms (default), 6 blocks / 80 regs
     // with spills 1.03 ms, 4 blocks / 128 regs 0.959 ms
 #define B2_FF2(NT_, ORTHO_)                                                                      \
   do {                                                                                           \
     if (p->variant == 1)                                                                         \
-      k_force_final2<NT_, K1, ORTHO_, 6><<<g, BLK, 0, st>>>(p->view, p0, p1, box, pe, f, v);     \
+      k_force_final2<NT_, K1, ORTHO_, 6><<<g, BLK, 0, st>>>(p->view, p0, p1, pz, box, pe, f, v);     \
     else if (p->variant == 2)                                                                    \
-      k_force_final2<NT_, K1, ORTHO_, 4><<<g, BLK, 0, st>>>(p->view, p0, p1, box, pe, f, v);     \
+      k_force_final2<NT_, K1, ORTHO_, 4><<<g, BLK, 0, st>>>(p->view, p0, p1, pz, box, pe, f, v);     \
     else                                                                                         \
-      k_force_final2<NT_, K1, ORTHO_, 5><<<g, BLK, 0, st>>>(p->view, p0, p1, box, pe, f, v);     \
+      k_force_final2<NT_, K1, ORTHO_, 5><<<g, BLK, 0, st>>>(p->view, p0, p1, pz, box, pe, f, v);     \
   } while (0)
     if (p->model.nt == 1 && box.ortho)
       B2_FF2(1, true);
@@ -602,6 +631,7 @@ int nep_setup(b200md_nep* p, int num_atoms)
   const char* rad_env = std::getenv("B200MD_NEP_RADIAL");
   p->radial_v2 = m.nt <= 2 && !team && !(rad_env && std::strcmp(rad_env, "v1") == 0) &&
                  (double)num_atoms * (mn_skin + 2) < 4.0e9; // 32-bit list offsets in those kernels
+  p->nb.tag_types = p->radial_v2; // skin entries carry the neighbour type (b2_nep_radial.cuh)
   if (p->radial_v2)
     B2_TRY(p->nb.enable_planes());
   const int pitch_r = (m.MN_radial + 7) / 8 * 8;
@@ -610,10 +640,10 @@ int nep_setup(b200md_nep* p, int num_atoms)
   B2_CUDA(p->nl_r.reserve(N * (size_t)pitch_r));
   B2_CUDA(p->nn_a.reserve(N));
   B2_CUDA(p->nl_a.reserve(N * m.MN_angular));
-  B2_CUDA(p->q.reserve(N * ((m.dim + 3) / 4 * 4)));
+  B2_CUDA(p->q.reserve(N * m.dim));
   B2_CUDA(p->sfx.reserve(N * m.na1 * B2_NABC));
   B2_CUDA(p->FpR.reserve(N * m.nr1));
-  B2_CUDA(p->FpA.reserve(N * ((m.dim_angular + 3) / 4 * 4) + 4));
+  B2_CUDA(p->FpA.reserve(N * m.dim_angular));
   B2_CUDA(p->U.reserve(N * m.UST));
   B2_CUDA(p->f12.reserve(N * 3 * m.MN_angular));
   B2_CUDA(p->acc.reserve(N)); // site energies from the MLP pass
@@ -633,8 +663,6 @@ int nep_setup(b200md_nep* p, int num_atoms)
   P.has1111 = m.has1111;
   P.num_L = m.num_L;
   P.dim = m.dim;
-  P.qs = (m.dim + 3) / 4 * 4;
-  P.fas = (m.dim_angular + 3) / 4 * 4;
   P.dim_ang = m.dim_angular;
   P.nneu = m.nneu;
   P.DIMP = m.DIMP;
@@ -680,7 +708,7 @@ int nep_setup(b200md_nep* p, int num_atoms)
   P.acc = p->acc.p;
   P.flags = p->nb.flags.p;
   P.team = team ? 1 : 0;
-  P.u_planes = (team || p->radial_v2) ? 1 : 0;
+  P.u_planes = p->radial_v2 ? 2 : (team ? 1 : 0);
   P.pitch_r = pitch_r;
   {
     const B2NeighborView nv = p->nb.view();
@@ -841,7 +869,7 @@ int b200md_nep_compute(
     double* acc = p->rep_out.p;
     B2_TRY(nep_pipeline(p, box, st, acc, acc + nR, acc + 4 * (size_t)nR));
     k_fold_replica<<<grid_for(n, BLK), BLK, 0, st>>>(
-      n, (size_t)nR, acc, d_potential, d_force, d_virial);
+      n, (size_t)nR, acc, d_potential, d_force, d_virial, p->view.overwrite);
     B2_LAUNCHED();
     return B200MD_OK;
   }
@@ -890,13 +918,14 @@ int b200md_nep_export_neighbors(
     k_export_list<<<grid_for(n, 128), 128, 0, st>>>(
       n, p->rep_n ? p->rep_n : n, p->nb.perm.p, p->nn_r.p, p->nl_r.p,
       p->view.team ? (size_t)p->view.pitch_r : 1,
-      p->view.team ? 1 : (size_t)n, mn_r, d_NN_r, d_NL_r, p->nb.flags.p);
+      p->view.team ? 1 : (size_t)n, mn_r, d_NN_r, d_NL_r, p->nb.flags.p,
+      p->radial_v2 ? B2_TAG_MASK : -1);
     B2_LAUNCHED();
   }
   if (d_NN_a && d_NL_a) {
     k_export_list<<<grid_for(n, 128), 128, 0, st>>>(
       n, p->rep_n ? p->rep_n : n, p->nb.perm.p, p->nn_a.p, p->nl_a.p, 1, (size_t)n, mn_a, d_NN_a,
-      d_NL_a, p->nb.flags.p);
+      d_NL_a, p->nb.flags.p, -1);
     B2_LAUNCHED();
   }
   return B200MD_OK;
@@ -909,6 +938,12 @@ int b200md_nep_set_owned(b200md_nep* p, int n_owned)
     return B200MD_ERR_ARG;
   }
   p->view.n_own = n_owned;
+  return B200MD_OK;
+}
+
+int b200md_nep_set_accumulate(b200md_nep* p, int accumulate)
+{
+  p->view.overwrite = accumulate ? 0 : 1;
   return B200MD_OK;
 }
 

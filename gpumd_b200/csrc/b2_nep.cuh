@@ -85,15 +85,10 @@ struct B2NepView {
   int* nl_r; // [mn_r * n]
   int* nn_a;
   int* nl_a; // [mn_a * n]
-  // descriptors and dU/dq(angular) are AoS ROWS per atom: the tensor-core hidden layer gathers /
-  // scatters rows by type tile, and a row is one run of full sectors whichever atom it belongs to
-  // (SoA columns made that kernel move 2.3x (PbTe) to 4x (16 types) its algorithmic bytes)
-  int qs;       // row stride of q   (dim rounded up to a multiple of 4)
-  int fas;      // row stride of FpA (dim_ang rounded up to a multiple of 4)
-  float* q;   // [n * qs]   unscaled descriptors, q[i*qs + d]
+  float* q;   // [dim * n]   unscaled descriptors
   float* sfx; // [na1*24 * n] angular sums s[n][abc]
   float* FpR; // [nr1 * n]     dU/dq, radial part (input of k_utable)
-  float* FpA; // [n * fas] dU/dq (already multiplied by q_scaler), angular part, FpA[i*fas + d]
+  float* FpA; // [dim_ang * n] dU/dq (already multiplied by q_scaler), angular part
   float* U;   // [n * UST]   pre-contracted radial table
   float* f12; // [3 * mn_a * n]
   double* acc; // [13 * n]: pe, fx,fy,fz, virial xx,yy,zz,xy,xz,yz,yx,zx,zy (sorted order)
@@ -102,10 +97,13 @@ struct B2NepView {
   size_t skin_si, skin_sk; // B2NeighborView::skin_si / skin_sk
   int pitch_r;             // row pitch of nl_r when team != 0 (else nl_r is column-major)
   int team;                // 1: k_team_* kernels own the radial passes
-  int u_planes;            // 1: U is stored as float4 planes [(t*KP4+q)*n + i] (few-type kernels and
-                           //    lane teams), 0: AoS rows of UST floats (many-type path, tests/emu)
+  int u_planes;            // 0: U as AoS rows of UST floats (many-type path, tests/emu); 1: float4 planes
+                           //    [(t*KP4+q)*n + i] (lane teams); 2: compact planes of b2_nep_radial.cuh:
+                           //    KQ = (K1-1)/4 float4 planes [(t*KQ+q)*n + i] + a float plane [t*n + i]
   int n_own;               // > 0: only caller indices < n_own get outputs (domain decomposition:
                            // the rest are ghosts whose forces the caller discards)
+  int overwrite;           // 1: the final kernel STORES pe / force / virial instead of adding to them
+                           //    (b200md_nep_set_accumulate(p, 0): the caller skips its zeroing pass)
   int use_active;          // 1: atoms outside [act_lo, act_hi) get empty neighbour sets, i.e. no
   double act_lo[3];        //    descriptor / MLP-gradient / partial-force work: ghosts further than
   double act_hi[3];        //    rc from every owned atom only serve as neighbours (b200md_nep_set_active_region)
@@ -263,7 +261,7 @@ B2_HD void b2_body_desc_radial(
     P.nn_r[i] = 0;
     P.nn_a[i] = 0;
     for (int n = 0; n < P.nr1; ++n)
-      P.q[(size_t)i * P.qs + n] = 0.0f;
+      P.q[(size_t)n * P.n + i] = 0.0f;
     return;
   }
   const int nn = SPLIT ? P.nn_skin[i] : P.nn_r[i];
@@ -362,7 +360,7 @@ B2_HD void b2_body_desc_radial(
           q = fmaf(B2_LDG(&c[k]), a[(size_t)k * stride], q);
       }
     }
-    P.q[(size_t)i * P.qs + n] = q;
+    P.q[(size_t)n * P.n + i] = q;
   }
 }
 
@@ -504,7 +502,7 @@ B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
     for (int c = 0; c < NCH; ++c) {
       const int n = n0 + c;
       if (n < P.na1) {
-        float* qa = P.q + (size_t)i * P.qs + P.nr1; // q[i*qs + nr1 + L*na1 + n]
+        float* qa = P.q + (size_t)P.nr1 * P.n + i; // q[(nr1 + L*na1 + n) * N + i]
         // 3-body invariants, L = 1..4
         int st = 0;
 #pragma unroll
@@ -514,7 +512,7 @@ B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
           for (int k = 1; k < 2 * L + 1; ++k)
             v = fmaf(C3B[st + k] * s[c][st + k], s[c][st + k], v);
           v = 2.0f * v + C3B[st] * s[c][st] * s[c][st];
-          qa[(L - 1) * P.na1 + n] = v;
+          qa[(size_t)((L - 1) * P.na1 + n) * P.n] = v;
           st += 2 * L + 1;
         }
         int Lidx = 4;
@@ -523,12 +521,12 @@ B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
           const float v = B2_C4B0 * t[0] * t[0] * t[0] + B2_C4B1 * t[0] * (t[1] * t[1] + t[2] * t[2]) +
                           B2_C4B2 * t[0] * (t[3] * t[3] + t[4] * t[4]) +
                           B2_C4B3 * t[3] * (t[2] * t[2] - t[1] * t[1]) + B2_C4B4 * t[1] * t[2] * t[4];
-          qa[Lidx * P.na1 + n] = v;
+          qa[(size_t)(Lidx * P.na1 + n) * P.n] = v;
           ++Lidx;
         }
         if (P.has1111) {
           const float s0 = s[c][0] * s[c][0], tt = s[c][1] * s[c][1] + s[c][2] * s[c][2];
-          qa[Lidx * P.na1 + n] = B2_C5B0 * s0 * s0 + B2_C5B1 * s0 * tt + B2_C5B2 * tt * tt;
+          qa[(size_t)(Lidx * P.na1 + n) * P.n] = B2_C5B0 * s0 * s0 + B2_C5B1 * s0 * tt + B2_C5B2 * tt * tt;
           ++Lidx;
         }
 #pragma unroll
@@ -553,7 +551,7 @@ B2_HD void b2_body_mlp(
   float q[DIMP], Fp[DIMP];
 #pragma unroll
   for (int d = 0; d < DIMP; ++d) {
-    q[d] = (d < P.dim) ? P.q[(size_t)i * P.qs + d] * B2_LDG(&P.q_scaler[d]) : 0.0f;
+    q[d] = (d < P.dim) ? P.q[(size_t)d * P.n + i] * B2_LDG(&P.q_scaler[d]) : 0.0f;
     Fp[d] = 0.0f;
   }
   const float4* w0 = reinterpret_cast<const float4*>(w0_all + (size_t)t * P.nneu * DIMP);
@@ -597,7 +595,7 @@ B2_HD void b2_body_mlp(
     if (d < P.nr1)
       P.FpR[(size_t)d * P.n + i] = Fp[d];
     else if (d < P.dim)
-      P.FpA[(size_t)i * P.fas + (d - P.nr1)] = Fp[d];
+      P.FpA[(size_t)(d - P.nr1) * P.n + i] = Fp[d];
   }
 }
 
@@ -838,7 +836,7 @@ B2_HD void b2_body_force_angular(int i, const B2NepView& P, const B2Box& box, fl
     int st = 0;
 #pragma unroll
     for (int L = 1; L <= 4; ++L) {
-      const float F = P.FpA[(size_t)i * P.fas + (L - 1) * P.na1 + n];
+      const float F = P.FpA[(size_t)((L - 1) * P.na1 + n) * N + i];
       wv[st] = 2.0f * F * C3B[st] * s[st];
 #pragma unroll
       for (int k = 1; k < 2 * L + 1; ++k)
@@ -847,7 +845,7 @@ B2_HD void b2_body_force_angular(int i, const B2NepView& P, const B2Box& box, fl
     }
     int Lidx = 4;
     if (P.has222) {
-      const float F = P.FpA[(size_t)i * P.fas + Lidx * P.na1 + n];
+      const float F = P.FpA[(size_t)(Lidx * P.na1 + n) * N + i];
       const float* t = &s[3];
       wv[3] += F * (3.0f * B2_C4B0 * t[0] * t[0] + B2_C4B1 * (t[1] * t[1] + t[2] * t[2]) +
                     B2_C4B2 * (t[3] * t[3] + t[4] * t[4]));
@@ -858,7 +856,7 @@ B2_HD void b2_body_force_angular(int i, const B2NepView& P, const B2Box& box, fl
       ++Lidx;
     }
     if (P.has1111) {
-      const float F = P.FpA[(size_t)i * P.fas + Lidx * P.na1 + n];
+      const float F = P.FpA[(size_t)(Lidx * P.na1 + n) * N + i];
       const float tt = s[1] * s[1] + s[2] * s[2];
       wv[0] += F * (4.0f * B2_C5B0 * s[0] * s[0] * s[0] + 2.0f * B2_C5B1 * tt * s[0]);
       wv[1] += F * (2.0f * B2_C5B1 * s[0] * s[0] * s[1] + 4.0f * B2_C5B2 * tt * s[1]);
@@ -1134,6 +1132,16 @@ B2_HD void b2_body_force_final(
   }
   const int dst = P.perm[i];
   const size_t N = (size_t)P.n;
+  if (P.overwrite) {
+    pe[dst] = P.acc[i] + (double)zpe;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+      force[k * N + dst] = (double)r[k] + (double)a[k] + (double)z[k];
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+      virial[k * N + dst] = (double)r[3 + k] + (double)a[3 + k] + (double)z[3 + k];
+    return;
+  }
   pe[dst] += P.acc[i] + (double)zpe; // acc[i] = site energy from the MLP pass
 #pragma unroll
   for (int k = 0; k < 3; ++k)
@@ -1262,7 +1270,7 @@ B2_HD void b2_team_desc_radial(int i, int l, const B2NepView& P, const B2Box& bo
           q = fmaf(B2_LDG(&c[k]), S[t][k], q);
       }
     }
-    P.q[(size_t)i * P.qs + n] = q;
+    P.q[(size_t)n * P.n + i] = q;
   }
 }
 

@@ -92,24 +92,12 @@ __global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
     cur_type = t;
     // ---- stage Q (scaled descriptors) as the A operand: row tid, four columns per store.
     //      16 columns are fetched at a time so that their (strided) loads are all in flight ----
-    // this thread's row q[i*qs .. +dim) is one contiguous run (qs is a multiple of 4: float4 loads)
-    const float4* qrow = reinterpret_cast<const float4*>(P.q + (size_t)(i >= 0 ? i : 0) * P.qs);
     for (int c0 = 0; c0 < DK; c0 += 16) {
       float v[16];
 #pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        float4 t = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (i >= 0 && c0 + 4 * g < P.qs)
-          t = qrow[c0 / 4 + g];
-        v[4 * g] = t.x;
-        v[4 * g + 1] = t.y;
-        v[4 * g + 2] = t.z;
-        v[4 * g + 3] = t.w;
-      }
-#pragma unroll
       for (int c = 0; c < 16; ++c) {
         const int d = c0 + c;
-        v[c] = (i >= 0 && d < P.dim) ? v[c] * __ldg(&P.q_scaler[d]) : 0.0f;
+        v[c] = (i >= 0 && d < P.dim) ? P.q[(size_t)d * N + i] * __ldg(&P.q_scaler[d]) : 0.0f;
       }
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -212,7 +200,7 @@ __global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
           const int d = c0 + c;
           if (d < P.dim) {
             if (d >= P.nr1)
-              P.FpA[(size_t)i * P.fas + (d - P.nr1)] = f[c];
+              P.FpA[(size_t)(d - P.nr1) * N + i] = f[c];
             else if (N3 == 0)
               P.FpR[(size_t)d * N + i] = f[c];
           }
@@ -275,7 +263,16 @@ __global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
               const float4 val =
                 make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
                             __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
-              if (P.u_planes)
+              if (P.u_planes == 2) {
+                // compact planes: row offset 4*(t2*KP4 + q); q < KP4-1 -> float4 plane t2*KQ + q, the last
+                // chunk of a type holds k = K1-1 in .x -> float plane t2
+                const int chunk = c0 / 4 + g, KP4 = P.KP / 4, KQ = KP4 - 1;
+                const int t2 = chunk / KP4, q = chunk - t2 * KP4;
+                if (q < KQ)
+                  Upl[(size_t)(t2 * KQ + q) * N] = val;
+                else
+                  (P.U + (size_t)P.nt * KQ * 4 * N)[(size_t)t2 * N + (i >= 0 ? i : 0)] = val.x;
+              } else if (P.u_planes)
                 Upl[(size_t)(c0 / 4 + g) * N] = val;
               else
                 *reinterpret_cast<float4*>(Urow + c0 + 4 * g) = val;

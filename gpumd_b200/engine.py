@@ -130,6 +130,10 @@ class NEP(Potential):
     def invalidate(self, n_new):
         _lib.check(self._L.b200md_nep_invalidate(self._h, int(n_new), _stream()))
 
+    def set_accumulate(self, accumulate):
+        """False: outputs are overwritten instead of added to (the caller may skip its zeroing pass)."""
+        _lib.check(self._L.b200md_nep_set_accumulate(self._h, 1 if accumulate else 0))
+
     def set_owned(self, n_owned):
         """Spatial domains: only caller indices < n_owned get outputs (0 = all)."""
         _lib.check(self._L.b200md_nep_set_owned(self._h, int(n_owned)))
@@ -352,13 +356,20 @@ class Force:
         else:
             raise _lib.B200mdError(f"illegal potential model '{first}' for gpumd_b200")
         self.potentials = [pot]
+        # a single NEP potential: let its final kernel store the outputs and drop the zeroing pass
+        # (Force::compute zeroes because its potentials accumulate, force.cu:794-801)
+        self._zero = True
+        if isinstance(pot, NEP):
+            pot.set_accumulate(False)
+            self._zero = False
         return pot
 
     def compute(self, box, position, type_, potential, force, virial):
         n = type_.shape[0]
         st = _stream()
         _lib.check(self._L.b200md_apply_pbc(n, box._h, box._p, _ptr(position), st))
-        _lib.check(self._L.b200md_zero_properties(n, _ptr(potential), _ptr(force), _ptr(virial), st))
+        if self._zero:
+            _lib.check(self._L.b200md_zero_properties(n, _ptr(potential), _ptr(force), _ptr(virial), st))
         self.potentials[0].compute(box, type_, position, potential, force, virial)
 
 

@@ -15,8 +15,12 @@ void Force::parse_potential(const char* file_potential, const int num_atoms)
   in >> name;
   in.close();
   potentials.clear();
+  zero_first_ = true;
   if (name.rfind("nep", 0) == 0) {
-    potentials.emplace_back(new NEP_B200(file_potential, num_atoms));
+    NEP_B200* nep = new NEP_B200(file_potential, num_atoms);
+    nep->set_accumulate(false); // the only potential: store instead of += and skip the zeroing pass
+    zero_first_ = false;
+    potentials.emplace_back(nep);
   } else if (name == "lj") {
     potentials.emplace_back(new LJ_B200(file_potential, num_atoms));
   } else if (name == "tersoff_1989") {
@@ -42,9 +46,10 @@ void Force::compute(
   b2h_pbc(box, pbc);
   if (b200md_apply_pbc(n, box.cpu_h, pbc, position_per_atom.data(), nullptr) != B200MD_OK)
     b2h_fail("Force::compute (apply_pbc)");
-  if (b200md_zero_properties(
+  if (zero_first_ &&
+      b200md_zero_properties(
         n, potential_per_atom.data(), force_per_atom.data(), virial_per_atom.data(), nullptr) !=
-      B200MD_OK)
+        B200MD_OK)
     b2h_fail("Force::compute (zero)");
   potentials[0]->compute(
     box, type, position_per_atom, potential_per_atom, force_per_atom, virial_per_atom);

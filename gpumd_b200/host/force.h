@@ -16,4 +16,7 @@ public:
     GPU_Vector<double>& potential_per_atom, GPU_Vector<double>& force_per_atom,
     GPU_Vector<double>& virial_per_atom);
   std::vector<std::unique_ptr<Potential>> potentials;
+
+private:
+  bool zero_first_ = true; // false when the single potential overwrites its outputs (NEP_B200)
 };

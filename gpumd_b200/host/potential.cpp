@@ -43,6 +43,12 @@ void NEP_B200::compute(
     check();
 }
 
+void NEP_B200::set_accumulate(bool accumulate)
+{
+  if (b200md_nep_set_accumulate(handle_, accumulate ? 1 : 0) != B200MD_OK)
+    b2h_fail("NEP_B200::set_accumulate");
+}
+
 void NEP_B200::export_radial()
 {
   if (lists_current_)

@@ -73,6 +73,8 @@ public:
   // order, as the reference's NEP exposes them (nep.cuh:100-101, potential.cuh:66-77)
   const GPU_Vector<int>& get_NN_radial_ptr() override;
   const GPU_Vector<int>& get_NL_radial_ptr() override;
+  // false: outputs are stored, not added (a driver with this single potential skips its zeroing pass)
+  void set_accumulate(bool accumulate);
 
 private:
   void export_radial();

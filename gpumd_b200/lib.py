@@ -93,6 +93,7 @@ SIGNATURES = {
     "b200md_halo_pack": (C.c_int, [C.c_int, _vp, C.c_int, _vp, _dp, _vp, _vp]),
     "b200md_nep_invalidate": (C.c_int, [_vp, C.c_int, _vp]),
     "b200md_nep_set_owned": (C.c_int, [_vp, C.c_int]),
+    "b200md_nep_set_accumulate": (C.c_int, [_vp, C.c_int]),
     "b200md_nep_set_active_region": (C.c_int, [_vp, _dp, _dp]),
     "b200md_tc_selftest": (C.c_int, [C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
 }

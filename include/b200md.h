@@ -306,6 +306,11 @@ int b200md_nep_invalidate(b200md_nep* p, int n_new, void* stream);
  * whose results the owner rank computes and the local rank would discard
  * (cf. nep_multigpu.cu:1764-1802, which copies back the owned range only). */
 int b200md_nep_set_owned(b200md_nep* p, int n_owned);
+/* accumulate = 1 (default): outputs are ADDED to the caller's arrays, the contract of Potential::compute
+ * (nep.cu:653,755-770; Force::compute zeroes them first, force.cu:794-801).  accumulate = 0: they are
+ * OVERWRITTEN, so a driver with a single potential can drop its zeroing pass and the final kernel its
+ * read-modify-write (208 bytes per atom and step).  Small boxes (supercell path) always accumulate. */
+int b200md_nep_set_accumulate(b200md_nep* p, int accumulate);
 /* Atoms whose position (in the coordinates passed to b200md_nep_compute) lies outside [lo, hi) get
  * EMPTY radial / angular neighbour sets from the following calls: no descriptor, dU/dq or partial-
  * force work is spent on them, they only serve as neighbours of the others.  A spatial domain sets

@@ -250,10 +250,10 @@ static void emu_nep_alloc(emu_nep* p, int n)
   p->nl_r.resize(N * pitch_r);
   p->nn_a.resize(N);
   p->nl_a.resize(N * m.MN_angular);
-  p->q.resize(N * ((m.dim + 3) / 4 * 4));
+  p->q.resize(N * m.dim);
   p->sfx.resize(N * m.na1 * B2_NABC);
   p->FpR.resize(N * m.nr1 + 1);
-  p->FpA.resize(N * ((m.dim_angular + 3) / 4 * 4) + 4);
+  p->FpA.resize(N * m.dim_angular + 1);
   p->U.resize(N * m.UST);
   p->f12.resize(N * 3 * m.MN_angular + 1);
   p->acc.resize(N * 13);
@@ -267,7 +267,6 @@ static void emu_nep_alloc(emu_nep* p, int n)
   P.K1R = m.K1R; P.K1A = m.K1A; P.KP = m.KP; P.UST = m.UST;
   P.has222 = m.has222; P.has1111 = m.has1111; P.num_L = m.num_L;
   P.dim = m.dim; P.dim_ang = m.dim_angular; P.nneu = m.nneu; P.DIMP = m.DIMP;
-  P.qs = (m.dim + 3) / 4 * 4; P.fas = (m.dim_angular + 3) / 4 * 4;
   P.zbl_enabled = m.zbl_enabled; P.zbl_flexible = m.zbl_flexible; P.zbl_typewise = m.zbl_typewise;
   P.zbl_rc_inner = m.zbl_rc_inner; P.zbl_rc_outer = m.zbl_rc_outer;
   P.zbl_typewise_factor = m.zbl_typewise_factor;
@@ -455,7 +454,7 @@ void emu_nep_export_descriptors(emu_nep* p, float* q)
   for (int i = 0; i < p->n; ++i)
     for (int d = 0; d < p->m.dim; ++d)
       if (p->P.perm[i] < p->n_cell)
-        q[(size_t)d * p->n_cell + p->P.perm[i]] = p->q[(size_t)i * p->P.qs + d] * p->m.q_scaler[d];
+        q[(size_t)d * p->n_cell + p->P.perm[i]] = p->q[(size_t)d * p->n + i] * p->m.q_scaler[d];
 }
 
 // skin list of the last rebuild, in caller indices (row-major, ascending) -- neighbour tests
