@@ -267,7 +267,11 @@ __global__ void __launch_bounds__(BLK) k_tile_fill(B2NeighborView v)
   int before;
   const int rank = block_rank_by_type(t, valid, v.tile_nt, wcnt, before);
   if (valid)
-    v.tile_atom[v.tile_meta[1 + t] + v.tile_blk[(size_t)t * v.tile_nblk + blockIdx.x] + before + rank] = i;
+  {
+    const int slot = v.tile_meta[1 + t] + v.tile_blk[(size_t)t * v.tile_nblk + blockIdx.x] + before + rank;
+    v.tile_atom[slot] = i;
+    v.tile_slot[i] = slot;
+  }
 }
 
 __global__ void k_rebuild_done(int* flags)
@@ -345,6 +349,7 @@ B2NeighborView Neighbor::view() const
   v.tile_nblk = grid_for(n, BLK);
   v.tile_nslot = n + 128 * tile_nt;
   v.tile_atom = tile_atom.p;
+  v.tile_slot = tile_slot.p;
   v.tile_type = tile_type.p;
   v.tile_blk = tile_blk.p;
   v.tile_meta = tile_meta.p;
@@ -448,6 +453,7 @@ int Neighbor::enable_type_tiles(int num_types)
   }
   tile_nt = num_types;
   B2_CUDA(tile_atom.reserve((size_t)capacity + 128 * (size_t)num_types));
+  B2_CUDA(tile_slot.reserve((size_t)capacity));
   B2_CUDA(tile_type.reserve((size_t)capacity / 128 + num_types + 2));
   B2_CUDA(tile_blk.reserve((size_t)num_types * grid_for(capacity, BLK)));
   B2_CUDA(tile_meta.reserve(num_types + 2));

@@ -59,6 +59,7 @@ struct B2NeighborView {
   int tile_nblk = 0;        // blocks of BLK atoms
   int tile_nslot = 0;       // n + 128 * tile_nt
   int* tile_atom = nullptr; // [tile_nslot] sorted atom index or -1 (padding)
+  int* tile_slot = nullptr; // [n] slot of every sorted atom (inverse of tile_atom)
   int* tile_type = nullptr; // [tile_nslot / 128] type of each 128-slot tile
   int* tile_blk = nullptr;  // [tile_nt * tile_nblk] per-block counts, then offsets inside the bucket
   int* tile_meta = nullptr; // [0] number of tiles, [1 + t] first slot of type t

@@ -29,7 +29,7 @@ public:
   DevBuf<int> perm, perm_tmp, cell_of, order_tmp, cell_count, cell_fill, cell_start, nn_skin,
     nl_skin, flags;
   int tile_nt = 0; // type tiles (see B2NeighborView) are maintained when > 0
-  DevBuf<int> tile_atom, tile_type, tile_blk, tile_meta;
+  DevBuf<int> tile_atom, tile_slot, tile_type, tile_blk, tile_meta;
 
   // Neighbor::initialize, src/force/neighbor.cu:824-833
   int init(int num_atoms, double rc, int mn_skin);

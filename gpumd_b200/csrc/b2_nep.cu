@@ -260,7 +260,7 @@ __global__ void k_export_q(B2NepView P, int n_cell, float* out)
   if (a >= n_cell)
     return;
   for (int d = 0; d < P.dim; ++d)
-    out[(size_t)d * n_cell + a] = P.q[(size_t)d * P.n + i] * P.q_scaler[d];
+    out[(size_t)d * n_cell + a] = *b2_q_ptr(P, i, P.qt ? P.tile_slot[i] : 0, d) * P.q_scaler[d];
 }
 
 // ---- small periodic boxes: evaluate a supercell, keep the first replica -----------------------
@@ -324,7 +324,7 @@ struct b200md_nep {
   DevBuf<int> nn_r, nl_r, nn_a, nl_a;
   DevBuf<float> q, sfx, FpR, FpA, U, f12;
   DevBuf<double> acc;
-  DevBuf<float> tc_img;
+  DevBuf<float> tc_img, qt, fpt; // tile-major q / dU/dq for k_mlp_tc (B2NepView::qt)
   int num_sms = 148;
   int variant = 0;         // B200MD_NEP_VARIANT: kernel tuning variants for A/B measurements
   bool fuse_split = false; // many-type path: neighbour split inside the radial descriptor pass
@@ -374,6 +374,7 @@ int dispatch_desc_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
     A.nn_skin = P.nn_skin; A.nl_skin = P.nl_skin;
     A.nn_r = P.nn_r; A.nl_r = P.nl_r; A.nn_a = P.nn_a; A.nl_a = P.nl_a;
     A.q = P.q; A.flags = P.flags;
+    A.tile_slot = P.tile_slot; A.qt = P.qt; A.DKT = P.DKT;
     A.rc_r = P.rc_r; A.rcinv_r = P.rcinv_r; A.rc2_r = P.rc2_r; A.rc2_a = P.rc2_a; A.c_r = P.c_r;
     A.use_active = P.use_active;
     for (int d = 0; d < 3; ++d) {
@@ -735,6 +736,17 @@ int nep_setup(b200md_nep* p, int num_atoms)
     const char* u_env = std::getenv("B200MD_NEP_UTABLE");
     P.N3 = (m.tc3_ok && !(u_env && std::strcmp(u_env, "simt") == 0)) ? m.N3 : 0;
     P.tile_atom = p->nb.tile_atom.p;
+    { // tile-major q and dU/dq: zeroed once so that padding rows / columns hold finite values
+      const size_t floats = (size_t)p->nb.max_tiles() * 128 * m.DK;
+      B2_CUDA(p->qt.reserve(floats));
+      B2_CUDA(p->fpt.reserve(floats));
+      B2_CUDA(cudaMemset(p->qt.p, 0, sizeof(float) * floats));
+      B2_CUDA(cudaMemset(p->fpt.p, 0, sizeof(float) * floats));
+      P.qt = p->qt.p;
+      P.fpt = p->fpt.p;
+      P.DKT = m.DK;
+      P.tile_slot = p->nb.tile_slot.p;
+    }
     P.tile_type = p->nb.tile_type.p;
     P.tile_meta = p->nb.tile_meta.p;
   }

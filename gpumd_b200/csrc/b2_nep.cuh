@@ -111,10 +111,30 @@ struct B2NepView {
   const float* tc_img;  // [nt][tc_img_floats] shared-memory images, see NepModel::tc_img
   int tc_img_floats, HN, DK, DN;
   int K3, N3;           // U-table GEMM inside k_mlp_tc (N3 = 0: done by k_utable instead)
+  // Tile-major copies of the hidden layer's input and output (non-null when k_mlp_tc is in use):
+  //   qt [tile][k/4][row][k%4], fpt the same shape for dU/dq -- a 128-atom tile of one type is ONE
+  //   contiguous block of DKT*128 floats, already in the K-major order of the tcgen05 A operand, so the
+  //   kernel fetches it with a single TMA bulk copy and stores dU/dq with fully coalesced float4s.
+  //   The descriptor kernels write q there (through tile_slot) instead of the SoA columns.
+  const int* tile_slot; // [n] slot (tile*128 + row) of every sorted atom
+  float* qt;
+  float* fpt;
+  int DKT;              // columns per tile row (= DK, a multiple of 8)
   const int* tile_atom; // B2NeighborView::tile_atom / tile_type / tile_meta
   const int* tile_type;
   const int* tile_meta;
 };
+
+// address of descriptor component k of sorted atom i (slot = P.tile_slot[i] when the tile-major copy is
+// in use, ignored otherwise); the same indexing serves dU/dq in P.fpt
+B2_HD size_t b2_tile_offset(int DKT, int slot, int k)
+{
+  return ((size_t)(slot >> 7) * (DKT >> 2) + (k >> 2)) * 512 + (size_t)(slot & 127) * 4 + (k & 3);
+}
+B2_HD float* b2_q_ptr(const B2NepView& P, int i, int slot, int k)
+{
+  return P.qt ? P.qt + b2_tile_offset(P.DKT, slot, k) : P.q + (size_t)k * P.n + i;
+}
 
 // inside the region whose atoms need descriptors (always true without a region)
 B2_HD bool b2_is_active(const B2NepView& P, double x, double y, double z)
@@ -260,8 +280,9 @@ B2_HD void b2_body_desc_radial(
   if (SPLIT && !b2_is_active(P, a1.x, a1.y, a1.z)) {
     P.nn_r[i] = 0;
     P.nn_a[i] = 0;
+    const int slot0 = P.qt ? P.tile_slot[i] : 0;
     for (int n = 0; n < P.nr1; ++n)
-      P.q[(size_t)n * P.n + i] = 0.0f;
+      *b2_q_ptr(P, i, slot0, n) = 0.0f;
     return;
   }
   const int nn = SPLIT ? P.nn_skin[i] : P.nn_r[i];
@@ -339,6 +360,7 @@ B2_HD void b2_body_desc_radial(
     P.nn_a[i] = ca;
   }
   // contraction with the expansion coefficients
+  const int qslot = P.qt ? P.tile_slot[i] : 0;
   for (int n = 0; n < P.nr1; ++n) {
     float q = 0.0f;
     if (NT > 0) {
@@ -360,7 +382,7 @@ B2_HD void b2_body_desc_radial(
           q = fmaf(B2_LDG(&c[k]), a[(size_t)k * stride], q);
       }
     }
-    P.q[(size_t)n * P.n + i] = q;
+    *b2_q_ptr(P, i, qslot, n) = q;
   }
 }
 
@@ -502,7 +524,7 @@ B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
     for (int c = 0; c < NCH; ++c) {
       const int n = n0 + c;
       if (n < P.na1) {
-        float* qa = P.q + (size_t)P.nr1 * P.n + i; // q[(nr1 + L*na1 + n) * N + i]
+        const int qslot = P.qt ? P.tile_slot[i] : 0; // q[nr1 + L*na1 + n] of atom i
         // 3-body invariants, L = 1..4
         int st = 0;
 #pragma unroll
@@ -512,7 +534,7 @@ B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
           for (int k = 1; k < 2 * L + 1; ++k)
             v = fmaf(C3B[st + k] * s[c][st + k], s[c][st + k], v);
           v = 2.0f * v + C3B[st] * s[c][st] * s[c][st];
-          qa[(size_t)((L - 1) * P.na1 + n) * P.n] = v;
+          *b2_q_ptr(P, i, qslot, P.nr1 + (L - 1) * P.na1 + n) = v;
           st += 2 * L + 1;
         }
         int Lidx = 4;
@@ -521,12 +543,13 @@ B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
           const float v = B2_C4B0 * t[0] * t[0] * t[0] + B2_C4B1 * t[0] * (t[1] * t[1] + t[2] * t[2]) +
                           B2_C4B2 * t[0] * (t[3] * t[3] + t[4] * t[4]) +
                           B2_C4B3 * t[3] * (t[2] * t[2] - t[1] * t[1]) + B2_C4B4 * t[1] * t[2] * t[4];
-          qa[(size_t)(Lidx * P.na1 + n) * P.n] = v;
+          *b2_q_ptr(P, i, qslot, P.nr1 + Lidx * P.na1 + n) = v;
           ++Lidx;
         }
         if (P.has1111) {
           const float s0 = s[c][0] * s[c][0], tt = s[c][1] * s[c][1] + s[c][2] * s[c][2];
-          qa[(size_t)(Lidx * P.na1 + n) * P.n] = B2_C5B0 * s0 * s0 + B2_C5B1 * s0 * tt + B2_C5B2 * tt * tt;
+          *b2_q_ptr(P, i, qslot, P.nr1 + Lidx * P.na1 + n) =
+            B2_C5B0 * s0 * s0 + B2_C5B1 * s0 * tt + B2_C5B2 * tt * tt;
           ++Lidx;
         }
 #pragma unroll
@@ -825,6 +848,16 @@ B2_HD void b2_body_force_angular(int i, const B2NepView& P, const B2Box& box, fl
   constexpr size_t stride = STRIDE;
   const float C3B[B2_NABC] = {B2_C3B_LIST};
   const size_t N = (size_t)P.n;
+  // dU/dq of this atom: tile-major copy written by k_mlp_tc (component d at fbase + (d/4)*512 + d%4),
+  // or the SoA columns FpA[(d - nr1)*N + i] of the SIMT layer
+  const float* fbase = P.fpt ? P.fpt + b2_tile_offset(P.DKT, P.tile_slot[i], 0) : nullptr;
+  auto FpAt = [&](int da) -> float { // da = index inside the angular part
+    if (fbase) {
+      const int d = P.nr1 + da;
+      return fbase[(size_t)(d >> 2) * 512 + (d & 3)];
+    }
+    return P.FpA[(size_t)da * N + i];
+  };
   // ---- weights: 3-body (calculate_s_one, nep_utilities.cuh:1327-1340) + chain rule of the
   //      4-body (:625-679) and 5-body (:681-718) invariants ----
   for (int n = 0; n < P.na1; ++n) {
@@ -836,7 +869,7 @@ B2_HD void b2_body_force_angular(int i, const B2NepView& P, const B2Box& box, fl
     int st = 0;
 #pragma unroll
     for (int L = 1; L <= 4; ++L) {
-      const float F = P.FpA[(size_t)((L - 1) * P.na1 + n) * N + i];
+      const float F = FpAt((L - 1) * P.na1 + n);
       wv[st] = 2.0f * F * C3B[st] * s[st];
 #pragma unroll
       for (int k = 1; k < 2 * L + 1; ++k)
@@ -845,7 +878,7 @@ B2_HD void b2_body_force_angular(int i, const B2NepView& P, const B2Box& box, fl
     }
     int Lidx = 4;
     if (P.has222) {
-      const float F = P.FpA[(size_t)(Lidx * P.na1 + n) * N + i];
+      const float F = FpAt(Lidx * P.na1 + n);
       const float* t = &s[3];
       wv[3] += F * (3.0f * B2_C4B0 * t[0] * t[0] + B2_C4B1 * (t[1] * t[1] + t[2] * t[2]) +
                     B2_C4B2 * (t[3] * t[3] + t[4] * t[4]));
@@ -856,7 +889,7 @@ B2_HD void b2_body_force_angular(int i, const B2NepView& P, const B2Box& box, fl
       ++Lidx;
     }
     if (P.has1111) {
-      const float F = P.FpA[(size_t)(Lidx * P.na1 + n) * N + i];
+      const float F = FpAt(Lidx * P.na1 + n);
       const float tt = s[1] * s[1] + s[2] * s[2];
       wv[0] += F * (4.0f * B2_C5B0 * s[0] * s[0] * s[0] + 2.0f * B2_C5B1 * tt * s[0]);
       wv[1] += F * (2.0f * B2_C5B1 * s[0] * s[0] * s[1] + 4.0f * B2_C5B2 * tt * s[1]);

@@ -257,7 +257,7 @@ std::string NepModel::load(const char* path)
     int ka = DK > HN ? DK : HN;
     if (tc3_ok && K3 > ka)
       ka = K3;
-    const size_t smem = (size_t)tc_img_floats * 4 + 2 * 128 * (size_t)ka * 4 + 256;
+    const size_t smem = (size_t)tc_img_floats * 4 + 2 * 128 * (size_t)ka * 4 + 128 * (size_t)DK * 4 + 256;
     tc_ok = HN <= 256 && DN <= 256 && cols <= 512 && smem <= 200 * 1024;
   }
   if (tc_ok) {

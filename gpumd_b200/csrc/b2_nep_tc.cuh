@@ -32,18 +32,23 @@ __host__ __device__ inline int b2_tc_ka(int HN, int DK, int K3)
   int ka = DK > HN ? DK : HN;
   return K3 > ka ? K3 : ka;
 }
+// weight image + the two A tiles (hi / lo) + the landing buffer of the TMA copy of one q tile
 __host__ __device__ inline size_t b2_tc_smem_bytes(int img_floats, int HN, int DK, int K3)
 {
-  return b2_tc_img_bytes(img_floats) + 2 * 128 * (size_t)b2_tc_ka(HN, DK, K3) * 4;
+  return b2_tc_img_bytes(img_floats) + 2 * 128 * (size_t)b2_tc_ka(HN, DK, K3) * 4 + 128 * (size_t)DK * 4;
 }
 
+// Input: the tile-major copy of q (B2NepView::qt) -- ONE cp.async.bulk per 128-atom tile into a landing
+// buffer that already has the K-major order of the A operand; the copy of tile k+1 is issued as soon as
+// tile k has been split into its TF32 hi / lo operands, so it flies under the three GEMMs and epilogues
+// of tile k.  Output: dU/dq goes back tile-major (P.fpt) with coalesced float4 stores.
 // Persistent: each CTA walks tiles blockIdx.x, blockIdx.x + gridDim.x, ... so that the TMEM
 // allocation, barrier set-up and (tiles being ordered by type) almost every weight fetch are paid
 // once per CTA instead of once per tile.
 __global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
 {
   extern __shared__ __align__(128) unsigned char tc_smem[];
-  __shared__ __align__(8) uint64_t bar_w, bar_mma;
+  __shared__ __align__(8) uint64_t bar_w, bar_mma, bar_q;
   __shared__ uint32_t tmem_slot;
   const int ntile = P.tile_meta[0];
   if ((int)blockIdx.x >= ntile)
@@ -58,6 +63,8 @@ __global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
   const float* sw1 = sb0 + HN;
   unsigned char* a_hi = tc_smem + b2_tc_img_bytes(P.tc_img_floats);
   unsigned char* a_lo = a_hi + (size_t)128 * KA * 4;
+  float4* stage = reinterpret_cast<float4*>(a_lo + (size_t)128 * KA * 4); // [DK/4][128] float4
+  const uint32_t q_bytes = (uint32_t)DK * 128u * 4u;
   const uint32_t ncols = (uint32_t)b2_tc_tmem_cols(HN, DN, N3);
 
   if (warp == 0)
@@ -65,6 +72,7 @@ __global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
   if (tid == 0) {
     b2tc::mbar_init(&bar_w, 1);
     b2tc::mbar_init(&bar_mma, 1);
+    b2tc::mbar_init(&bar_q, 1);
   }
   b2tc::fence_before_sync();
   __syncthreads();
@@ -72,8 +80,12 @@ __global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
   const uint32_t tmem = tmem_slot;
   const uint32_t ah = b2tc::smem_u32(a_hi), al = b2tc::smem_u32(a_lo);
   const uint32_t lane_base = (uint32_t)(warp * 32) << 16;
-  uint32_t w_phase = 0, mma_phase = 0;
+  uint32_t w_phase = 0, mma_phase = 0, q_phase = 0;
   int cur_type = -1;
+  if (tid == 0) { // first q tile of this CTA
+    b2tc::mbar_expect_tx(&bar_q, q_bytes);
+    b2tc::bulk_g2s(stage, P.qt + (size_t)blockIdx.x * DK * 128, q_bytes, &bar_q);
+  }
 
   int i_next = P.tile_atom[blockIdx.x * 128 + tid];
   for (int tile = blockIdx.x; tile < ntile; tile += gridDim.x) {
@@ -90,32 +102,32 @@ __global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
       b2tc::bulk_g2s(img, P.tc_img + (size_t)t * P.tc_img_floats, bytes, &bar_w);
     }
     cur_type = t;
-    // ---- stage Q (scaled descriptors) as the A operand: row tid, four columns per store.
-    //      16 columns are fetched at a time so that their (strided) loads are all in flight ----
-    for (int c0 = 0; c0 < DK; c0 += 16) {
-      float v[16];
+    // ---- Q tile (landed by TMA, K-major like the A operand): scale, split into TF32 hi / lo ----
+    b2tc::mbar_wait(&bar_q, q_phase);
+    q_phase ^= 1u;
+    for (int kc = 0; kc < DK / 4; ++kc) {
+      float4 v = stage[kc * 128 + tid];
+      const float4 sc = __ldg(reinterpret_cast<const float4*>(P.q_scaler) + kc); // zero beyond dim
+      if (i < 0)
+        v = make_float4(0.0f, 0.0f, 0.0f, 0.0f); // padding row
+      const float x[4] = {v.x * sc.x, v.y * sc.y, v.z * sc.z, v.w * sc.w};
+      float hi[4], lo[4];
 #pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        const int d = c0 + c;
-        v[c] = (i >= 0 && d < P.dim) ? P.q[(size_t)d * N + i] * __ldg(&P.q_scaler[d]) : 0.0f;
-      }
-#pragma unroll
-      for (int g = 0; g < 4; ++g) {
-        if (c0 + 4 * g < DK) {
-          float hi[4], lo[4];
-#pragma unroll
-          for (int c = 0; c < 4; ++c)
-            b2tc::split_tf32(v[4 * g + c], hi[c], lo[c]);
-          const uint32_t off = (uint32_t)tid * 16u + (uint32_t)(c0 / 4 + g) * 2048u;
-          *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
-        }
-      }
+      for (int c = 0; c < 4; ++c)
+        b2tc::split_tf32(x[c], hi[c], lo[c]);
+      const uint32_t off = (uint32_t)tid * 16u + (uint32_t)kc * 2048u;
+      *reinterpret_cast<float4*>(a_hi + off) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+      *reinterpret_cast<float4*>(a_lo + off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
     }
     b2tc::fence_async_smem();
     b2tc::fence_before_sync();
     __syncthreads();
     b2tc::fence_after_sync();
+    if (tid == 0 && tile + (int)gridDim.x < ntile) {
+      // every thread has read the landing buffer (barrier above): fetch the next tile under this one
+      b2tc::mbar_expect_tx(&bar_q, q_bytes);
+      b2tc::bulk_g2s(stage, P.qt + (size_t)(tile + gridDim.x) * DK * 128, q_bytes, &bar_q);
+    }
     if (new_weights) {
       b2tc::mbar_wait(&bar_w, w_phase); // weights, b0, w1 have landed
       w_phase ^= 1u;
@@ -194,17 +206,17 @@ __global__ void __launch_bounds__(128) k_mlp_tc(B2NepView P)
         const int d = c0 + c;
         f[c] = (i >= 0 && d < P.dim) ? __uint_as_float(v[c]) * __ldg(&P.q_scaler[d]) : 0.0f;
       }
-      if (i >= 0) {
+      // tile-major dU/dq: row tid, chunk (c0 + 4g)/4 -- consecutive threads, consecutive 16 bytes
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          const int d = c0 + c;
-          if (d < P.dim) {
-            if (d >= P.nr1)
-              P.FpA[(size_t)(d - P.nr1) * N + i] = f[c];
-            else if (N3 == 0)
-              P.FpR[(size_t)d * N + i] = f[c];
-          }
-        }
+      for (int g = 0; g < 4; ++g)
+        if (c0 + 4 * g < DK)
+          reinterpret_cast<float4*>(P.fpt)[((size_t)tile * (DK / 4) + (c0 / 4 + g)) * 128 + tid] =
+            make_float4(f[4 * g], f[4 * g + 1], f[4 * g + 2], f[4 * g + 3]);
+      if (i >= 0 && N3 == 0) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c)
+          if (c0 + c < P.nr1)
+            P.FpR[(size_t)(c0 + c) * N + i] = f[c];
       }
       if (N3 && c0 < K3) { // nr1 <= K3 <= 16: the radial part sits in the first chunk
 #pragma unroll
