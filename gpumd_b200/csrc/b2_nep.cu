@@ -329,6 +329,8 @@ struct b200md_nep {
   int variant = 0;         // B200MD_NEP_VARIANT: kernel tuning variants for A/B measurements
   bool fuse_split = false; // many-type path: neighbour split inside the radial descriptor pass
   bool use_tc = false; // hidden layer on the tensor cores (k_mlp_tc) instead of k_mlp
+  bool slot_map = false;  // k_force_final2: thread per tile slot (type-pure warps); measured slower
+                          // (0.804 vs 0.736 ms, profiles/r01_f_ab.md), B200MD_NEP_SLOTMAP=1 for A/B runs
   bool radial_v2 = false; // few-type radial passes of b2_nep_radial.cuh (planes, branch-free loop)
   // small periodic boxes: supercell replication, see b200md_nep_compute
   DevBuf<int> rep_type;
@@ -431,7 +433,11 @@ int dispatch_force_final(
   else if (p->view.team)
     k_team_force_final<2, K1><<<team_grid, BLK, 0, st>>>(p->view, box, pe, f, v);
   else if (p->radial_v2) {
-    const int g = grid_for(p->n, BLK);
+    // one thread per tile slot when type tiles exist (type-pure warps), else per sorted atom
+    B2NepView V = p->view;
+    if (!p->slot_map)
+      V.tile_atom = nullptr; // B200MD_NEP_SLOTMAP=0: thread per sorted atom (A/B runs)
+    const int g = V.tile_atom ? p->nb.max_tiles() : grid_for(p->n, BLK);
     const int4* p0 = p->nb.plane0.p;
     const int4* p1 = p->nb.plane1.p;
     const double* pz = p->nb.planez.p;
@@ -441,11 +447,11 @@ int dispatch_force_final(
 #define B2_FF2(NT_, ORTHO_)                                                                      \
   do {                                                                                           \
     if (p->variant == 1)                                                                         \
-      k_force_final2<NT_, K1, ORTHO_, 6><<<g, BLK, 0, st>>>(p->view, p0, p1, pz, box, pe, f, v);     \
+      k_force_final2<NT_, K1, ORTHO_, 6><<<g, BLK, 0, st>>>(V, p0, p1, pz, box, pe, f, v);     \
     else if (p->variant == 2)                                                                    \
-      k_force_final2<NT_, K1, ORTHO_, 4><<<g, BLK, 0, st>>>(p->view, p0, p1, pz, box, pe, f, v);     \
+      k_force_final2<NT_, K1, ORTHO_, 4><<<g, BLK, 0, st>>>(V, p0, p1, pz, box, pe, f, v);     \
     else                                                                                         \
-      k_force_final2<NT_, K1, ORTHO_, 5><<<g, BLK, 0, st>>>(p->view, p0, p1, pz, box, pe, f, v);     \
+      k_force_final2<NT_, K1, ORTHO_, 5><<<g, BLK, 0, st>>>(V, p0, p1, pz, box, pe, f, v);     \
   } while (0)
     if (p->model.nt == 1 && box.ortho)
       B2_FF2(1, true);
@@ -632,6 +638,8 @@ int nep_setup(b200md_nep* p, int num_atoms)
   const char* rad_env = std::getenv("B200MD_NEP_RADIAL");
   p->radial_v2 = m.nt <= 2 && !team && !(rad_env && std::strcmp(rad_env, "v1") == 0) &&
                  (double)num_atoms * (mn_skin + 2) < 4.0e9; // 32-bit list offsets in those kernels
+  if (const char* v = std::getenv("B200MD_NEP_SLOTMAP"))
+    p->slot_map = std::atoi(v) != 0;
   p->nb.tag_types = p->radial_v2; // skin entries carry the neighbour type (b2_nep_radial.cuh)
   if (p->radial_v2)
     B2_TRY(p->nb.enable_planes());

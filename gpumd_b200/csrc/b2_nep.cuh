@@ -1303,7 +1303,7 @@ B2_HD void b2_team_desc_radial(int i, int l, const B2NepView& P, const B2Box& bo
           q = fmaf(B2_LDG(&c[k]), S[t][k], q);
       }
     }
-    P.q[(size_t)n * P.n + i] = q;
+    *b2_q_ptr(P, i, P.qt ? P.tile_slot[i] : 0, n) = q;
   }
 }
 
