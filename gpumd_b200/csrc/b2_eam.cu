@@ -95,6 +95,11 @@ int b200md_eam_create(const char* path, int num_atoms, b200md_eam** out)
     return B200MD_ERR_ARG;
   }
   b200md_eam* p = new (std::nothrow) b200md_eam;
+  if (!p) {
+    fclose(fid);
+    set_error("out of host memory");
+    return B200MD_ERR_ARG;
+  }
   p->nt = nt;
   p->model = model;
   for (int k = 0; k < nt; ++k) {
@@ -173,7 +178,7 @@ int b200md_eam_create(const char* path, int num_atoms, b200md_eam** out)
   const double rs = rc + 1.0;
   int mn = (int)(400 * rs * rs * rs / ((double)rc * rc * rc));
   const int mn_dense = (int)(4.19 * rs * rs * rs * 0.2) + 32;
-  if (mn > mn_dense)
+  if (b2_tight_lists() && mn > mn_dense)
     mn = mn_dense;
   int r = p->nb.init(num_atoms, rc, mn);
   if (r != B200MD_OK) {

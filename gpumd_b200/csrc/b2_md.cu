@@ -305,6 +305,11 @@ int b200md_lj_create(const char* path, int num_atoms, b200md_lj** out)
     return B200MD_ERR_IO;
   }
   b200md_lj* p = new (std::nothrow) b200md_lj;
+  if (!p) {
+    fclose(fid);
+    set_error("out of host memory");
+    return B200MD_ERR_ARG;
+  }
   char name[64];
   int nt = 0;
   // "lj Nt sym..." then Nt*Nt lines "epsilon sigma cutoff" (force.cu:93-100, lj.cu:28-56)
@@ -353,12 +358,13 @@ int b200md_lj_create(const char* path, int num_atoms, b200md_lj** out)
     delete p;
     return rc;
   }
-  // neighbor.initialize(rc, num_atoms, 700), lj.cu:58 -> capacity 700*((rc+1)/rc)^3.  The cap
-  // is a memory knob, not physics: bound it by what rc+skin can hold at liquid-argon density x2.
+  // neighbor.initialize(rc, num_atoms, 700), lj.cu:58 -> capacity 700*((rc+1)/rc)^3 by default.
+  // B200MD_TIGHT_LISTS=1 bounds it by what rc+skin can hold at twice liquid-argon density (a
+  // memory knob for very large systems; an overflow is still latched and reported).
   const double rs = p->rc + 1.0;
   int mn = (int)(700 * rs * rs * rs / (p->rc * p->rc * p->rc));
   const int mn_dense = (int)(4.19 * rs * rs * rs * 0.06) + 32;
-  if (mn > mn_dense)
+  if (b2_tight_lists() && mn > mn_dense)
     mn = mn_dense;
   if ((rc = p->nb.init(num_atoms, p->rc, mn)) != B200MD_OK) {
     delete p;

@@ -114,6 +114,11 @@ int b200md_tersoff_create(const char* path, int num_atoms, b200md_tersoff** out)
     return B200MD_ERR_ARG;
   }
   b200md_tersoff* p = new (std::nothrow) b200md_tersoff;
+  if (!p) {
+    fclose(fid);
+    set_error("out of host memory");
+    return B200MD_ERR_ARG;
+  }
   p->nt = nt;
   for (int k = 0; k < nt; ++k) {
     if (fscanf(fid, "%63s", name) != 1) {

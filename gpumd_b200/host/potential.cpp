@@ -115,6 +115,8 @@ void LJ_B200::compute(
         handle_, (int)type.size(), box.cpu_h, pbc, type.data(), position.data(), potential.data(),
         force.data(), virial.data(), nullptr) != B200MD_OK)
     b2h_fail("LJ_B200::compute");
+  if (++num_calls_ % 1000 == 1)
+    check(); // latched neighbour-capacity errors, the cadence NEP_B200 uses
 }
 
 int LJ_B200::type_of(const std::string& symbol) const
@@ -153,6 +155,8 @@ void Tersoff1989_B200::compute(
         handle_, (int)type.size(), box.cpu_h, pbc, type.data(), position.data(), potential.data(),
         force.data(), virial.data(), nullptr) != B200MD_OK)
     b2h_fail("Tersoff1989_B200::compute");
+  if (++num_calls_ % 1000 == 1)
+    check(); // latched neighbour-capacity errors, the cadence NEP_B200 uses
 }
 
 int Tersoff1989_B200::type_of(const std::string& symbol) const
@@ -191,6 +195,8 @@ void EAM_B200::compute(
         handle_, (int)type.size(), box.cpu_h, pbc, type.data(), position.data(), potential.data(),
         force.data(), virial.data(), nullptr) != B200MD_OK)
     b2h_fail("EAM_B200::compute");
+  if (++num_calls_ % 1000 == 1)
+    check(); // latched neighbour-capacity errors, the cadence NEP_B200 uses
 }
 
 int EAM_B200::type_of(const std::string& symbol) const

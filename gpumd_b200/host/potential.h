@@ -100,6 +100,7 @@ public:
 
 private:
   b200md_lj* handle_ = nullptr;
+  int num_calls_ = 0;
 };
 
 // replaces class Tersoff1989 : Potential, src/force/tersoff1989.cuh:22-60 (FP64 like the reference)
@@ -117,6 +118,7 @@ public:
 
 private:
   b200md_tersoff* handle_ = nullptr;
+  int num_calls_ = 0;
 };
 
 // replaces class EAM : Potential, src/force/eam.cuh:44-75 (eam_zhou_2004, eam_dai_2006)
@@ -134,6 +136,7 @@ public:
 
 private:
   b200md_eam* handle_ = nullptr;
+  int num_calls_ = 0;
 };
 
 [[noreturn]] void b2h_fail(const char* where);

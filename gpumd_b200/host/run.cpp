@@ -819,11 +819,16 @@ private:
         b2h_fail("compute_hac");
       ++global_step_;
       global_time_ += time_step_;
-      if (fid && (step + 1) % dump_thermo_ == 0)
+      const bool out_thermo = fid && (step + 1) % dump_thermo_ == 0;
+      const bool out_xyz = dump_xyz_.interval > 0 && (step + 1) % dump_xyz_.interval == 0;
+      const bool out_restart = dump_restart_ > 0 && (step + 1) % dump_restart_ == 0;
+      if (out_thermo || out_xyz || out_restart)
+        force_.potentials[0]->check(); // nothing computed from a truncated list reaches a file
+      if (out_thermo)
         write_thermo(fid);
-      if (dump_xyz_.interval > 0 && (step + 1) % dump_xyz_.interval == 0)
+      if (out_xyz)
         write_xyz_frame(step);
-      if (dump_restart_ > 0 && (step + 1) % dump_restart_ == 0)
+      if (out_restart)
         write_restart();
     }
     B2H_CHECK(cudaDeviceSynchronize());

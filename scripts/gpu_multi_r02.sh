@@ -30,6 +30,6 @@ if [ "$N" = "8" ]; then
   run c3_weak_blocks_n8 --steps 100 --grid 2x2x2 --no-reference-gpu
 else
   run c5_si_n$N --workload si --steps 200
-  run c3_weak_n$N --steps 100
+  [ -n "${WITH_C3:-}" ] && run c3_weak_n$N --steps 100
 fi
 ls gpurun_out | tail -20
