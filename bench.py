@@ -151,11 +151,16 @@ def reference_gpu(s, vel, n_gpus, steps, potential=MODEL, symbols=None, ensemble
         wall = time.time() - t0
         speed = re.findall(r"Speed of this run = ([0-9.eE+-]+) atom\*step/second", r.stdout)
         tail = [ln.strip() for ln in r.stdout.splitlines() if ln.strip() and not ln.startswith("---")][-6:]
+        kind = Path(potential).read_text().split(None, 1)[0]
+        if kind.startswith("nep"):
+            path = "NEP_MULTIGPU" if n_gpus > 1 else "NEP"
+        else:  # only NEP has a multi-GPU path in the reference (force.cu:139-160): one device is used
+            path = kind + (" (the reference runs this potential on one GPU)" if n_gpus > 1 else "")
         out = {"value": float(speed[-1]) if speed else None, "unit": "atom-steps/s", "steps": steps,
                "n_gpus": n_gpus, "n_atoms": int(s["type"].shape[0]), "returncode": r.returncode,
                "wall_s": round(wall, 2), "input_write_s": round(t_write, 2),
                "binary": "oracle/_ref/gpumd_ref (unmodified reference, nvcc -O3 -arch=sm_100 -DDEBUG)",
-               "path": "NEP_MULTIGPU" if n_gpus > 1 else "NEP", "stdout_tail": tail}
+               "path": path, "stdout_tail": tail}
         if r.returncode != 0:
             out["stderr_tail"] = r.stderr[-500:]
         return out
