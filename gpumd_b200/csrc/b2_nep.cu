@@ -318,7 +318,7 @@ struct b200md_nep {
   NepModel model;
   Neighbor nb;
   int n = 0;
-  DevBuf<float> rc_r, rcinv_r, rc2_r, rc_a, rcinv_a, rc2_a, c_r, c_a, w0p, b0, w1, bias, q_scaler,
+  DevBuf<float> rc_r, rcinv_r, rc2_r, rc_a, rcinv_a, rc2_a, c_r, c_a, c_a4, c_r4, w0p, b0, w1, bias, q_scaler,
     zbl_para, cov_radius;
   DevBuf<int> zbl_z;
   DevBuf<int> nn_r, nl_r, nn_a, nl_a;
@@ -608,6 +608,8 @@ int nep_setup(b200md_nep* p, int num_atoms)
   B2_TRY(upload(p->rc2_a, m.rc2_a));
   B2_TRY(upload(p->c_r, m.c_r));
   B2_TRY(upload(p->c_a, m.c_a));
+  B2_TRY(upload(p->c_a4, m.c_a4));
+  B2_TRY(upload(p->c_r4, m.c_r4));
   B2_TRY(upload(p->w0p, m.w0p));
   B2_TRY(upload(p->b0, m.b0));
   B2_TRY(upload(p->w1, m.w1));
@@ -689,6 +691,14 @@ int nep_setup(b200md_nep* p, int num_atoms)
   P.rc2_a = p->rc2_a.p;
   P.c_r = p->c_r.p;
   P.c_a = p->c_a.p;
+  {
+    // B200MD_NEP_CVEC=0: scalar coefficient loads (A/B switch; results are bit-identical)
+    const char* e = getenv("B200MD_NEP_CVEC");
+    const bool cvec = !(e && e[0] == '0');
+    P.c_a4 = cvec ? reinterpret_cast<const float4*>(p->c_a4.p) : nullptr;
+    P.c_r4 = cvec ? reinterpret_cast<const float4*>(p->c_r4.p) : nullptr;
+    P.nqr = m.nqr;
+  }
   P.w0p = p->w0p.p;
   P.b0 = p->b0.p;
   P.w1 = p->w1.p;

@@ -66,6 +66,12 @@ struct B2NepView {
   const float* rc2_a;
   const float* c_r;      // [nt*nt][nr1][K1R] zero-padded in k
   const float* c_a;      // [nt*nt][na1][K1A]
+  // the same coefficients padded for 128-bit loads (null: scalar loads).  With many types every lane
+  // of a warp reads a different (t1, t2) row, so each load instruction costs one L1 wavefront per
+  // lane; four coefficients per instruction cut that cost by four.
+  const float4* c_a4;    // [nt*nt][na1][(K1A+3)/4]: k = 4q .. 4q+3, zero-padded
+  const float4* c_r4;    // [nt*nt][nqr][K1R]: n = 4*nq .. 4*nq+3 of basis function k, zero-padded
+  int nqr;               // (nr1 + 3) / 4
   const float* w0p;      // [nt][nneu][DIMP] zero-padded rows
   const float* b0;       // [nt][nneu]
   const float* w1;       // [nt][nneu]
@@ -361,6 +367,35 @@ B2_HD void b2_body_desc_radial(
   }
   // contraction with the expansion coefficients
   const int qslot = P.qt ? P.tile_slot[i] : 0;
+  if (NT == 0 && P.c_r4) {
+    // four radial channels per pass: one 128-bit coefficient load and one read of the accumulator
+    // serve four FMAs; per channel the (t outer, k inner) summation order is the scalar path's
+    for (int nq = 0; nq < P.nqr; ++nq) {
+      float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
+      for (int t = 0; t < P.nt; ++t) {
+        const float4* c4 = P.c_r4 + ((size_t)(t1 * P.nt + t) * P.nqr + nq) * K1;
+        const float* a = acc + (size_t)(t * K1) * stride + lane;
+#pragma unroll
+        for (int k = 0; k < K1; ++k) {
+          const float av = a[(size_t)k * stride];
+          const float4 v = B2_LDG(&c4[k]);
+          q0 = fmaf(v.x, av, q0);
+          q1 = fmaf(v.y, av, q1);
+          q2 = fmaf(v.z, av, q2);
+          q3 = fmaf(v.w, av, q3);
+        }
+      }
+      const int n = 4 * nq;
+      *b2_q_ptr(P, i, qslot, n) = q0;
+      if (n + 1 < P.nr1)
+        *b2_q_ptr(P, i, qslot, n + 1) = q1;
+      if (n + 2 < P.nr1)
+        *b2_q_ptr(P, i, qslot, n + 2) = q2;
+      if (n + 3 < P.nr1)
+        *b2_q_ptr(P, i, qslot, n + 3) = q3;
+    }
+    return;
+  }
   for (int n = 0; n < P.nr1; ++n) {
     float q = 0.0f;
     if (NT > 0) {
@@ -509,11 +544,28 @@ B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
 #pragma unroll
       for (int c = 0; c < NCH; ++c) {
         if (n0 + c < P.na1) {
-          const float* cc = P.c_a + ((size_t)pair * P.na1 + (n0 + c)) * K1;
           float g = 0.0f;
+          if (P.c_a4) {
+            constexpr int KQ = (K1 + 3) / 4;
+            const float4* c4 = P.c_a4 + ((size_t)pair * P.na1 + (n0 + c)) * KQ;
+            float ck[KQ * 4];
 #pragma unroll
-          for (int k = 0; k < K1; ++k)
-            g = fmaf(fn[k], B2_LDG(&cc[k]), g);
+            for (int q = 0; q < KQ; ++q) {
+              const float4 v = B2_LDG(&c4[q]);
+              ck[4 * q] = v.x;
+              ck[4 * q + 1] = v.y;
+              ck[4 * q + 2] = v.z;
+              ck[4 * q + 3] = v.w;
+            }
+#pragma unroll
+            for (int k = 0; k < K1; ++k)
+              g = fmaf(fn[k], ck[k], g);
+          } else {
+            const float* cc = P.c_a + ((size_t)pair * P.na1 + (n0 + c)) * K1;
+#pragma unroll
+            for (int k = 0; k < K1; ++k)
+              g = fmaf(fn[k], B2_LDG(&cc[k]), g);
+          }
 #pragma unroll
           for (int abc = 0; abc < B2_NABC; ++abc)
             s[c][abc] = fmaf(g, B[abc], s[c][abc]);
@@ -732,10 +784,22 @@ B2_HD void b2_radial_pair(
       A = fmaf(fnp[k], u, A);
     }
   } else {
-    const float* Uit = Ui + t2 * P.KP;
+    // own row U_i[t2]: every lane reads a different row, so 128-bit loads (rows are KP = 4*KQ
+    // floats, 16-byte aligned) cost a quarter of the L1 wavefronts of K1 scalar ones
+    constexpr int KQ = (K1 + 3) / 4;
+    const float4* Uit = reinterpret_cast<const float4*>(Ui + t2 * P.KP);
+    float u[KQ * 4];
+#pragma unroll
+    for (int q = 0; q < KQ; ++q) {
+      const float4 v = Uit[q];
+      u[4 * q] = v.x;
+      u[4 * q + 1] = v.y;
+      u[4 * q + 2] = v.z;
+      u[4 * q + 3] = v.w;
+    }
 #pragma unroll
     for (int k = 0; k < K1; ++k)
-      A = fmaf(fnp[k], Uit[k], A);
+      A = fmaf(fnp[k], u[k], A);
   }
 #pragma unroll
   for (int k = 0; k < K1; ++k)
@@ -928,13 +992,32 @@ B2_HD void b2_body_force_angular(int i, const B2NepView& P, const B2Box& box, fl
       Wp[abc] = 0.0f;
     }
     for (int n = 0; n < P.na1; ++n) {
-      const float* cc = P.c_a + ((size_t)pair * P.na1 + n) * K1;
       float g = 0.0f, gp = 0.0f;
+      if (P.c_a4) {
+        constexpr int KQ = (K1 + 3) / 4;
+        const float4* c4 = P.c_a4 + ((size_t)pair * P.na1 + n) * KQ;
+        float ck[KQ * 4];
 #pragma unroll
-      for (int k = 0; k < K1; ++k) {
-        const float ck = B2_LDG(&cc[k]);
-        g = fmaf(fn[k], ck, g);
-        gp = fmaf(fnp[k], ck, gp);
+        for (int q = 0; q < KQ; ++q) {
+          const float4 v = B2_LDG(&c4[q]);
+          ck[4 * q] = v.x;
+          ck[4 * q + 1] = v.y;
+          ck[4 * q + 2] = v.z;
+          ck[4 * q + 3] = v.w;
+        }
+#pragma unroll
+        for (int k = 0; k < K1; ++k) {
+          g = fmaf(fn[k], ck[k], g);
+          gp = fmaf(fnp[k], ck[k], gp);
+        }
+      } else {
+        const float* cc = P.c_a + ((size_t)pair * P.na1 + n) * K1;
+#pragma unroll
+        for (int k = 0; k < K1; ++k) {
+          const float ck = B2_LDG(&cc[k]);
+          g = fmaf(fn[k], ck, g);
+          gp = fmaf(fnp[k], ck, gp);
+        }
       }
       const float* wn = w + (size_t)(n * B2_NABC) * stride + lane;
 #pragma unroll

@@ -242,6 +242,21 @@ std::string NepModel::load(const char* path)
       for (int k = 0; k < ka1; ++k)
         c_a[((size_t)pair * na1 + n) * K1A + k] = ca[(size_t)(n * ka1 + k) * ntsq + pair];
   }
+  // ---- the same coefficients padded to float4 granularity ----
+  {
+    const int kqa = (K1A + 3) / 4;
+    nqr = (nr1 + 3) / 4;
+    c_a4.assign((size_t)ntsq * na1 * kqa * 4, 0.0f);
+    c_r4.assign((size_t)ntsq * nqr * K1R * 4, 0.0f);
+    for (int pair = 0; pair < ntsq; ++pair) {
+      for (int n = 0; n < na1; ++n)
+        for (int k = 0; k < K1A; ++k)
+          c_a4[((size_t)pair * na1 + n) * kqa * 4 + k] = c_a[((size_t)pair * na1 + n) * K1A + k];
+      for (int n = 0; n < nr1; ++n)
+        for (int k = 0; k < K1R; ++k)
+          c_r4[(((size_t)pair * nqr + n / 4) * K1R + k) * 4 + n % 4] = c_r[((size_t)pair * nr1 + n) * K1R + k];
+    }
+  }
   // ---- tensor-core images of the hidden layer (layout documented in b2_nep_model.h) ----
   HN = (nneu + 15) / 16 * 16;
   DK = (dim + 7) / 8 * 8;

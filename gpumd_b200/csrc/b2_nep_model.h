@@ -27,6 +27,10 @@ struct NepModel {
   // flattened tables (see B2NepView for layouts)
   std::vector<float> rc_r, rcinv_r, rc2_r, rc_a, rcinv_a, rc2_a; // [nt*nt]
   std::vector<float> c_r, c_a, w0p, b0, w1, bias, q_scaler;
+  // c_a / c_r padded for 128-bit loads: c_a4 [pair][n][(K1A+3)/4][4], c_r4 [pair][nq][K1R][4]
+  // (n = 4*nq + lane of the vector), see B2NepView::c_a4 / c_r4
+  std::vector<float> c_a4, c_r4;
+  int nqr = 0;
 
   // tensor-core hidden layer (k_mlp_tc): per type one ready-to-copy shared-memory image
   //   [B1_hi | B1_lo | B2_hi | B2_lo | b0 | w1 | B3_hi | B3_lo]  (tc_img_floats floats, multiple of 4)

@@ -272,6 +272,13 @@ static void emu_nep_alloc(emu_nep* p, int n)
   P.zbl_typewise_factor = m.zbl_typewise_factor;
   P.rc_r = m.rc_r.data(); P.rcinv_r = m.rcinv_r.data(); P.rc2_r = m.rc2_r.data();
   P.rc_a = m.rc_a.data(); P.rcinv_a = m.rcinv_a.data(); P.rc2_a = m.rc2_a.data();
+  {
+    const char* e = getenv("B200MD_NEP_CVEC");
+    const bool cvec = !(e && e[0] == '0');
+    P.c_a4 = cvec ? reinterpret_cast<const float4*>(m.c_a4.data()) : nullptr;
+    P.c_r4 = cvec ? reinterpret_cast<const float4*>(m.c_r4.data()) : nullptr;
+    P.nqr = m.nqr;
+  }
   P.c_r = m.c_r.data(); P.c_a = m.c_a.data(); P.w0p = m.w0p.data(); P.b0 = m.b0.data();
   P.w1 = m.w1.data(); P.bias = m.bias.data(); P.q_scaler = m.q_scaler.data();
   P.zbl_z = p->zbl_z.data(); P.zbl_para = m.zbl_para.data(); P.cov_radius = p->cov.data();
