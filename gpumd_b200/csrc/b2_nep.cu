@@ -55,11 +55,26 @@ __global__ void __launch_bounds__(BLK)
 }
 
 template <int K1, int NCH>
-__global__ void __launch_bounds__(BLK) k_desc_angular(B2NepView P, B2Box box)
+__global__ void __launch_bounds__(BLK, 3) k_desc_angular(B2NepView P, B2Box box, int stage_rs4)
 {
+  // stage_rs4 > 0: every block first copies the padded angular coefficient table into shared memory,
+  // rows re-strided to stage_rs4 (odd) float4s.  With many types each lane reads a different
+  // (t1, t2) row: from shared memory that costs bank conflicts only, from L1 one wavefront per lane.
+  extern __shared__ float4 ctab_s[];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < P.n)
-    b2_body_desc_angular<K1, NCH>(i, P, box);
+  constexpr int KQ = (K1 + 3) / 4;
+  if (stage_rs4 > 0) {
+    const int row4 = P.na1 * KQ, tot = P.nt * P.nt * row4;
+    for (int e = threadIdx.x; e < tot; e += blockDim.x) {
+      const int r = e / row4;
+      ctab_s[r * stage_rs4 + (e - r * row4)] = P.c_a4[e];
+    }
+    __syncthreads();
+    if (i < P.n)
+      b2_body_desc_angular<K1, NCH>(i, P, box, ctab_s, stage_rs4);
+  } else if (i < P.n) {
+    b2_body_desc_angular<K1, NCH>(i, P, box, P.c_a4, P.na1 * KQ);
+  }
 }
 
 // One tile of MLP_BLK consecutive (cell-sorted) atoms per block.  The tile is counting-sorted by
@@ -331,6 +346,8 @@ struct b200md_nep {
   bool use_tc = false; // hidden layer on the tensor cores (k_mlp_tc) instead of k_mlp
   bool slot_map = false;  // k_force_final2: thread per tile slot (type-pure warps); measured slower
                           // (0.804 vs 0.736 ms, profiles/r01_f_ab.md), B200MD_NEP_SLOTMAP=1 for A/B runs
+  bool rad_reg = true;    // 3..16 types: radial accumulators in registers (k_desc_radial<4|8|16,...>)
+  bool ang_cstage = true; // k_desc_angular: coefficient table staged in shared memory
   bool radial_v2 = false; // few-type radial passes of b2_nep_radial.cuh (planes, branch-free loop)
   // small periodic boxes: supercell replication, see b200md_nep_compute
   DevBuf<int> rep_type;
@@ -396,12 +413,30 @@ int dispatch_desc_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
     return launch_desc_radial<1, K1, true>(p, box, st);
   } else if (p->model.nt == 2) {
     return launch_desc_radial<2, K1, true>(p, box, st);
-  } else if (p->fuse_split) {
-    return launch_desc_radial<0, K1, true>(p, box, st);
   } else {
-    k_split<<<grid_for(p->n, BLK), BLK, 0, st>>>(p->view, box);
-    B2_LAUNCHED();
-    return launch_desc_radial<0, K1, false>(p, box, st);
+    // 3..16 types: register accumulators when NT*K1 fits the register file (B200MD_NEP_RADREG=0
+    // keeps the shared-memory accumulators for A/B runs)
+    const int nt = p->model.nt;
+    const int ntb = !p->rad_reg ? 0 : nt <= 4 ? 4 : nt <= 8 ? 8 : nt <= 16 ? 16 : 0;
+    if (!p->fuse_split) {
+      k_split<<<grid_for(p->n, BLK), BLK, 0, st>>>(p->view, box);
+      B2_LAUNCHED();
+    }
+#define B2_DR(NT_)                                                 \
+  return p->fuse_split ? launch_desc_radial<NT_, K1, true>(p, box, st) \
+                       : launch_desc_radial<NT_, K1, false>(p, box, st)
+    if (ntb == 4)
+      B2_DR(4);
+    if constexpr (8 * K1 <= 160) {
+      if (ntb == 8)
+        B2_DR(8);
+    }
+    if constexpr (16 * K1 <= 160) {
+      if (ntb == 16)
+        B2_DR(16);
+    }
+    B2_DR(0);
+#undef B2_DR
   }
   B2_LAUNCHED();
   return B200MD_OK;
@@ -477,7 +512,18 @@ template <int K1>
 int launch_angular(const b200md_nep* p, const B2Box& box, cudaStream_t st, bool force)
 {
   if (!force) {
-    k_desc_angular<K1, 5><<<grid_for(p->n, BLK), BLK, 0, st>>>(p->view, box);
+    {
+      // shared-memory copy of the angular coefficients when three blocks of it fit an SM
+      // (B200MD_NEP_CSTAGE=0: read them from global memory)
+      constexpr int KQ = (K1 + 3) / 4;
+      const int rs4 = (p->model.na1 * KQ) | 1;
+      const size_t bytes = (size_t)p->model.nt * p->model.nt * rs4 * sizeof(float4);
+      const bool stage = p->view.c_a4 && p->ang_cstage && bytes <= 72 * 1024;
+      auto kern = k_desc_angular<K1, 5>;
+      if (stage && bytes > 48 * 1024)
+        B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+      kern<<<grid_for(p->n, BLK), BLK, stage ? bytes : 0, st>>>(p->view, box, stage ? rs4 : 0);
+    }
     B2_LAUNCHED();
     return B200MD_OK;
   }
@@ -642,6 +688,10 @@ int nep_setup(b200md_nep* p, int num_atoms)
                  (double)num_atoms * (mn_skin + 2) < 4.0e9; // 32-bit list offsets in those kernels
   if (const char* v = std::getenv("B200MD_NEP_SLOTMAP"))
     p->slot_map = std::atoi(v) != 0;
+  if (const char* v = std::getenv("B200MD_NEP_RADREG"))
+    p->rad_reg = std::atoi(v) != 0;
+  if (const char* v = std::getenv("B200MD_NEP_CSTAGE"))
+    p->ang_cstage = std::atoi(v) != 0;
   p->nb.tag_types = p->radial_v2; // skin entries carry the neighbour type (b2_nep_radial.cuh)
   if (p->radial_v2)
     B2_TRY(p->nb.enable_planes());

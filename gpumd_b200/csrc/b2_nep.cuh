@@ -269,8 +269,11 @@ B2_HD void b2_basis_d(float d, float rc, float rcinv, float* fn, float* fnp)
 
 // ---------------------------------------------------------------------------------------------
 // radial descriptor (radial half of find_descriptor, nep.cu:521-546)
-// NT > 0: per-type accumulators in registers (models with <= NT types); NT == 0: accumulators in
-// the caller-provided scratch `acc` laid out [(t2*K1+k)*stride + lane].
+// NT > 0: per-type accumulators in registers (models with <= NT types), updated with a 0/1 mask per
+// type -- NT*K1 FMAs per pair, which for 16 types x 9 functions is still only ~0.2 ms of FP32 issue
+// per million atoms and beats read-modify-write accumulators in shared memory (18 % occupancy,
+// 1.7 ms).  NT == 0: accumulators in the caller-provided scratch `acc` laid out
+// [(t2*K1+k)*stride + lane] (models with more than 16 types or NT*K1 > 160).
 // ---------------------------------------------------------------------------------------------
 // SPLIT = true fuses the neighbour-set split (b2_body_split) into this pass: the loop then walks
 // the skin list, applies the reference's two FP32 membership tests and emits the radial /
@@ -367,11 +370,28 @@ B2_HD void b2_body_desc_radial(
   }
   // contraction with the expansion coefficients
   const int qslot = P.qt ? P.tile_slot[i] : 0;
-  if (NT == 0 && P.c_r4) {
+  if ((NT == 0 || NT > 2) && P.c_r4) {
     // four radial channels per pass: one 128-bit coefficient load and one read of the accumulator
     // serve four FMAs; per channel the (t outer, k inner) summation order is the scalar path's
     for (int nq = 0; nq < P.nqr; ++nq) {
       float q0 = 0.0f, q1 = 0.0f, q2 = 0.0f, q3 = 0.0f;
+      if (NT > 2) {
+#pragma unroll
+        for (int t = 0; t < (NT > 0 ? NT : 1); ++t) {
+          if (t < P.nt) {
+            const float4* c4 = P.c_r4 + ((size_t)(t1 * P.nt + t) * P.nqr + nq) * K1;
+#pragma unroll
+            for (int k = 0; k < K1; ++k) {
+              const float av = S[t][k];
+              const float4 v = B2_LDG(&c4[k]);
+              q0 = fmaf(v.x, av, q0);
+              q1 = fmaf(v.y, av, q1);
+              q2 = fmaf(v.z, av, q2);
+              q3 = fmaf(v.w, av, q3);
+            }
+          }
+        }
+      } else
       for (int t = 0; t < P.nt; ++t) {
         const float4* c4 = P.c_r4 + ((size_t)(t1 * P.nt + t) * P.nqr + nq) * K1;
         const float* a = acc + (size_t)(t * K1) * stride + lane;
@@ -513,7 +533,10 @@ B2_HD void b2_harmonics_grad_dot(
 // NCH*24 accumulators stay in registers; each chunk walks the (short) angular list once.
 // ---------------------------------------------------------------------------------------------
 template <int K1, int NCH>
-B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
+// ctab / rs4: the padded angular coefficients c_a4 (B2NepView) and their row stride per type pair in
+// float4 units -- the global table (rs4 = na1*KQ) or the block's shared-memory copy; null: scalar loads
+B2_HD void b2_body_desc_angular(
+  int i, const B2NepView& P, const B2Box& box, const float4* ctab = nullptr, int rs4 = 0)
 {
   const float C3B[B2_NABC] = {B2_C3B_LIST};
   const B2Geo geo = b2_geo(box);
@@ -545,13 +568,13 @@ B2_HD void b2_body_desc_angular(int i, const B2NepView& P, const B2Box& box)
       for (int c = 0; c < NCH; ++c) {
         if (n0 + c < P.na1) {
           float g = 0.0f;
-          if (P.c_a4) {
+          if (ctab) {
             constexpr int KQ = (K1 + 3) / 4;
-            const float4* c4 = P.c_a4 + ((size_t)pair * P.na1 + (n0 + c)) * KQ;
+            const float4* c4 = ctab + (size_t)pair * rs4 + (n0 + c) * KQ;
             float ck[KQ * 4];
 #pragma unroll
             for (int q = 0; q < KQ; ++q) {
-              const float4 v = B2_LDG(&c4[q]);
+              const float4 v = c4[q];
               ck[4 * q] = v.x;
               ck[4 * q + 1] = v.y;
               ck[4 * q + 2] = v.z;

@@ -189,10 +189,30 @@ static void run_desc_radial(emu_nep* p, const B2Box& box)
       b2_body_desc_radial<1, K1, true>(i, p->P, box, scratch.data(), 1, 0);
     else if (p->m.nt == 2)
       b2_body_desc_radial<2, K1, true>(i, p->P, box, scratch.data(), 1, 0);
-    else if (p->fuse_split)
-      b2_body_desc_radial<0, K1, true>(i, p->P, box, scratch.data(), 1, 0);
-    else
-      b2_body_desc_radial<0, K1, false>(i, p->P, box, scratch.data(), 1, 0);
+    else {
+      // the library's choice (dispatch_desc_radial): register accumulators for 3..16 types
+      const char* e = getenv("B200MD_NEP_RADREG");
+      const int nt = p->m.nt;
+      int ntb = (e && e[0] == '0') ? 0 : nt <= 4 ? 4 : nt <= 8 ? 8 : nt <= 16 ? 16 : 0;
+      if (ntb * K1 > 160)
+        ntb = 0;
+#define EMU_DR(NT_)                                                                         \
+  do {                                                                                      \
+    if (p->fuse_split)                                                                      \
+      b2_body_desc_radial<NT_, K1, true>(i, p->P, box, scratch.data(), 1, 0);               \
+    else                                                                                    \
+      b2_body_desc_radial<NT_, K1, false>(i, p->P, box, scratch.data(), 1, 0);              \
+  } while (0)
+      if (ntb == 4)
+        EMU_DR(4);
+      else if (ntb == 8)
+        EMU_DR(8);
+      else if (ntb == 16)
+        EMU_DR(16);
+      else
+        EMU_DR(0);
+#undef EMU_DR
+    }
   }
 }
 template <int K1>
@@ -219,7 +239,7 @@ static void run_angular(emu_nep* p, const B2Box& box, bool force)
     if (force)
       b2_body_force_angular<K1, 1>(i, p->P, box, w.data(), 0);
     else
-      b2_body_desc_angular<K1, 5>(i, p->P, box);
+      b2_body_desc_angular<K1, 5>(i, p->P, box, p->P.c_a4, p->P.na1 * ((K1 + 3) / 4));
   }
 }
 template <int DIMP>
