@@ -346,7 +346,8 @@ struct b200md_nep {
   bool use_tc = false; // hidden layer on the tensor cores (k_mlp_tc) instead of k_mlp
   bool slot_map = false;  // k_force_final2: thread per tile slot (type-pure warps); measured slower
                           // (0.804 vs 0.736 ms, profiles/r01_f_ab.md), B200MD_NEP_SLOTMAP=1 for A/B runs
-  bool rad_reg = true;    // 3..16 types: radial accumulators in registers (k_desc_radial<4|8|16,...>)
+  bool rad_reg = false;   // 3..16 types: radial accumulators in registers (k_desc_radial<4|8|16,...>); measured
+                          // slower than the shared-memory accumulators on UNEP-v1 (2.86 vs 2.49 ms), B200MD_NEP_RADREG=1
   bool ang_cstage = true; // k_desc_angular: coefficient table staged in shared memory
   bool radial_v2 = false; // few-type radial passes of b2_nep_radial.cuh (planes, branch-free loop)
   // small periodic boxes: supercell replication, see b200md_nep_compute
@@ -414,8 +415,8 @@ int dispatch_desc_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
   } else if (p->model.nt == 2) {
     return launch_desc_radial<2, K1, true>(p, box, st);
   } else {
-    // 3..16 types: register accumulators when NT*K1 fits the register file (B200MD_NEP_RADREG=0
-    // keeps the shared-memory accumulators for A/B runs)
+    // 3..16 types: register accumulators when NT*K1 fits the register file are an opt-in
+    // (B200MD_NEP_RADREG=1); the default keeps the accumulators in shared memory
     const int nt = p->model.nt;
     const int ntb = !p->rad_reg ? 0 : nt <= 4 ? 4 : nt <= 8 ? 8 : nt <= 16 ? 16 : 0;
     if (!p->fuse_split) {
@@ -748,6 +749,8 @@ int nep_setup(b200md_nep* p, int num_atoms)
     P.c_a4 = cvec ? reinterpret_cast<const float4*>(p->c_a4.p) : nullptr;
     P.c_r4 = cvec ? reinterpret_cast<const float4*>(p->c_r4.p) : nullptr;
     P.nqr = m.nqr;
+    if (const char* d = getenv("B200MD_DEBUG_SKIP"))
+      P.debug_skip = atoi(d);
   }
   P.w0p = p->w0p.p;
   P.b0 = p->b0.p;

@@ -72,6 +72,7 @@ struct B2NepView {
   const float4* c_a4;    // [nt*nt][na1][(K1A+3)/4]: k = 4q .. 4q+3, zero-padded
   const float4* c_r4;    // [nt*nt][nqr][K1R]: n = 4*nq .. 4*nq+3 of basis function k, zero-padded
   int nqr;               // (nr1 + 3) / 4
+  int debug_skip;        // TIMING ONLY (B200MD_DEBUG_SKIP): 1 no radial sum, 2 no angular reduction, 4 no ZBL
   const float* w0p;      // [nt][nneu][DIMP] zero-padded rows
   const float* b0;       // [nt][nneu]
   const float* w1;       // [nt][nneu]
@@ -270,10 +271,9 @@ B2_HD void b2_basis_d(float d, float rc, float rcinv, float* fn, float* fnp)
 // ---------------------------------------------------------------------------------------------
 // radial descriptor (radial half of find_descriptor, nep.cu:521-546)
 // NT > 0: per-type accumulators in registers (models with <= NT types), updated with a 0/1 mask per
-// type -- NT*K1 FMAs per pair, which for 16 types x 9 functions is still only ~0.2 ms of FP32 issue
-// per million atoms and beats read-modify-write accumulators in shared memory (18 % occupancy,
-// 1.7 ms).  NT == 0: accumulators in the caller-provided scratch `acc` laid out
-// [(t2*K1+k)*stride + lane] (models with more than 16 types or NT*K1 > 160).
+// type -- NT*K1 FMAs per pair.  That is the default for 1 and 2 types; for 16 types x 9 functions it
+// needs 211 registers and was measured slower than NT == 0 (2.86 vs 2.49 ms per million UNEP atoms).
+// NT == 0: accumulators in the caller-provided scratch `acc` laid out [(t2*K1+k)*stride + lane].
 // ---------------------------------------------------------------------------------------------
 // SPLIT = true fuses the neighbour-set split (b2_body_split) into this pass: the loop then walks
 // the skin list, applies the reference's two FP32 membership tests and emits the radial /
@@ -1260,9 +1260,17 @@ B2_HD void b2_body_force_final(
     return; // ghost atom of a spatial domain
   float r[12], a[12], z[12];
   float zpe = 0.0f;
-  b2_force_radial_sum<NT, K1, DEPTH>(i, P, box, r);
-  b2_reduce_angular_sum(i, P, box, a);
-  if (P.zbl_enabled) {
+  if (!(P.debug_skip & 1))
+    b2_force_radial_sum<NT, K1, DEPTH>(i, P, box, r);
+  else
+    for (int k = 0; k < 12; ++k)
+      r[k] = 0.0f;
+  if (!(P.debug_skip & 2))
+    b2_reduce_angular_sum(i, P, box, a);
+  else
+    for (int k = 0; k < 12; ++k)
+      a[k] = 0.0f;
+  if (P.zbl_enabled && !(P.debug_skip & 4)) {
     b2_zbl_sum(i, P, box, z, zpe);
   } else {
 #pragma unroll

@@ -193,7 +193,7 @@ static void run_desc_radial(emu_nep* p, const B2Box& box)
       // the library's choice (dispatch_desc_radial): register accumulators for 3..16 types
       const char* e = getenv("B200MD_NEP_RADREG");
       const int nt = p->m.nt;
-      int ntb = (e && e[0] == '0') ? 0 : nt <= 4 ? 4 : nt <= 8 ? 8 : nt <= 16 ? 16 : 0;
+      int ntb = !(e && e[0] == '1') ? 0 : nt <= 4 ? 4 : nt <= 8 ? 8 : nt <= 16 ? 16 : 0;
       if (ntb * K1 > 160)
         ntb = 0;
 #define EMU_DR(NT_)                                                                         \
