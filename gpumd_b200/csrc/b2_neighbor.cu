@@ -164,6 +164,15 @@ __global__ void __launch_bounds__(128)
     b2_body_skin_list(i, v, box, g, cutoff2);
 }
 
+__global__ void __launch_bounds__(128) k_skin_reverse(B2NeighborView v)
+{
+  if (!v.flags[0])
+    return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < v.n)
+    b2_body_skin_reverse(i, v);
+}
+
 // ---- type tiles: stable counting sort of the sorted atoms by type, buckets padded to 128 ------
 // rank of this thread's atom among the same-type atoms of its block (ascending thread order);
 // leaves the per-warp counts in wcnt[warp][type]
@@ -332,6 +341,7 @@ B2NeighborView Neighbor::view() const
   v.plane1 = planes ? plane1.p : nullptr;
   v.planez = planes ? planez.p : nullptr;
   v.tag_types = tag_types ? 1 : 0;
+  v.rskin = reverse ? rskin.p : nullptr;
   v.snap = snap.p;
   v.perm = perm.p;
   v.perm_tmp = perm_tmp.p;
@@ -423,6 +433,10 @@ int Neighbor::update(
   B2_LAUNCHED();
   k_skin_list<<<grid_for(n, 128), 128, 0, st>>>(v, box, g, cutoff);
   B2_LAUNCHED();
+  if (reverse) {
+    k_skin_reverse<<<grid_for(n, 128), 128, 0, st>>>(v);
+    B2_LAUNCHED();
+  }
   if (tile_nt > 0) {
     k_tile_count<<<gn, BLK, 0, st>>>(v);
     B2_LAUNCHED();
@@ -442,6 +456,17 @@ int Neighbor::enable_planes()
   B2_CUDA(plane1.reserve(capacity));
   B2_CUDA(planez.reserve(capacity));
   planes = true;
+  return B200MD_OK;
+}
+
+int Neighbor::enable_reverse()
+{
+  if (skin_row_major || tag_types) {
+    set_error("enable_reverse: needs column-major, untagged skin lists");
+    return B200MD_ERR_ARG;
+  }
+  B2_CUDA(rskin.reserve((size_t)capacity * mn_skin));
+  reverse = true;
   return B200MD_OK;
 }
 

@@ -52,6 +52,10 @@ struct B2NeighborView {
                      // (si = 1, sk = n) for thread-per-atom kernels, row-major (si = pitch,
                      // sk = 1) for kernels that spread one atom's neighbours over lanes
   size_t skin_si = 1, skin_sk = 0;
+  // optional (Neighbor::enable_reverse, column-major untagged lists only): rskin[k*n + i] = the slot of
+  // atom i in the skin list of its k-th skin neighbour.  Built once per rebuild; lets a consumer that
+  // needs the partner's view of a pair (the angular force reduction) skip the per-step binary search.
+  int* rskin = nullptr;
   int* flags;        // [0] rebuild requested, [1] error bits, [2] rebuild counter
   // optional type tiles (Neighbor::enable_type_tiles): the sorted atoms bucketed by type, every
   // bucket padded to a multiple of 128 slots -- row blocks of the tensor-core hidden layer
@@ -246,3 +250,29 @@ B2_HD void b2_body_skin_list(
   }
   v.nn_skin[i] = count;
 }
+
+// ---- reverse slots of the skin list (the relation is symmetric: FP32 distances are exact mirror
+//      images under i <-> j) -------------------------------------------------------------------
+B2_HD void b2_body_skin_reverse(int i, const B2NeighborView& v)
+{
+  const size_t N = (size_t)v.n;
+  const int nn = v.nn_skin[i];
+  for (int k = 0; k < nn; ++k) {
+    const int j = v.nl_skin[(size_t)k * N + i];
+    int lo = 0, hi = v.nn_skin[j] - 1, rev = 0;
+    while (lo <= hi) { // j's list is ascending
+      const int mid = (lo + hi) >> 1;
+      const int v2 = v.nl_skin[(size_t)mid * N + j];
+      if (v2 < i)
+        lo = mid + 1;
+      else if (v2 > i)
+        hi = mid - 1;
+      else {
+        rev = mid;
+        break;
+      }
+    }
+    v.rskin[(size_t)k * N + i] = rev;
+  }
+}
+

@@ -36,6 +36,8 @@ public:
   DevBuf<double> snap;
   DevBuf<int> perm, perm_tmp, cell_of, order_tmp, cell_count, cell_fill, cell_start, nn_skin,
     nl_skin, flags;
+  DevBuf<int> rskin;    // see B2NeighborView::rskin (enable_reverse)
+  bool reverse = false;
   int tile_nt = 0; // type tiles (see B2NeighborView) are maintained when > 0
   DevBuf<int> tile_atom, tile_slot, tile_type, tile_blk, tile_meta;
 
@@ -45,6 +47,8 @@ public:
   int enable_type_tiles(int num_types);
   // also maintain the 16-byte planes of the sorted records (call after init)
   int enable_planes();
+  // also maintain the reverse slots of the skin list (column-major, untagged lists; call after init)
+  int enable_reverse();
   int max_tiles() const { return (n + 127) / 128 + tile_nt; }
   // Neighbor::find_neighbor_global, src/force/neighbor.cu:756-800 (fully asynchronous here)
   int update(const B2Box& box, const int* d_type, const double* d_pos, int n, cudaStream_t st);

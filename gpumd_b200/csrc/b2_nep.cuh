@@ -72,6 +72,14 @@ struct B2NepView {
   const float4* c_a4;    // [nt*nt][na1][(K1A+3)/4]: k = 4q .. 4q+3, zero-padded
   const float4* c_r4;    // [nt*nt][nqr][K1R]: n = 4*nq .. 4*nq+3 of basis function k, zero-padded
   int nqr;               // (nr1 + 3) / 4
+  // Direct reverse slots for the angular pair reduction (many-type path; null = binary search):
+  //   rskin  [mn_skin*n]  slot of i in the skin list of its k-th skin neighbour (per rebuild, b2_neighbor)
+  //   aslot  [mn_skin*n]  per step: angular slot of i's k-th skin neighbour, or -1
+  //   nla_rs [mn_a*n]     per step: rskin of the skin slot the m-th angular neighbour came from
+  // so the slot of i in j's angular list is aslot[nla_rs[m*n+i]*n + j].
+  const int* rskin;
+  int* aslot;
+  int* nla_rs;
   int debug_skip;        // TIMING ONLY (B200MD_DEBUG_SKIP): 1 no radial sum, 2 no angular reduction, 4 no ZBL
   const float* w0p;      // [nt][nneu][DIMP] zero-padded rows
   const float* b0;       // [nt][nneu]
@@ -163,6 +171,9 @@ B2_HD void b2_body_split(int i, const B2NepView& P, const B2Box& box)
   if (!b2_is_active(P, a1.x, a1.y, a1.z)) {
     P.nn_r[i] = 0;
     P.nn_a[i] = 0;
+    if (P.aslot)
+      for (int k = 0; k < P.nn_skin[i]; ++k)
+        P.aslot[(size_t)k * N + i] = -1;
     return;
   }
   const int nn = P.nn_skin[i];
@@ -183,16 +194,23 @@ B2_HD void b2_body_split(int i, const B2NepView& P, const B2Box& box)
     b2_r12(geo, box, a1, a2, x12, y12, z12);
     const float d2 = b2_d2(x12, y12, z12);
     const int pair = row + a2.type;
-    if (d2 >= B2_LDG(&P.rc2_r[pair]))
-      continue;
-    if (cr < P.mn_r)
-      P.nl_r[(size_t)cr * N + i] = j;
-    ++cr;
-    if (d2 < B2_LDG(&P.rc2_a[pair])) {
-      if (ca < P.mn_a)
-        P.nl_a[(size_t)ca * N + i] = j;
-      ++ca;
+    int as = -1; // angular slot of skin candidate k
+    if (d2 < B2_LDG(&P.rc2_r[pair])) {
+      if (cr < P.mn_r)
+        P.nl_r[(size_t)cr * N + i] = j;
+      ++cr;
+      if (d2 < B2_LDG(&P.rc2_a[pair])) {
+        if (ca < P.mn_a) {
+          P.nl_a[(size_t)ca * N + i] = j;
+          if (P.aslot)
+            P.nla_rs[(size_t)ca * N + i] = P.rskin[(size_t)k * N + i];
+          as = ca;
+        }
+        ++ca;
+      }
     }
+    if (P.aslot)
+      P.aslot[(size_t)k * N + i] = as;
   }
   if (cr > P.mn_r) {
     B2_ATOMIC_OR(&P.flags[1], (int)B2_ERR_RADIAL_OVERFLOW);
@@ -930,7 +948,9 @@ B2_HD void b2_force_radial_sum(int i, const B2NepView& P, const B2Box& box, floa
 // STRIDE = threads per block (compile-time so that the scratch offsets are immediates; the host
 // build of tests/emu uses 1)
 template <int K1, int STRIDE>
-B2_HD void b2_body_force_angular(int i, const B2NepView& P, const B2Box& box, float* w, int lane)
+B2_HD void b2_body_force_angular(
+  int i, const B2NepView& P, const B2Box& box, float* w, int lane, const float4* ctab = nullptr,
+  int rs4 = 0) // ctab / rs4 as in b2_body_desc_angular
 {
   constexpr size_t stride = STRIDE;
   const float C3B[B2_NABC] = {B2_C3B_LIST};
@@ -1016,13 +1036,13 @@ B2_HD void b2_body_force_angular(int i, const B2NepView& P, const B2Box& box, fl
     }
     for (int n = 0; n < P.na1; ++n) {
       float g = 0.0f, gp = 0.0f;
-      if (P.c_a4) {
+      if (ctab) {
         constexpr int KQ = (K1 + 3) / 4;
-        const float4* c4 = P.c_a4 + ((size_t)pair * P.na1 + n) * KQ;
+        const float4* c4 = ctab + (size_t)pair * rs4 + n * KQ;
         float ck[KQ * 4];
 #pragma unroll
         for (int q = 0; q < KQ; ++q) {
-          const float4 v = B2_LDG(&c4[q]);
+          const float4 v = c4[q];
           ck[4 * q] = v.x;
           ck[4 * q + 1] = v.y;
           ck[4 * q + 2] = v.z;
@@ -1101,17 +1121,24 @@ B2_HD void b2_reduce_angular_sum(
     double xd = a2.x - a1.x, yd = a2.y - a1.y, zd = a2.z - a1.z;
     b2_mic(box, xd, yd, zd); // potential.cu:211-217: FP64 minimum image, then narrowed
     const float r[3] = {(float)xd, (float)yd, (float)zd};
-    int lo = 0, hi = P.nn_a[j] - 1, rev = 0;
-    while (lo <= hi) {
-      const int mid = (lo + hi) >> 1;
-      const int v2 = P.nl_a[(size_t)mid * N + j];
-      if (v2 < i)
-        lo = mid + 1;
-      else if (v2 > i)
-        hi = mid - 1;
-      else {
-        rev = mid;
-        break;
+    int rev = 0;
+    if (P.aslot) {
+      // direct: j's angular slot for its skin neighbour i (same value the search below finds)
+      rev = P.aslot[(size_t)P.nla_rs[slot] * N + j];
+      rev = rev < 0 ? 0 : rev;
+    } else {
+      int lo = 0, hi = P.nn_a[j] - 1;
+      while (lo <= hi) {
+        const int mid = (lo + hi) >> 1;
+        const int v2 = P.nl_a[(size_t)mid * N + j];
+        if (v2 < i)
+          lo = mid + 1;
+        else if (v2 > i)
+          hi = mid - 1;
+        else {
+          rev = mid;
+          break;
+        }
       }
     }
     const size_t rslot = (size_t)rev * N + j;
@@ -1196,27 +1223,35 @@ B2_HD void b2_zbl_sum(
     const float dinv = 1.0f / d;
     const int ty2 = a2.type;
     const int zj = B2_LDG(&P.zbl_z[ty2]);
+    // Outer cutoff of this pair first: beyond it the switching function and its derivative are exactly
+    // zero, every contribution below is +-0 and the sums are unchanged -- so the four exponentials, the
+    // power and the sin/cos are skipped.  (The reference evaluates them and multiplies by zero.)
+    float para[10];
+    float rin = P.zbl_rc_inner, rout = P.zbl_rc_outer;
+    if (P.zbl_flexible) {
+      const int ta = ty1 < ty2 ? ty1 : ty2, tb = ty1 < ty2 ? ty2 : ty1;
+      const int zidx = ta * P.nt - (ta * (ta - 1)) / 2 + (tb - ta);
+#pragma unroll
+      for (int k = 0; k < 10; ++k)
+        para[k] = B2_LDG(&P.zbl_para[10 * zidx + k]);
+      rin = para[0];
+      rout = para[1];
+    } else if (P.zbl_typewise) {
+      const float tw =
+        (B2_LDG(&P.cov_radius[zi - 1]) + B2_LDG(&P.cov_radius[zj - 1])) * P.zbl_typewise_factor;
+      rout = fminf(tw, rout);
+      rin = 0.0f;
+    }
+    if (!(d < rout))
+      continue;
     const float a_inv = (pzi + powf((float)zj, 0.23f)) * 2.134563f;
     const float zizj = 14.399645f * (float)zi * (float)zj; // K_C_SP, common.cuh:23
     float fv, fpv;
     if (P.zbl_flexible) {
-      const int ta = ty1 < ty2 ? ty1 : ty2, tb = ty1 < ty2 ? ty2 : ty1;
-      const int zidx = ta * P.nt - (ta * (ta - 1)) / 2 + (tb - ta);
-      float para[10];
-#pragma unroll
-      for (int k = 0; k < 10; ++k)
-        para[k] = B2_LDG(&P.zbl_para[10 * zidx + k]);
-      b2_zbl_pair(para + 2, para[0], para[1], zizj, a_inv, d, dinv, fv, fpv);
+      b2_zbl_pair(para + 2, rin, rout, zizj, a_inv, d, dinv, fv, fpv);
     } else {
       const float uni[8] = {0.18175f, 3.1998f, 0.50986f, 0.94229f,
                             0.28022f, 0.4029f, 0.02817f, 0.20162f};
-      float rin = P.zbl_rc_inner, rout = P.zbl_rc_outer;
-      if (P.zbl_typewise) {
-        const float tw =
-          (B2_LDG(&P.cov_radius[zi - 1]) + B2_LDG(&P.cov_radius[zj - 1])) * P.zbl_typewise_factor;
-        rout = fminf(tw, rout);
-        rin = 0.0f;
-      }
       b2_zbl_pair(uni, rin, rout, zizj, a_inv, d, dinv, fv, fpv);
     }
     const float f2 = fpv * dinv * 0.5f; // f12 = r12 * f2, f21 = -f12

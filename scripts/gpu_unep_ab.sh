@@ -9,6 +9,8 @@ mkdir -p gpurun_out
 echo "== parity (NEP cases)"
 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_reference_properties.py -q -x -p no:cacheprovider -k "nep or golden or propert or invarian or consisten" > gpurun_out/${T}_pytest.txt 2>&1
 tail -3 gpurun_out/${T}_pytest.txt
+timeout 600 python -m pytest tests/test_gpu_mgpu.py -q -x -p no:cacheprovider -k "many_types or single_point" > gpurun_out/${T}_pytest_mgpu.txt 2>&1
+tail -3 gpurun_out/${T}_pytest_mgpu.txt
 run() { # workload label envs extra-args
   local w=$1 c=$2; shift 2
   local label=${c%%:*} envs=${c#*:}

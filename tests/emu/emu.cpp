@@ -64,7 +64,8 @@ struct EmuNeighbor {
   std::vector<B2Atom> atoms, atoms_tmp;
   std::vector<double> snap;
   std::vector<int> perm, perm_tmp, cell_of, order_tmp, cell_count, cell_fill, cell_start, nn_skin,
-    nl_skin, flags;
+    nl_skin, flags, rskin;
+  bool reverse = false; // mirrors Neighbor::enable_reverse
   B2NeighborView v;
   int rebuilds = 0;
   bool row_major = false; // mirrors Neighbor::skin_row_major
@@ -86,6 +87,8 @@ struct EmuNeighbor {
     order_tmp.resize(n);
     nn_skin.resize(n);
     nl_skin.resize((size_t)pitch() * n);
+    if (reverse)
+      rskin.assign((size_t)pitch() * n, 0);
     flags.assign(4, 0);
     flags[0] = 1;
   }
@@ -118,6 +121,7 @@ struct EmuNeighbor {
     v.cell_start = cell_start.data();
     v.nn_skin = nn_skin.data();
     v.nl_skin = nl_skin.data();
+    v.rskin = reverse ? rskin.data() : nullptr;
     v.skin_si = row_major ? (size_t)pitch() : 1;
     v.skin_sk = row_major ? 1 : (size_t)n;
     v.flags = flags.data();
@@ -148,6 +152,9 @@ struct EmuNeighbor {
         b2_body_commit(i, v);
       for (int i = 0; i < n; ++i)
         b2_body_skin_list(i, v, box, g, cutoff);
+      if (reverse)
+        for (int i = 0; i < n; ++i)
+          b2_body_skin_reverse(i, v);
       flags[0] = 0;
       flags[2]++;
     }
@@ -170,6 +177,8 @@ struct emu_nep {
   std::vector<float> cov;
   B2NepView P;
   bool team = false, fuse_split = false; // same choices as nep_setup() in b2_nep.cu
+  bool rev_slot = false;
+  std::vector<int> aslot, nla_rs;
   int n_cell = 0;                        // atoms of the caller's cell (n > n_cell: supercell)
 };
 
@@ -237,7 +246,7 @@ static void run_angular(emu_nep* p, const B2Box& box, bool force)
   std::vector<float> w((size_t)p->m.na1 * B2_NABC + 1);
   for (int i = 0; i < p->n; ++i) {
     if (force)
-      b2_body_force_angular<K1, 1>(i, p->P, box, w.data(), 0);
+      b2_body_force_angular<K1, 1>(i, p->P, box, w.data(), 0, p->P.c_a4, p->P.na1 * ((K1 + 3) / 4));
     else
       b2_body_desc_angular<K1, 5>(i, p->P, box, p->P.c_a4, p->P.na1 * ((K1 + 3) / 4));
   }
@@ -264,7 +273,16 @@ static void emu_nep_alloc(emu_nep* p, int n)
   p->team = m.nt <= 2 && team_env && std::strcmp(team_env, "1") == 0;
   p->fuse_split = rs * rs * rs / (rc * rc * rc) < 1.45;
   p->nb.row_major = p->team;
+  {
+    const char* e = std::getenv("B200MD_NEP_REVSLOT");
+    p->rev_slot = m.nt > 2 && !p->team && !p->fuse_split && !(e && e[0] == '0');
+    p->nb.reverse = p->rev_slot;
+  }
   p->nb.init(n, rc, (int)(m.MN_radial * rs * rs * rs / (rc * rc * rc)));
+  if (p->rev_slot) {
+    p->aslot.assign((size_t)p->nb.pitch() * n, -1);
+    p->nla_rs.assign(N * m.MN_angular, 0);
+  }
   const int pitch_r = (m.MN_radial + 7) / 8 * 8;
   p->nn_r.resize(N);
   p->nl_r.resize(N * pitch_r);
@@ -304,6 +322,8 @@ static void emu_nep_alloc(emu_nep* p, int n)
   P.zbl_z = p->zbl_z.data(); P.zbl_para = m.zbl_para.data(); P.cov_radius = p->cov.data();
   P.n = n; P.mn_r = m.MN_radial; P.mn_a = m.MN_angular;
   P.nn_r = p->nn_r.data(); P.nl_r = p->nl_r.data(); P.nn_a = p->nn_a.data(); P.nl_a = p->nl_a.data();
+  P.aslot = p->rev_slot ? p->aslot.data() : nullptr;
+  P.nla_rs = p->rev_slot ? p->nla_rs.data() : nullptr;
   P.q = p->q.data(); P.sfx = p->sfx.data(); P.FpR = p->FpR.data(); P.FpA = p->FpA.data(); P.U = p->U.data();
   P.f12 = p->f12.data(); P.acc = p->acc.data();
   P.team = p->team ? 1 : 0;
@@ -397,6 +417,7 @@ static int emu_nep_pipeline(
   P.perm = p->nb.perm.data();
   P.nn_skin = p->nb.nn_skin.data();
   P.nl_skin = p->nb.nl_skin.data();
+  P.rskin = p->rev_slot ? p->nb.rskin.data() : nullptr;
   P.skin_si = p->nb.v.skin_si;
   P.skin_sk = p->nb.v.skin_sk;
   P.flags = p->nb.flags.data();

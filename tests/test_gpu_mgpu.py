@@ -51,6 +51,25 @@ def test_blocks_match_the_oracle_single_point(oracle, mg, grid):
     assert abs(th[1] - r["pe"].sum()) < 1e-6 * n
 
 
+@pytest.mark.parametrize("grid", [(2, 1, 1), (2, 2, 1)])
+def test_blocks_match_the_oracle_many_types(oracle, mg, grid):
+    """The many-type kernels (UNEP-v1: 16 species, ZBL, separate neighbour split, direct reverse slots in the
+    angular reduction) inside block domains: ghosts outside the active region must not disturb them."""
+    from gpumd_b200.structures import nep_type_order
+    model = GOLDEN / "nep_UNEP_v1.txt"
+    s = fcc((10, 10, 8), 3.9, rattle=0.08, seed=5, num_types=16, symbols=nep_type_order(model))  # 39 A: 19.5 A blocks > 13 A halo
+    n = s["type"].shape[0]
+    g = mg.DomainGroup(s["h"], s["pbc"], grid, model)
+    g.distribute(s["type"], s["pos"], s["mass"])
+    out = g.gather_local()
+    assert np.array_equal(out["id"], np.arange(n))
+    orc = oracle.NepOracle(model)
+    r = orc.compute(s["type"], s["h"], s["pbc"], s["pos"], precision=32)
+    r64 = orc.compute(s["type"], s["h"], s["pbc"], s["pos"], precision=64)
+    check_fv(out, r, gap_f=np.abs(r["force"] - r64["force"]).max(), gap_v=np.abs(r["virial"] - r64["virial"]).max())
+    assert abs(out["pe"].sum() - r["pe"].sum()) / n < 1e-6
+
+
 @pytest.mark.parametrize("ensemble", ["nve", "nvt_nhc"])
 def test_blocks_follow_the_single_domain_trajectory(oracle, mg, ensemble):
     """200 steps on 2x2x2 blocks vs one domain (same library, no decomposition), then the state against
