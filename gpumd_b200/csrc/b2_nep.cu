@@ -226,27 +226,15 @@ __global__ void __launch_bounds__(BLK, MINB)
 }
 
 template <int K1, int NTHR>
-__global__ void __launch_bounds__(NTHR) k_force_angular(B2NepView P, B2Box box, int stage_rs4)
+__global__ void __launch_bounds__(NTHR) k_force_angular(B2NepView P, B2Box box)
 {
-  // dyn_smem: [NTHR * na1 * 24] per-thread weights dU/ds, then (stage_rs4 > 0) the block's copy of the
-  // padded angular coefficient table with rows of stage_rs4 float4s (see k_desc_angular)
-  extern __shared__ float4 dyn_smem4[];
-  float* dyn_smem = reinterpret_cast<float*>(dyn_smem4);
+  // (a shared-memory copy of the coefficient table as in k_desc_angular needs 256-thread blocks to fit
+  // next to the weights; measured on UNEP-v1: 2.47 vs 2.47 ms, and the second code path cost the
+  // few-type case 0.03 ms -- not kept)
+  extern __shared__ float dyn_smem[];
   const int i = blockIdx.x * NTHR + threadIdx.x;
-  constexpr int KQ = (K1 + 3) / 4;
-  if (stage_rs4 > 0) {
-    float4* ctab_s = dyn_smem4 + (size_t)NTHR * P.na1 * B2_NABC / 4;
-    const int row4 = P.na1 * KQ, tot = P.nt * P.nt * row4;
-    for (int e = threadIdx.x; e < tot; e += NTHR) {
-      const int r = e / row4;
-      ctab_s[r * stage_rs4 + (e - r * row4)] = P.c_a4[e];
-    }
-    __syncthreads();
-    if (i < P.n)
-      b2_body_force_angular<K1, NTHR>(i, P, box, dyn_smem, threadIdx.x, ctab_s, stage_rs4);
-  } else if (i < P.n) {
-    b2_body_force_angular<K1, NTHR>(i, P, box, dyn_smem, threadIdx.x, P.c_a4, P.na1 * KQ);
-  }
+  if (i < P.n)
+    b2_body_force_angular<K1, NTHR>(i, P, box, dyn_smem, threadIdx.x, P.c_a4, P.na1 * ((K1 + 3) / 4));
 }
 
 // parity hooks ---------------------------------------------------------------------------------
@@ -377,7 +365,6 @@ struct b200md_nep {
   B2NepView view;
   StageProfiler prof;
   int ang_block = BLK;
-  bool fa_stage = false; // k_force_angular: 256 threads per block + staged coefficient table
   size_t ang_smem = 0, rad_smem = 0;
 };
 
@@ -553,20 +540,15 @@ int launch_angular(const b200md_nep* p, const B2Box& box, cudaStream_t st, bool 
     B2_LAUNCHED();
     return B200MD_OK;
   }
-  void (*kern)(B2NepView, B2Box, int) = k_force_angular<K1, 128>;
-  if (p->ang_block == 256)
-    kern = k_force_angular<K1, 256>;
-  else if (p->ang_block == 64)
+  void (*kern)(B2NepView, B2Box) = k_force_angular<K1, 128>;
+  if (p->ang_block == 64)
     kern = k_force_angular<K1, 64>;
   else if (p->ang_block == 32)
     kern = k_force_angular<K1, 32>;
-  constexpr int KQ = (K1 + 3) / 4;
-  const int rs4 = p->fa_stage ? ((p->model.na1 * KQ) | 1) : 0;
-  const size_t smem =
-    p->ang_smem + (size_t)p->model.nt * p->model.nt * rs4 * sizeof(float4);
-  if (smem > 48 * 1024)
-    B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<grid_for(p->n, p->ang_block), p->ang_block, smem, st>>>(p->view, box, rs4);
+  if (p->ang_smem > 48 * 1024)
+    B2_CUDA(cudaFuncSetAttribute(
+      kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)p->ang_smem));
+  kern<<<grid_for(p->n, p->ang_block), p->ang_block, p->ang_smem, st>>>(p->view, box);
   B2_LAUNCHED();
   return B200MD_OK;
 }
@@ -727,11 +709,13 @@ int nep_setup(b200md_nep* p, int num_atoms)
   if (p->radial_v2)
     B2_TRY(p->nb.enable_planes());
   const int pitch_r = (m.MN_radial + 7) / 8 * 8;
-  // many types with the neighbour split as its own kernel: direct reverse slots for the angular pair
-  // reduction instead of a binary search per pair (B200MD_NEP_REVSLOT=0 for A/B runs)
+  // B200MD_NEP_REVSLOT=1 (many types with the neighbour split as its own kernel): direct reverse slots
+  // for the angular pair reduction instead of a binary search per pair.  Measured on UNEP-v1
+  // (profiles/r01_f_ab.md): k_force_final 2.99 -> 2.81 ms, but the extra stores make k_split 0.34 ms
+  // slower, so it stays an opt-in.
   {
     const char* e = std::getenv("B200MD_NEP_REVSLOT");
-    p->rev_slot = m.nt > 2 && !team && !p->fuse_split && !(e && e[0] == '0');
+    p->rev_slot = m.nt > 2 && !team && !p->fuse_split && e && e[0] == '1';
     if (p->rev_slot) {
       B2_TRY(p->nb.enable_reverse());
       B2_CUDA(p->aslot.reserve(N * (size_t)mn_skin));
@@ -874,18 +858,6 @@ int nep_setup(b200md_nep* p, int num_atoms)
   while (p->ang_smem > 200 * 1024 && p->ang_block > 32) {
     p->ang_block /= 2;
     p->ang_smem = (size_t)m.na1 * B2_NABC * p->ang_block * sizeof(float);
-  }
-  // B200MD_NEP_FA_STAGE=1: 256 threads per block so that one block's weights plus a shared-memory copy
-  // of the angular coefficient table fit an SM (for A/B runs on many-type models)
-  p->fa_stage = false;
-  if (const char* e = std::getenv("B200MD_NEP_FA_STAGE")) {
-    const size_t w256 = (size_t)m.na1 * B2_NABC * 256 * sizeof(float);
-    const size_t ctab = (size_t)m.nt * m.nt * (((size_t)m.na1 * ((m.K1A + 3) / 4)) | 1) * sizeof(float4);
-    if (e[0] == '1' && p->view.c_a4 && w256 + ctab <= 200 * 1024) {
-      p->fa_stage = true;
-      p->ang_block = 256;
-      p->ang_smem = w256;
-    }
   }
   p->rad_smem = (size_t)m.nt * m.K1R * BLK * sizeof(float);
   if (m.nt > 2 && p->rad_smem > 200 * 1024) {

@@ -275,7 +275,7 @@ static void emu_nep_alloc(emu_nep* p, int n)
   p->nb.row_major = p->team;
   {
     const char* e = std::getenv("B200MD_NEP_REVSLOT");
-    p->rev_slot = m.nt > 2 && !p->team && !p->fuse_split && !(e && e[0] == '0');
+    p->rev_slot = m.nt > 2 && !p->team && !p->fuse_split && e && e[0] == '1';
     p->nb.reverse = p->rev_slot;
   }
   p->nb.init(n, rc, (int)(m.MN_radial * rs * rs * rs / (rc * rc * rc)));
