@@ -531,7 +531,7 @@ int launch_angular(const b200md_nep* p, const B2Box& box, cudaStream_t st, bool 
       constexpr int KQ = (K1 + 3) / 4;
       const int rs4 = (p->model.na1 * KQ) | 1;
       const size_t bytes = (size_t)p->model.nt * p->model.nt * rs4 * sizeof(float4);
-      const bool stage = p->view.c_a4 && p->ang_cstage && bytes <= 72 * 1024;
+      const bool stage = p->ang_cstage && bytes <= 72 * 1024;
       auto kern = k_desc_angular<K1, 5>;
       if (stage && bytes > 48 * 1024)
         B2_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
@@ -770,10 +770,11 @@ int nep_setup(b200md_nep* p, int num_atoms)
   P.c_r = p->c_r.p;
   P.c_a = p->c_a.p;
   {
-    // B200MD_NEP_CVEC=0: scalar coefficient loads (A/B switch; results are bit-identical)
+    // B200MD_NEP_CVEC=0: scalar coefficient loads in the radial contraction (A/B switch; results are
+    // bit-identical).  The angular kernels always use the padded rows.
     const char* e = getenv("B200MD_NEP_CVEC");
     const bool cvec = !(e && e[0] == '0');
-    P.c_a4 = cvec ? reinterpret_cast<const float4*>(p->c_a4.p) : nullptr;
+    P.c_a4 = reinterpret_cast<const float4*>(p->c_a4.p);
     P.c_r4 = cvec ? reinterpret_cast<const float4*>(p->c_r4.p) : nullptr;
     P.nqr = m.nqr;
     if (const char* d = getenv("B200MD_DEBUG_SKIP"))

@@ -69,8 +69,9 @@ struct B2NepView {
   // the same coefficients padded for 128-bit loads (null: scalar loads).  With many types every lane
   // of a warp reads a different (t1, t2) row, so each load instruction costs one L1 wavefront per
   // lane; four coefficients per instruction cut that cost by four.
-  const float4* c_a4;    // [nt*nt][na1][(K1A+3)/4]: k = 4q .. 4q+3, zero-padded
-  const float4* c_r4;    // [nt*nt][nqr][K1R]: n = 4*nq .. 4*nq+3 of basis function k, zero-padded
+  const float4* c_a4;    // [nt*nt][na1][(K1A+3)/4]: k = 4q .. 4q+3, zero-padded (always set)
+  const float4* c_r4;    // [nt*nt][nqr][K1R]: n = 4*nq .. 4*nq+3 of basis function k, zero-padded; null:
+                         // scalar loads in the radial contraction (B200MD_NEP_CVEC=0)
   int nqr;               // (nr1 + 3) / 4
   // Direct reverse slots for the angular pair reduction (many-type path; null = binary search):
   //   rskin  [mn_skin*n]  slot of i in the skin list of its k-th skin neighbour (per rebuild, b2_neighbor)
@@ -552,9 +553,9 @@ B2_HD void b2_harmonics_grad_dot(
 // ---------------------------------------------------------------------------------------------
 template <int K1, int NCH>
 // ctab / rs4: the padded angular coefficients c_a4 (B2NepView) and their row stride per type pair in
-// float4 units -- the global table (rs4 = na1*KQ) or the block's shared-memory copy; null: scalar loads
+// float4 units -- the global table (rs4 = na1*KQ) or the block's shared-memory copy
 B2_HD void b2_body_desc_angular(
-  int i, const B2NepView& P, const B2Box& box, const float4* ctab = nullptr, int rs4 = 0)
+  int i, const B2NepView& P, const B2Box& box, const float4* ctab, int rs4)
 {
   const float C3B[B2_NABC] = {B2_C3B_LIST};
   const B2Geo geo = b2_geo(box);
@@ -586,27 +587,20 @@ B2_HD void b2_body_desc_angular(
       for (int c = 0; c < NCH; ++c) {
         if (n0 + c < P.na1) {
           float g = 0.0f;
-          if (ctab) {
-            constexpr int KQ = (K1 + 3) / 4;
-            const float4* c4 = ctab + (size_t)pair * rs4 + (n0 + c) * KQ;
-            float ck[KQ * 4];
+          constexpr int KQ = (K1 + 3) / 4;
+          const float4* c4 = ctab + (size_t)pair * rs4 + (n0 + c) * KQ;
+          float ck[KQ * 4];
 #pragma unroll
-            for (int q = 0; q < KQ; ++q) {
-              const float4 v = c4[q];
-              ck[4 * q] = v.x;
-              ck[4 * q + 1] = v.y;
-              ck[4 * q + 2] = v.z;
-              ck[4 * q + 3] = v.w;
-            }
-#pragma unroll
-            for (int k = 0; k < K1; ++k)
-              g = fmaf(fn[k], ck[k], g);
-          } else {
-            const float* cc = P.c_a + ((size_t)pair * P.na1 + (n0 + c)) * K1;
-#pragma unroll
-            for (int k = 0; k < K1; ++k)
-              g = fmaf(fn[k], B2_LDG(&cc[k]), g);
+          for (int q = 0; q < KQ; ++q) {
+            const float4 v = c4[q];
+            ck[4 * q] = v.x;
+            ck[4 * q + 1] = v.y;
+            ck[4 * q + 2] = v.z;
+            ck[4 * q + 3] = v.w;
           }
+#pragma unroll
+          for (int k = 0; k < K1; ++k)
+            g = fmaf(fn[k], ck[k], g);
 #pragma unroll
           for (int abc = 0; abc < B2_NABC; ++abc)
             s[c][abc] = fmaf(g, B[abc], s[c][abc]);
@@ -949,8 +943,8 @@ B2_HD void b2_force_radial_sum(int i, const B2NepView& P, const B2Box& box, floa
 // build of tests/emu uses 1)
 template <int K1, int STRIDE>
 B2_HD void b2_body_force_angular(
-  int i, const B2NepView& P, const B2Box& box, float* w, int lane, const float4* ctab = nullptr,
-  int rs4 = 0) // ctab / rs4 as in b2_body_desc_angular
+  int i, const B2NepView& P, const B2Box& box, float* w, int lane, const float4* ctab,
+  int rs4) // ctab / rs4 as in b2_body_desc_angular
 {
   constexpr size_t stride = STRIDE;
   const float C3B[B2_NABC] = {B2_C3B_LIST};
@@ -1036,31 +1030,21 @@ B2_HD void b2_body_force_angular(
     }
     for (int n = 0; n < P.na1; ++n) {
       float g = 0.0f, gp = 0.0f;
-      if (ctab) {
-        constexpr int KQ = (K1 + 3) / 4;
-        const float4* c4 = ctab + (size_t)pair * rs4 + n * KQ;
-        float ck[KQ * 4];
+      constexpr int KQ = (K1 + 3) / 4;
+      const float4* c4 = ctab + (size_t)pair * rs4 + n * KQ;
+      float ck[KQ * 4];
 #pragma unroll
-        for (int q = 0; q < KQ; ++q) {
-          const float4 v = c4[q];
-          ck[4 * q] = v.x;
-          ck[4 * q + 1] = v.y;
-          ck[4 * q + 2] = v.z;
-          ck[4 * q + 3] = v.w;
-        }
+      for (int q = 0; q < KQ; ++q) {
+        const float4 v = c4[q];
+        ck[4 * q] = v.x;
+        ck[4 * q + 1] = v.y;
+        ck[4 * q + 2] = v.z;
+        ck[4 * q + 3] = v.w;
+      }
 #pragma unroll
-        for (int k = 0; k < K1; ++k) {
-          g = fmaf(fn[k], ck[k], g);
-          gp = fmaf(fnp[k], ck[k], gp);
-        }
-      } else {
-        const float* cc = P.c_a + ((size_t)pair * P.na1 + n) * K1;
-#pragma unroll
-        for (int k = 0; k < K1; ++k) {
-          const float ck = B2_LDG(&cc[k]);
-          g = fmaf(fn[k], ck, g);
-          gp = fmaf(fnp[k], ck, gp);
-        }
+      for (int k = 0; k < K1; ++k) {
+        g = fmaf(fn[k], ck[k], g);
+        gp = fmaf(fnp[k], ck[k], gp);
       }
       const float* wn = w + (size_t)(n * B2_NABC) * stride + lane;
 #pragma unroll

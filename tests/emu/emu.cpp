@@ -313,7 +313,7 @@ static void emu_nep_alloc(emu_nep* p, int n)
   {
     const char* e = getenv("B200MD_NEP_CVEC");
     const bool cvec = !(e && e[0] == '0');
-    P.c_a4 = cvec ? reinterpret_cast<const float4*>(m.c_a4.data()) : nullptr;
+    P.c_a4 = reinterpret_cast<const float4*>(m.c_a4.data());
     P.c_r4 = cvec ? reinterpret_cast<const float4*>(m.c_r4.data()) : nullptr;
     P.nqr = m.nqr;
   }
