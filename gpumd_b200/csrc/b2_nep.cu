@@ -777,8 +777,12 @@ int nep_setup(b200md_nep* p, int num_atoms)
     P.c_a4 = reinterpret_cast<const float4*>(p->c_a4.p);
     P.c_r4 = cvec ? reinterpret_cast<const float4*>(p->c_r4.p) : nullptr;
     P.nqr = m.nqr;
-    if (const char* d = getenv("B200MD_DEBUG_SKIP"))
+    if (const char* d = getenv("B200MD_DEBUG_SKIP")) {
       P.debug_skip = atoi(d);
+      if (P.debug_skip)
+        fprintf(stderr, "libb200md: B200MD_DEBUG_SKIP=%d -- parts of the NEP force are SWITCHED OFF "
+                        "(kernel timing only, results are wrong)\n", P.debug_skip);
+    }
   }
   P.w0p = p->w0p.p;
   P.b0 = p->b0.p;
