@@ -72,6 +72,21 @@ def test_nep_matches_oracle(oracle, eng, case, mlp, team, monkeypatch):
     check_nep(oracle, GpuNep(eng, model, n), model, s, n)
 
 
+@pytest.mark.parametrize("switch", ["B200MD_NEP_REVSLOT", "B200MD_NEP_RADREG"])
+def test_many_type_opt_ins_are_bit_identical(oracle, eng, switch, monkeypatch):
+    """UNEP-v1 (16 types) through the opt-in many-type paths (direct reverse slots in the angular pair
+    reduction; radial accumulators in registers): oracle parity and bit-identical with the default path."""
+    from test_kernel_bodies_cpu import check_nep
+    model, make = NEP_CASES["UNEP"]
+    s = make()
+    n = s["type"].shape[0]
+    monkeypatch.setenv(switch, "1")
+    out = check_nep(oracle, GpuNep(eng, model, n), model, s, n)
+    monkeypatch.delenv(switch)
+    ref = GpuNep(eng, model, n).compute(s["type"], s["h"], s["pbc"], s["pos"])[1]
+    assert np.array_equal(out["force"], ref["force"]) and np.array_equal(out["virial"], ref["virial"])
+
+
 def test_nep_accumulates_and_is_deterministic(oracle, eng):
     import torch
     s = rocksalt_pbte(4, rattle=0.05, seed=1)

@@ -71,6 +71,21 @@ def test_nep_bodies_match_oracle(oracle, emu, case, team, monkeypatch):
     check_nep(oracle, dev, model, s, n)
 
 
+@pytest.mark.parametrize("switch", ["B200MD_NEP_REVSLOT", "B200MD_NEP_RADREG"])
+@pytest.mark.parametrize("case", ["UNEP", "BaZrO3"])
+def test_many_type_opt_ins_match_oracle(oracle, emu, case, switch, monkeypatch):
+    """The many-type opt-in paths (direct reverse slots in the angular pair reduction; radial accumulators
+    in registers) produce the same results as the defaults (measured slower, kept as A/B switches)."""
+    monkeypatch.setenv(switch, "1")
+    model, make = NEP_CASES[case]
+    s = make()
+    n = s["type"].shape[0]
+    out = check_nep(oracle, emu.nep(GOLDEN / model, n), model, s, n)
+    monkeypatch.delenv(switch)
+    ref = emu.nep(GOLDEN / model, n).compute(s["type"], s["h"], s["pbc"], s["pos"])[1]
+    assert np.array_equal(out["force"], ref["force"]) and np.array_equal(out["virial"], ref["virial"])
+
+
 def test_nep_accumulates_into_outputs(oracle, emu):
     """Potential::compute contract: outputs are += (nep.cu:653,755-770)."""
     s = rocksalt_pbte(4, rattle=0.05, seed=1)
