@@ -68,6 +68,7 @@ static inline unsigned b2_team_ballot(bool p) { return p ? 1u : 0u; }
 
 // Box passed by value to kernels: GPUMD's Box::cpu_h / float_h (src/model/box.cuh:18-35).
 constexpr int B2_MAX_TYPES = 94; // NUM_ELEMENTS, src/utilities/common.cuh:18
+constexpr int B2_NQMAX = 5;      // radial channels in groups of four: up to n_max_radial = 19
 
 struct B2Box {
   double h[18]; // h[0..8] row-major (lattice vectors are columns), h[9..17] inverse

@@ -351,6 +351,7 @@ struct b200md_nep {
   bool use_tc = false; // hidden layer on the tensor cores (k_mlp_tc) instead of k_mlp
   bool slot_map = false;  // k_force_final2: thread per tile slot (type-pure warps); measured slower
                           // (0.804 vs 0.736 ms, profiles/r01_f_ab.md), B200MD_NEP_SLOTMAP=1 for A/B runs
+  bool rad_direct = false; // many types: contract every pair on the spot (k_desc_radial<-1,...>), see nep_setup
   bool rad_reg = false;   // 3..16 types: radial accumulators in registers (k_desc_radial<4|8|16,...>); measured
                           // slower than the shared-memory accumulators on UNEP-v1 (2.86 vs 2.49 ms), B200MD_NEP_RADREG=1
   bool ang_cstage = true; // k_desc_angular: coefficient table staged in shared memory
@@ -431,6 +432,8 @@ int dispatch_desc_radial(const b200md_nep* p, const B2Box& box, cudaStream_t st)
 #define B2_DR(NT_)                                                 \
   return p->fuse_split ? launch_desc_radial<NT_, K1, true>(p, box, st) \
                        : launch_desc_radial<NT_, K1, false>(p, box, st)
+    if (p->rad_direct)
+      B2_DR(-1);
     if (ntb == 4)
       B2_DR(4);
     if constexpr (8 * K1 <= 160) {
@@ -864,10 +867,23 @@ int nep_setup(b200md_nep* p, int num_atoms)
     p->ang_block /= 2;
     p->ang_smem = (size_t)m.na1 * B2_NABC * p->ang_block * sizeof(float);
   }
+  // Radial descriptor of a many-type model: per-type accumulators in shared memory while two blocks of
+  // them fit an SM, else (NEP89: 89 species) the per-pair contraction, which needs no such storage.
+  // B200MD_NEP_RADDIRECT=1 forces the latter for any model with more than two types (tests, A/B).
   p->rad_smem = (size_t)m.nt * m.K1R * BLK * sizeof(float);
-  if (m.nt > 2 && p->rad_smem > 200 * 1024) {
-    set_error("too many atom types for the shared-memory radial accumulators");
-    return B200MD_ERR_ARG;
+  p->rad_direct = false;
+  if (m.nt > 2) {
+    const char* e = std::getenv("B200MD_NEP_RADDIRECT");
+    const bool forced = e && e[0] == '1';
+    if (forced || p->rad_smem > 96 * 1024) {
+      if (m.nqr > B2_NQMAX) {
+        set_error("n_max_radial above 19 is not supported for models with this many atom types");
+        return B200MD_ERR_ARG;
+      }
+      p->rad_direct = true;
+      p->rad_smem = 0;
+      P.c_r4 = reinterpret_cast<const float4*>(p->c_r4.p); // regardless of B200MD_NEP_CVEC
+    }
   }
   B2_CUDA(cudaDeviceSynchronize());
   return B200MD_OK;

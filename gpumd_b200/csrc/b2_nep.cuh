@@ -72,7 +72,7 @@ struct B2NepView {
   const float4* c_a4;    // [nt*nt][na1][(K1A+3)/4]: k = 4q .. 4q+3, zero-padded (always set)
   const float4* c_r4;    // [nt*nt][nqr][K1R]: n = 4*nq .. 4*nq+3 of basis function k, zero-padded; null:
                          // scalar loads in the radial contraction (B200MD_NEP_CVEC=0)
-  int nqr;               // (nr1 + 3) / 4
+  int nqr;               // (nr1 + 3) / 4  (<= B2_NQMAX)
   // Direct reverse slots for the angular pair reduction (many-type path; null = binary search):
   //   rskin  [mn_skin*n]  slot of i in the skin list of its k-th skin neighbour (per rebuild, b2_neighbor)
   //   aslot  [mn_skin*n]  per step: angular slot of i's k-th skin neighbour, or -1
@@ -293,6 +293,9 @@ B2_HD void b2_basis_d(float d, float rc, float rcinv, float* fn, float* fnp)
 // type -- NT*K1 FMAs per pair.  That is the default for 1 and 2 types; for 16 types x 9 functions it
 // needs 211 registers and was measured slower than NT == 0 (2.86 vs 2.49 ms per million UNEP atoms).
 // NT == 0: accumulators in the caller-provided scratch `acc` laid out [(t2*K1+k)*stride + lane].
+// NT < 0: no per-type accumulators at all -- every pair is contracted with c[t1,t2,n,k] on the spot (45 FMAs
+// and K1 128-bit coefficient loads per pair for n_max = 4, K = 8).  Costs more per pair but needs no
+// storage that grows with the number of types: the path for models like NEP89 (89 species).
 // ---------------------------------------------------------------------------------------------
 // SPLIT = true fuses the neighbour-set split (b2_body_split) into this pass: the loop then walks
 // the skin list, applies the reference's two FP32 membership tests and emits the radial /
@@ -317,15 +320,20 @@ B2_HD void b2_body_desc_radial(
   const int* list = SPLIT ? P.nl_skin : P.nl_r;
   int cr = 0, ca = 0;
   float S[NT > 0 ? NT : 1][K1];
+  float Q[B2_NQMAX][4]; // NT < 0: the descriptor components themselves, four per register group
   if (NT > 0) {
 #pragma unroll
     for (int t = 0; t < (NT > 0 ? NT : 1); ++t)
 #pragma unroll
       for (int k = 0; k < K1; ++k)
         S[t][k] = 0.0f;
-  } else {
+  } else if (NT == 0) {
     for (int m = 0; m < P.nt * K1; ++m)
       acc[(size_t)m * stride + lane] = 0.0f;
+  } else {
+#pragma unroll
+    for (int nq = 0; nq < B2_NQMAX; ++nq)
+      Q[nq][0] = Q[nq][1] = Q[nq][2] = Q[nq][3] = 0.0f;
   }
   int jn = nn > 0 ? B2_LDCS(&list[i]) : i;
   B2Atom an = b2_load_atom(&P.atoms[jn]);
@@ -368,11 +376,33 @@ B2_HD void b2_body_desc_radial(
         for (int k = 0; k < K1; ++k)
           S[t][k] = fmaf(m, fn[k], S[t][k]);
       }
-    } else {
+    } else if (NT == 0) {
       float* a = acc + (size_t)(t2 * K1) * stride + lane;
 #pragma unroll
       for (int k = 0; k < K1; ++k)
         a[(size_t)k * stride] += fn[k];
+    } else {
+      // per-pair contraction, the reference's own order (find_descriptor, nep.cu:521-546):
+      // g_n = sum_k fn_k c[t1,t2,n,k], then q_n += g_n
+#pragma unroll
+      for (int nq = 0; nq < B2_NQMAX; ++nq) {
+        if (nq < P.nqr) {
+          const float4* c4 = P.c_r4 + ((size_t)pair * P.nqr + nq) * K1;
+          float g0 = 0.0f, g1 = 0.0f, g2 = 0.0f, g3 = 0.0f;
+#pragma unroll
+          for (int k = 0; k < K1; ++k) {
+            const float4 v = B2_LDG(&c4[k]);
+            g0 = fmaf(fn[k], v.x, g0);
+            g1 = fmaf(fn[k], v.y, g1);
+            g2 = fmaf(fn[k], v.z, g2);
+            g3 = fmaf(fn[k], v.w, g3);
+          }
+          Q[nq][0] += g0;
+          Q[nq][1] += g1;
+          Q[nq][2] += g2;
+          Q[nq][3] += g3;
+        }
+      }
     }
   }
   if (SPLIT) {
@@ -389,6 +419,15 @@ B2_HD void b2_body_desc_radial(
   }
   // contraction with the expansion coefficients
   const int qslot = P.qt ? P.tile_slot[i] : 0;
+  if (NT < 0) {
+#pragma unroll
+    for (int nq = 0; nq < B2_NQMAX; ++nq)
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (4 * nq + c < P.nr1)
+          *b2_q_ptr(P, i, qslot, 4 * nq + c) = Q[nq][c];
+    return;
+  }
   if ((NT == 0 || NT > 2) && P.c_r4) {
     // four radial channels per pass: one 128-bit coefficient load and one read of the accumulator
     // serve four FMAs; per channel the (t outer, k inner) summation order is the scalar path's

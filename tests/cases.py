@@ -58,6 +58,25 @@ NEP_CASES = {
 }
 
 
+def _random_alloy(model, cells, a, seed):
+    """fcc lattice with the species of `model` drawn i.i.d. (masses are irrelevant for single points)."""
+    s = fcc(cells, a, rattle=0.08, seed=seed)
+    order = nep_type_order(GOLDEN / model)
+    s["type"] = np.random.default_rng(seed).integers(0, len(order), s["type"].shape[0]).astype(np.int32)
+    s["symbols"] = order
+    return s
+
+
+# synthetic models (tests/golden/make_synthetic_models.py) for paths no shipped model reaches
+NEP_CASES_SYNTH = {
+    # 50 species: beyond the shared-memory radial accumulators -> per-pair contraction (the NEP89 situation)
+    "synth50": ("nep_synth_50types.txt", lambda: _random_alloy("nep_synth_50types.txt", 5, 4.2, 9)),
+    # `cutoff` line in its 2*Nt+2 form: per-type radial / angular cutoffs, pair cutoff = mean of the two
+    "pertype_cutoff": ("nep_synth_pertype_cutoff.txt",
+                       lambda: _random_alloy("nep_synth_pertype_cutoff.txt", 5, 4.0, 10)),
+}
+
+
 def _golden_static():
     order = nep_type_order(GOLDEN / "nep_PbTe_static.txt")
     return read_xyz(GOLDEN / "gpumd_static_model.xyz", order)

@@ -205,6 +205,12 @@ static void run_desc_radial(emu_nep* p, const B2Box& box)
       int ntb = !(e && e[0] == '1') ? 0 : nt <= 4 ? 4 : nt <= 8 ? 8 : nt <= 16 ? 16 : 0;
       if (ntb * K1 > 160)
         ntb = 0;
+      {
+        // nep_setup()'s rule: the per-pair contraction when the shared-memory accumulators get too big
+        const char* d = getenv("B200MD_NEP_RADDIRECT");
+        if ((d && d[0] == '1') || (size_t)nt * K1 * 128 * sizeof(float) > 96 * 1024)
+          ntb = -1;
+      }
 #define EMU_DR(NT_)                                                                         \
   do {                                                                                      \
     if (p->fuse_split)                                                                      \
@@ -212,7 +218,9 @@ static void run_desc_radial(emu_nep* p, const B2Box& box)
     else                                                                                    \
       b2_body_desc_radial<NT_, K1, false>(i, p->P, box, scratch.data(), 1, 0);              \
   } while (0)
-      if (ntb == 4)
+      if (ntb == -1)
+        EMU_DR(-1);
+      else if (ntb == 4)
         EMU_DR(4);
       else if (ntb == 8)
         EMU_DR(8);
@@ -314,7 +322,9 @@ static void emu_nep_alloc(emu_nep* p, int n)
     const char* e = getenv("B200MD_NEP_CVEC");
     const bool cvec = !(e && e[0] == '0');
     P.c_a4 = reinterpret_cast<const float4*>(m.c_a4.data());
-    P.c_r4 = cvec ? reinterpret_cast<const float4*>(m.c_r4.data()) : nullptr;
+    const char* d = getenv("B200MD_NEP_RADDIRECT");
+    const bool direct = m.nt > 2 && ((d && d[0] == '1') || (size_t)m.nt * m.K1R * 128 * sizeof(float) > 96 * 1024);
+    P.c_r4 = (cvec || direct) ? reinterpret_cast<const float4*>(m.c_r4.data()) : nullptr;
     P.nqr = m.nqr;
   }
   P.c_r = m.c_r.data(); P.c_a = m.c_a.data(); P.w0p = m.w0p.data(); P.b0 = m.b0.data();

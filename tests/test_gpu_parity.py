@@ -72,6 +72,23 @@ def test_nep_matches_oracle(oracle, eng, case, mlp, team, monkeypatch):
     check_nep(oracle, GpuNep(eng, model, n), model, s, n)
 
 
+@pytest.mark.parametrize("case", ["synth50", "pertype_cutoff", "UNEP_direct"])
+def test_many_species_and_per_type_cutoffs(oracle, eng, case, monkeypatch):
+    """50 species (radial descriptor by per-pair contraction, k_desc_radial<-1,...>: the path a model like the
+    reference's 89-species NEP89 takes), the per-type form of the `cutoff` line, and the per-pair contraction
+    forced on UNEP-v1 (16 species, ZBL)."""
+    from cases import NEP_CASES_SYNTH
+    from test_kernel_bodies_cpu import check_nep
+    if case == "UNEP_direct":
+        monkeypatch.setenv("B200MD_NEP_RADDIRECT", "1")
+        model, make = NEP_CASES["UNEP"]
+    else:
+        model, make = NEP_CASES_SYNTH[case]
+    s = make()
+    n = s["type"].shape[0]
+    check_nep(oracle, GpuNep(eng, model, n), model, s, n)
+
+
 @pytest.mark.parametrize("switch", ["B200MD_NEP_REVSLOT", "B200MD_NEP_RADREG"])
 def test_many_type_opt_ins(oracle, eng, switch, monkeypatch):
     """UNEP-v1 (16 types) through the opt-in many-type paths: oracle parity, and agreement with the default

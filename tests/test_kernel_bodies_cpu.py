@@ -6,7 +6,7 @@ tolerances."""
 import numpy as np
 import pytest
 
-from cases import NEP_CASES
+from cases import NEP_CASES, NEP_CASES_SYNTH
 from conftest import GOLDEN, TOL, assert_close
 from gpumd_b200.structures import fcc, rocksalt_pbte
 
@@ -69,6 +69,26 @@ def test_nep_bodies_match_oracle(oracle, emu, case, team, monkeypatch):
     n = s["type"].shape[0]
     dev = emu.nep(GOLDEN / model, n)
     check_nep(oracle, dev, model, s, n)
+
+
+@pytest.mark.parametrize("case", list(NEP_CASES_SYNTH))
+def test_synthetic_models_match_oracle(oracle, emu, case):
+    """50 species (radial descriptor by per-pair contraction, the path a model like NEP89 takes) and the
+    per-type `cutoff` form."""
+    model, make = NEP_CASES_SYNTH[case]
+    s = make()
+    n = s["type"].shape[0]
+    check_nep(oracle, emu.nep(GOLDEN / model, n), model, s, n)
+
+
+@pytest.mark.parametrize("case", ["UNEP", "BaZrO3"])
+def test_per_pair_radial_contraction_matches_oracle(oracle, emu, case, monkeypatch):
+    """B200MD_NEP_RADDIRECT=1 forces k_desc_radial<-1,...>'s body on the shipped many-type models."""
+    monkeypatch.setenv("B200MD_NEP_RADDIRECT", "1")
+    model, make = NEP_CASES[case]
+    s = make()
+    n = s["type"].shape[0]
+    check_nep(oracle, emu.nep(GOLDEN / model, n), model, s, n)
 
 
 @pytest.mark.parametrize("switch", ["B200MD_NEP_REVSLOT", "B200MD_NEP_RADREG"])

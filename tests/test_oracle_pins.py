@@ -49,7 +49,8 @@ def test_bazro3_golden_regression(oracle, precision):
 
 
 @pytest.mark.parametrize("model,structure", [
-    ("nep_PbTe_static.txt", "static"), ("nep_BaZrO3.txt", "bazro3"), ("nep_PbTe.txt", "c1")])
+    ("nep_PbTe_static.txt", "static"), ("nep_BaZrO3.txt", "bazro3"), ("nep_PbTe.txt", "c1"),
+    ("nep_synth_50types.txt", "synth50")])
 def test_oracle_matches_reference_nep_cpu(oracle, model, structure):
     """FP64 restatement vs the reference's own NEP_CPU compiled from /root/reference (oracle/_ref).
     Differences come only from NEP_CPU keeping the parameters in double while the GPU reference
@@ -61,6 +62,9 @@ def test_oracle_matches_reference_nep_cpu(oracle, model, structure):
         s = read_xyz(GOLDEN / "gpumd_static_model.xyz", order)
     elif structure == "bazro3":
         s = read_xyz(GOLDEN / "BaZrO3-nat40-rattled.xyz", order)
+    elif structure == "synth50":  # 50 random species (tests/golden/make_synthetic_models.py)
+        from cases import NEP_CASES_SYNTH
+        s = NEP_CASES_SYNTH["synth50"][1]()
     else:  # config C1: 216-atom rocksalt PbTe, rattle 0.05 A, seed 1
         s = rocksalt_pbte(3, rattle=0.05, seed=1)
     ref = oracle.RefNepCpu(GOLDEN / model).compute(s["type"], s["h"], s["pos"])
