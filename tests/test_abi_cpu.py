@@ -24,6 +24,20 @@ def test_library_exports_every_declared_symbol(b200md_lib):
         assert hasattr(L, n), f"{n} declared in b200md.h but not exported"
 
 
+def test_mgpu_library_exports_every_declared_symbol(b200md_lib):
+    """include/b200md_mgpu.h <-> libb200md_mgpu.so (C++ / CUDA / NCCL domain module) <-> gpumd_b200/mgpu.py."""
+    from gpumd_b200 import build
+    text = (ROOT / "include" / "b200md_mgpu.h").read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = sorted(set(re.findall(r"\b(b200md_mgpu_[a-z_0-9]+)\s*\(", text)))
+    assert len(names) >= 14
+    so = build.build_mgpu()
+    C.CDLL(str(b200md_lib), mode=C.RTLD_GLOBAL)
+    L = C.CDLL(str(so))
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in b200md_mgpu.h but not exported"
+
+
 def test_library_targets_sm_100a(b200md_lib):
     import subprocess
     out = subprocess.run(["cuobjdump", "-lelf", str(b200md_lib)], capture_output=True, text=True).stdout
